@@ -1,0 +1,139 @@
+"""TEST INFRASTRUCTURE -- not product code.
+
+Loads the UNMODIFIED reference sources from /root/reference and runs them on
+the torch-CPU `tensorflow` shim (oracle/tf_shim).  Only usable inside the build
+container (the GPU box has no /root/reference): used by oracle/make_golden.py
+to generate tests/golden/*.npz and by the CPU tests marked `reference`.
+
+Nothing is copied: whole modules are imported from where they lie, and the
+pieces of s_net_bundle_nobm.py / train_bundle_nobm.py that cannot be imported
+(they build a ResNet on tf.contrib at import time) are pulled out of the parsed
+AST *by name / name_scope* and exec'd verbatim.
+"""
+import ast
+import contextlib
+import importlib
+import io
+import os
+import sys
+
+REF = os.environ.get('MGW_REFERENCE_DIR', '/root/reference')
+_SHIM = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'tf_shim')
+
+
+def available():
+    return os.path.isfile(os.path.join(REF, 'spatial_transformer3.py'))
+
+
+@contextlib.contextmanager
+def _paths():
+    added = [_SHIM, REF]
+    for p in added:
+        sys.path.insert(0, p)
+    try:
+        yield
+    finally:
+        for p in added:
+            sys.path.remove(p)
+
+
+def tf():
+    with _paths():
+        import tensorflow          # the shim
+    assert getattr(tensorflow, 'NAMED', None) is not None, 'a real tensorflow shadowed the shim'
+    return tensorflow
+
+
+def _import(name):
+    with _paths(), contextlib.redirect_stdout(io.StringIO()):
+        return importlib.import_module(name)
+
+
+def st3(height, width, grid_h, grid_w):
+    """reference spatial_transformer3 with its config globals set (spatial_transformer3.py:16)."""
+    m = _import('spatial_transformer3')
+    m.height, m.width, m.grid_h, m.grid_w = height, width, grid_h, grid_w
+    return m
+
+
+def st1():
+    m = _import('spatial_transformer')
+    # the reference also imports spatial_transformer3 under `from spatial_transformer import *`
+    return m
+
+
+def quiet(fn, *a, **k):
+    """the operator prints at call time (spatial_transformer3.py:224-226,274-276,297-300)."""
+    with contextlib.redirect_stdout(io.StringIO()):
+        return fn(*a, **k)
+
+
+def _parse(fname):
+    with open(os.path.join(REF, fname)) as f:
+        src = f.read()
+    return ast.parse(src, filename=fname)
+
+
+def _scope_name(node):
+    """'x' for `with tf.name_scope('x'):` nodes, else None."""
+    if not isinstance(node, ast.With) or len(node.items) != 1:
+        return None
+    call = node.items[0].context_expr
+    if isinstance(call, ast.Call) and getattr(call.func, 'attr', None) == 'name_scope' and call.args \
+            and isinstance(call.args[0], ast.Constant):
+        return call.args[0].value
+    return None
+
+
+def _exec_nodes(nodes, ns, fname):
+    mod = ast.Module(body=list(nodes), type_ignores=[])
+    with contextlib.redirect_stdout(io.StringIO()):
+        exec(compile(mod, os.path.join(REF, fname), 'exec'), ns)   # noqa: S102
+    return ns
+
+
+def s_net_namespace(height, width, grid_h, grid_w, batch_size, max_matches, do_crop_rate=0.8):
+    """get_4_pts / warp_pts of s_net_bundle_nobm.py:29-71,215-230 as callables."""
+    tree = _parse('s_net_bundle_nobm.py')
+    ns = dict(tf=tf(), height=height, width=width, grid_h=grid_h, grid_w=grid_w,
+              batch_size=batch_size, max_matches=max_matches, do_crop_rate=do_crop_rate)
+    wanted = [n for n in tree.body if isinstance(n, ast.FunctionDef) and n.name in ('get_4_pts', 'warp_pts')]
+    assert len(wanted) == 2
+    return _exec_nodes(wanted, ns, 's_net_bundle_nobm.py')
+
+
+def s_net_losses(ns, matches, mask, flow, h_trans, y, black_pix):
+    """feature_loss and img_loss blocks of inference_stable_net (s_net_bundle_nobm.py:335-352)."""
+    tree = _parse('s_net_bundle_nobm.py')
+    fn = [n for n in tree.body if isinstance(n, ast.FunctionDef) and n.name == 'inference_stable_net'][0]
+    outer = [n for n in fn.body if isinstance(n, ast.With)][0]          # with tf.variable_scope('stable_net')
+    blocks = [n for n in outer.body if _scope_name(n) in ('feature_loss', 'img_loss')]
+    assert len(blocks) == 2
+    ns = dict(ns)
+    ns.update(matches=matches, mask=mask, flow=flow, h_trans=h_trans, y=y, black_pix=black_pix)
+    t = ns['tf']
+    saved = t.placeholder
+    t.placeholder = lambda *a, **k: None                                # use_feature_loss placeholder is unused
+    try:
+        _exec_nodes(blocks, ns, 's_net_bundle_nobm.py')
+    finally:
+        t.placeholder = saved
+    return ns['feature_loss'], ns['img_loss'], ns['stable_warpped']
+
+
+def train_temp_loss(height, width, batch_size, ret1, ret2, flow, use_temp_loss=1.0):
+    """temp_loss block of train_bundle_nobm.py:115-125 (interpolate from spatial_transformer.py)."""
+    tree = _parse('train_bundle_nobm.py')
+    block = [n for n in tree.body if _scope_name(n) == 'temp_loss']
+    assert len(block) == 1
+    t = tf()
+    ns = dict(tf=t, height=height, width=width, batch_size=batch_size, ret1=ret1, ret2=ret2,
+              interpolate=st1().interpolate, show_image=lambda *a, **k: None,
+              x_flow=flow[..., 0:1], y_flow=flow[..., 1:2])
+    saved = t.placeholder
+    t.placeholder = lambda *a, **k: use_temp_loss
+    try:
+        _exec_nodes(block, ns, 'train_bundle_nobm.py')
+    finally:
+        t.placeholder = saved
+    return ns['temp_loss']

@@ -1,0 +1,141 @@
+"""CPU: pin both oracles (oracle/mgw_oracle.c, oracle/mesh_warp_ref.py) to the golden vectors, which are
+outputs of the unmodified reference sources (oracle/make_golden.py)."""
+import numpy as np
+import pytest
+import torch
+
+import c_oracle
+import mesh_warp_ref as ref
+from conftest import (MESH_CASES, SMALL_MESH_CASES, bits_equal, golden_black, golden_inputs, load_golden, relmax)
+
+
+@pytest.mark.parametrize('name', MESH_CASES)
+def test_c_oracle_pixel_stage_bit_exact(name):
+    """given the reference's Hs: x_map/y_map, black_pix, output_img reproduce the reference BIT FOR BIT."""
+    g = load_golden(name)
+    U, _, _ = golden_inputs(name, g)
+    out, black, img, cell = c_oracle.warp(U, g['ref_Hs'])
+    assert bits_equal(img, g['ref_img']).all()
+    assert (black == golden_black(g)).all()
+    assert bits_equal(out, g['ref_out']).all()
+    gh, gw = g['grid']
+    assert cell.min() == 0 and cell.max() == gh * gw - 1
+
+
+@pytest.mark.parametrize('name', MESH_CASES)
+def test_c_oracle_solve_h(name):
+    """the 8x8 solve is LAPACK-shaped, not LAPACK: |dH| <= 1e-5 abs and no worse vs fp64 than 2x the reference."""
+    g = load_golden(name)
+    Hc = c_oracle.solve_h(g['theta'])
+    assert np.abs(Hc - g['ref_Hs']).max() < 1e-5
+    assert (Hc[..., 8] == 1).all()
+    if 'f64_Hs' in g:
+        H64 = c_oracle.solve_h(g['theta'], f64=True)
+        assert np.abs(H64 - g['f64_Hs']).max() < 1e-6
+        assert np.abs(Hc - g['f64_Hs']).max() <= 2 * np.abs(g['ref_Hs'] - g['f64_Hs']).max() + 1e-6
+
+
+@pytest.mark.parametrize('name', SMALL_MESH_CASES)
+def test_torch_port_forward_and_grads(name):
+    g = load_golden(name)
+    U, d_out, d_img = golden_inputs(name, g)
+    Ut = torch.tensor(U, requires_grad=True)
+    th = torch.tensor(g['theta'], requires_grad=True)
+    out, black, img, Hs = ref.transformer(Ut, th)
+    Hs.retain_grad()
+    ((out * torch.tensor(d_out)).sum() + (img * torch.tensor(d_img)).sum()).backward()
+    # same LAPACK behind torch.linalg.inv as the shim used -> Hs identical, everything downstream ~bit-exact
+    assert np.abs(Hs.detach().numpy() - g['ref_Hs']).max() < 1e-6
+    fin = np.isfinite(g['ref_out']).all(-1) & (np.abs(g['ref_img']).max(-1) < 1e3)
+    assert (black.numpy() == golden_black(g))[fin].all()
+    assert np.abs(out.detach().numpy() - g['ref_out'])[fin].max() < 1e-5
+    if name != 'mesh_fold_clamp_shift':       # a folded cell has z -> 0 pixels: gradients there are garbage in the reference too
+        assert relmax(Ut.grad.numpy(), g['ref_dU']) < 1e-4
+        assert relmax(th.grad.numpy(), g['ref_dtheta']) < 1e-4
+        assert relmax(Hs.grad.numpy()[..., :8], g['ref_dHs'][..., :8]) < 1e-4
+
+
+@pytest.mark.parametrize('name', SMALL_MESH_CASES[:5])
+def test_torch_port_fp64_arbiter(name):
+    g = load_golden(name)
+    U, d_out, d_img = golden_inputs(name, g)
+    Ut = torch.tensor(U, dtype=torch.float64, requires_grad=True)
+    th = torch.tensor(g['theta'], dtype=torch.float64, requires_grad=True)
+    out, black, img, Hs = ref.transformer(Ut, th)
+    ((out * torch.tensor(d_out, dtype=torch.float64)).sum() + (img * torch.tensor(d_img, dtype=torch.float64)).sum()).backward()
+    assert np.abs(Hs.detach().numpy() - g['f64_Hs']).max() < 1e-9
+    assert relmax(th.grad.numpy(), g['f64_dtheta']) < 1e-8
+    assert relmax(Ut.grad.numpy(), g['f64_dU']) < 1e-8
+
+
+@pytest.mark.parametrize('name', ['homog_s05', 'homog_c1_s10'])
+def test_homography_oracles(name):
+    g = load_golden(name)
+    n, h, w, c = g['U'].shape
+    out, black, _ = c_oracle.homography_warp(g['U'], g['theta'], (h, w))
+    assert bits_equal(out, g['ref_out']).all()
+    assert (black == g['ref_black']).all()
+    Ut = torch.tensor(g['U'], requires_grad=True)
+    th = torch.tensor(g['theta'], requires_grad=True)
+    o, b = ref.transformer_homography(Ut, th, (h, w))
+    (o * torch.tensor(g['d_out'])).sum().backward()
+    assert np.abs(o.detach().numpy() - g['ref_out']).max() < 1e-6
+    assert relmax(Ut.grad.numpy(), g['ref_dU']) < 1e-5
+    assert relmax(th.grad.numpy(), g['ref_dtheta']) < 1e-4
+
+
+@pytest.mark.parametrize('name', ['interp_same', 'interp_resize_c1'])
+def test_interp_oracles(name):
+    g = load_golden(name)
+    oh, ow = g['x'].shape[1:3]
+    out = c_oracle.interp(g['im'], g['x'], g['y'], (oh, ow))
+    assert bits_equal(out, g['ref_out']).all()
+    it = torch.tensor(g['im'], requires_grad=True)
+    xt = torch.tensor(g['x'], requires_grad=True)
+    yt = torch.tensor(g['y'], requires_grad=True)
+    o = ref.interpolate(it, xt, yt, (oh, ow))
+    (o * torch.tensor(g['d_out'])).sum().backward()
+    assert bits_equal(o.detach().numpy(), g['ref_out']).all()
+    assert relmax(it.grad.numpy(), g['ref_dim']) < 1e-5
+    assert relmax(xt.grad.numpy(), g['ref_dx']) < 1e-5
+    assert relmax(yt.grad.numpy(), g['ref_dy']) < 1e-5
+
+
+def test_losses_and_vertices_oracles():
+    g = load_golden('losses')
+    gh, gw = (int(v) for v in g['grid'])
+    n, h, w, _ = g['x1'].shape
+    p1, p2 = c_oracle.vertices(g['head'], gh, gw)
+    assert bits_equal(p1, g['ref_pts1']).all() and bits_equal(p2, g['ref_pts2']).all()
+    hd = torch.tensor(g['head'], requires_grad=True)
+    hd2 = torch.tensor(g['head2'], requires_grad=True)
+    pts1, pts2 = ref.get_4_pts(hd, gh, gw)
+    _, pts2b = ref.get_4_pts(hd2, gh, gw)
+    assert bits_equal(pts1.detach().numpy(), g['ref_pts1']).all()
+    out1, black1, img1, _ = ref.transformer(torch.tensor(g['x1']), pts2)
+    out2, black2, img2, _ = ref.transformer(torch.tensor(g['x2']), pts2b)
+    fl, warpped = ref.feature_loss(torch.tensor(g['matches']), torch.tensor(g['mask']), img1)
+    il = ref.img_loss(out1, torch.tensor(g['y1']), black1)
+    tl = ref.temp_loss(out1, black1, out2, black2, torch.tensor(g['flow']))
+    for nm, l in (('feature', fl), ('img', il), ('temp', tl)):
+        assert abs(float(l) - float(g['ref_%s_loss' % nm])) <= 1e-5 * max(1.0, abs(float(g['ref_%s_loss' % nm]))), nm
+        gr = torch.autograd.grad(l, [hd, hd2], retain_graph=True, allow_unused=True)
+        for k, t in (('dhead', gr[0]), ('dhead2', gr[1])):
+            want = g['ref_%s_%s' % (k, nm)]
+            got = np.zeros_like(want) if t is None else t.numpy()
+            if np.abs(want).max() > 0:
+                assert relmax(got, want) < 2e-4, (nm, k)
+            else:
+                assert np.abs(got).max() == 0
+
+
+@pytest.mark.reference
+def test_golden_is_reference_output():
+    """regenerate one fixture from /root/reference and compare with the committed file."""
+    import make_golden
+    import synth
+    name, fx = make_golden.mesh_case('mesh_smooth_s03', synth.smooth_image(2, 48, 64, 3, 10),
+                                     synth.random_mesh(2, 4, 4, 0.03, 11), 4, 4, 10, f64=False)
+    g = load_golden(name)
+    for k in ('ref_Hs', 'ref_out', 'ref_img', 'ref_dtheta', 'ref_dU'):
+        assert bits_equal(fx[k], g[k]).all(), k
