@@ -1,0 +1,281 @@
+#!/usr/bin/env python
+"""Benchmark of the multi-grid warp hot path (BASELINE.json: warp Mpix/s fwd & fwd+bwd; achieved HBM GB/s).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]          # B200 arm (one process per GPU under torchrun)
+    python bench.py --impl reference [...]                       # the reference arm: CPU port on the host cores
+
+A step = one forward + backward of spatial_transformer3.transformer over one batch of synthetic frames at
+BASELINE.json configs[1]: 32 x 288 x 512 x 3 fp32 per GPU, 4x4 mesh (weak scaling: every rank gets its own 32).
+Rank 0 prints ONE JSON line.  See DESIGN.md "Measurement" for how every field is obtained.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for _p in (ROOT, os.path.join(ROOT, 'oracle')):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+import numpy as np   # noqa: E402
+import torch         # noqa: E402
+
+H, W, C, GH, GW = 288, 512, 3, 4, 4
+FWD_BYTES_PER_PX = 8 * C + 12      # read U 4C, write out 4C, black 4, x/y maps 8        
+BWD_BYTES_PER_PX = 12 * C + 8      # read d_out 4C, U 4C, write dU 4C, read d_img 8
+METRIC = 'warp_fwd_bwd_mpix_per_s'
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, 'MEASURED_PEAKS.json')) as f:
+            return float(json.load(f)['hbm_gbs']), 'measured (MEASURED_PEAKS.json)'
+    except Exception:      # noqa: BLE001
+        return 6650.0, 'fallback (B200_PROFILING.md)'
+
+
+def synth_inputs(n, seed=0):
+    import synth
+    return dict(U=synth.noise_image(n, H, W, C, 900 + seed), theta=synth.random_mesh(n, GH, GW, 0.05, 901 + seed),
+                d_out=synth.randn((n, H, W, C), 902 + seed), d_img=synth.randn((n, H, W, 2), 903 + seed, 0.1))
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,'
+         'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index):
+        self.index, self.lines, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q, '--format=csv,noheader,nounits',
+                                          '-lms', '100'], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:      # noqa: BLE001
+            self.proc = None
+
+    def _pump(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(',')]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), f[5:9]):
+                if v.lower().startswith('active'):
+                    reasons.add(name)
+        return {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': max(mx) if mx else None,
+                'samples': len(sm), 'reasons': sorted(reasons)}
+
+
+def cpu_port_step(inp, n):
+    """one fwd+bwd of the oracle's torch-CPU port on the first n frames; returns seconds."""
+    import mesh_warp_ref as ref
+    U = torch.tensor(inp['U'][:n], requires_grad=True)
+    th = torch.tensor(inp['theta'][:n], requires_grad=True)
+    g_out, g_img = torch.tensor(inp['d_out'][:n]), torch.tensor(inp['d_img'][:n])
+    t0 = time.perf_counter()
+    out, black, img, _ = ref.transformer(U, th)
+    torch.autograd.backward([out, img], [g_out, g_img])
+    return time.perf_counter() - t0
+
+
+def run_reference(args):
+    """reference arm: the reference's CPU implementation of the path = the oracle port (TensorFlow is absent and the
+    reference is pure Python that cannot travel), all host threads, bounded sample per step."""
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    torch.set_num_threads(os.cpu_count() or 1)
+    ns = args.cpu_sample
+    inp = synth_inputs(ns)
+    for _ in range(max(args.warmup, 1)):
+        cpu_port_step(inp, ns)
+    steps = max(1, min(args.steps, 12))
+    t = sum(cpu_port_step(inp, ns) for _ in range(steps))
+    val = ns * H * W * steps / t / 1e6
+    sample = '%d of 32 frames of configs[1] per step (fwd+bwd, dU+dtheta), %d steps' % (ns, steps)
+    print(json.dumps({
+        'impl': 'reference', 'metric': METRIC, 'value': val, 'unit': 'Mpix/s', 'n_gpus': args.gpus, 'steps': steps,
+        'warmup': args.warmup, 'ms_per_step': 1e3 * t / steps, 'higher_is_better': True, 'scaling': 'weak',
+        'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+        'config': {'workload': 'configs[1]: %dx%dx%dx%d frames, %dx%d mesh warp fwd+bwd (bounded sample: %d frames/step)' % (32, H, W, C, GH, GW, ns)},
+        'cpu_baseline': {'value': val, 'unit': 'Mpix/s', 'cores': torch.get_num_threads(), 'kind': 'port', 'sample': sample},
+        'e2e': {'value': val, 'unit': 'Mpix/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'note': 'oracle/mesh_warp_ref.py (torch-CPU restatement of the reference graph); TensorFlow is not installable here',
+    }))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=50)
+    ap.add_argument('--warmup', type=int, default=5)
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--batch', type=int, default=32, help='frames per GPU')
+    ap.add_argument('--cpu-sample', type=int, default=4, help='frames per CPU-baseline step')
+    ap.add_argument('--no-cpu-baseline', action='store_true', help='skip the CPU leg (profiling runs)')
+    ap.add_argument('--kernel-impl', default='auto', choices=['auto', 'generic', 'tma'])
+    args = ap.parse_args()
+    if args.impl == 'reference':
+        return run_reference(args)
+
+    import dovs_b200 as mgw
+    from dovs_b200 import ops
+    import torch.distributed as dist
+    assert torch.cuda.is_available(), 'bench.py needs a CUDA device: the product has no CPU path'
+    rank, world, local = mgw.parallel.init_from_env()
+    assert world == args.gpus or world == 1, 'launch with torchrun --nproc-per-node %d' % args.gpus
+    dev = torch.device('cuda', local)
+    torch.cuda.set_device(dev)
+    mgw.set_impl(args.kernel_impl)
+    n, K, Wm = args.batch, args.steps, max(args.warmup, 3)
+    P = n * H * W
+
+    # --- inputs: 3 rotating sets so that no step finds its inputs in L2 (each set is 151 MB, L2 is 126 MB)
+    base = synth_inputs(n, seed=rank)
+    R = 3
+    sets = []
+    for k in range(R):
+        sets.append({key: torch.tensor(np.roll(v, k, axis=0), device=dev) for key, v in base.items()})
+    feats = torch.randn(n, 512, device=dev)
+    reducer = mgw.parallel.MeshHeadGradReducer(512, 2 * (GH + 1) * (GW + 1), dev)
+
+    def step(i):
+        s = sets[i % R]
+        out, black, img, Hs = ops.mesh_warp_fwd(s['U'], s['theta'])
+        dU, dtheta = ops.mesh_warp_bwd(s['U'], s['theta'], Hs, s['d_out'], s['d_img'])
+        if world > 1:
+            reducer.wait()
+            reducer.head_grad(feats, dtheta)
+            reducer.launch()
+        return dtheta
+
+    def timed(fn, steps, warm):
+        for i in range(warm):
+            fn(i)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps):
+            fn(i)
+        if world > 1:
+            reducer.wait()
+        e1.record()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.3)
+    l0 = mgw.launch_count()
+    ms_total = timed(step, K, Wm)
+    launches = (mgw.launch_count() - l0 - 0) * 1.0
+    launches_timed = int(round(launches * K / (K + Wm)))
+    clocks = sampler.stop() if rank == 0 else None
+
+    # --- per-kernel timings (same rotation, CUDA events around the single C-ABI call)
+    Hs_sets = [ops.solve_h_fwd(s['theta']) for s in sets]
+    ms_fwd = timed(lambda i: ops.warp_fwd(sets[i % R]['U'], Hs_sets[i % R]), K, Wm)
+    ms_bwd = timed(lambda i: ops.warp_bwd(sets[i % R]['U'], Hs_sets[i % R], sets[i % R]['d_out'], sets[i % R]['d_img']), K, Wm)
+    ms_fwd_full = timed(lambda i: ops.mesh_warp_fwd(sets[i % R]['U'], sets[i % R]['theta']), K, Wm)
+
+    # --- end to end through the public API with HOST (pinned) buffers: H2D of the step's inputs and D2H of its result
+    host = {k: torch.tensor(v).pin_memory() for k, v in base.items()}
+    stage = {k: torch.empty_like(v, device=dev) for k, v in host.items()}
+    res_host = torch.empty((n, GH + 1, GW + 1, 2)).pin_memory()
+    h2d = sum(v.numel() * 4 for v in host.values())
+    d2h = res_host.numel() * 4
+
+    def e2e_step(i):
+        for k in host:
+            stage[k].copy_(host[k], non_blocking=True)
+        Ut, th = stage['U'].requires_grad_(True), stage['theta'].requires_grad_(True)
+        out, black, img = mgw.transformer(Ut, th)
+        torch.autograd.backward([out, img], [stage['d_out'], stage['d_img']])
+        res_host.copy_(th.grad, non_blocking=True)
+        Ut.grad = None; th.grad = None
+        Ut.requires_grad_(False); th.requires_grad_(False)
+        torch.cuda.current_stream().synchronize()          # the caller reads the result on the host
+
+    Ke = max(3, min(K, 20))
+    ms_e2e = timed(e2e_step, Ke, 3)
+
+    if rank != 0:
+        return
+    peak, peak_src = peaks()
+    pix_per_step = P * world
+    value = pix_per_step * K / (ms_total * 1e-3) / 1e6
+    gbs_fwd = FWD_BYTES_PER_PX * P / (ms_fwd / K * 1e-3) / 1e9
+    gbs_bwd = BWD_BYTES_PER_PX * P / (ms_bwd / K * 1e-3) / 1e9
+    gbs_step = (FWD_BYTES_PER_PX + BWD_BYTES_PER_PX) * P / (ms_total / K * 1e-3) / 1e9
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, 'profiles', 'traffic.json')) as f:
+            traffic = json.load(f)
+    except Exception:      # noqa: BLE001
+        pass
+    dominant = 'warp_bwd' if ms_bwd >= ms_fwd else 'warp_fwd'
+    roof = {
+        'warp_fwd': {'bound': 'hbm', 'achieved': gbs_fwd, 'peak': peak, 'unit': 'GB/s', 'frac': gbs_fwd / peak,
+                     'traffic': (traffic or {}).get('warp_fwd'), 'us_per_launch': 1e3 * ms_fwd / K,
+                     'algorithmic_bytes_per_launch': FWD_BYTES_PER_PX * P},
+        'warp_bwd': {'bound': 'hbm', 'achieved': gbs_bwd, 'peak': peak, 'unit': 'GB/s', 'frac': gbs_bwd / peak,
+                     'traffic': (traffic or {}).get('warp_bwd'), 'us_per_launch': 1e3 * ms_bwd / K,
+                     'algorithmic_bytes_per_launch': BWD_BYTES_PER_PX * P,
+                     'note': 'timed around mgw_warp_bwd: includes the dU zero-fill and the dH partial reduction'},
+    }
+    line = {
+        'metric': METRIC, 'value': value, 'unit': 'Mpix/s', 'n_gpus': world, 'steps': K, 'warmup': Wm,
+        'ms_per_step': ms_total / K, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
+        'data': 'synthetic',
+        'config': {'workload': 'configs[1]: %d x %dx%dx%d fp32 frames per GPU, %dx%d mesh warp forward+backward (dU + dtheta)' % (n, H, W, C, GH, GW),
+                   'l2': 'inputs rotate over %d sets of 151 MB (> 126 MB L2)' % R, 'kernel_impl': args.kernel_impl,
+                   'parallelism': 'dp%d (batch-sharded, 100 KB mesh-head grad all-reduce)' % world if world > 1 else 'single GPU'},
+        'fwd_mpix_per_s': pix_per_step * K / (ms_fwd_full * 1e-3) / 1e6,
+        'step_hbm_gbs': gbs_step, 'step_hbm_frac_of_measured': gbs_step / peak, 'step_hbm_frac_of_8tbs': gbs_step / 8000.0,
+        'roofline': dict(roof[dominant], kernel=dominant, peak_source=peak_src), 'roofline_kernels': roof,
+        'e2e': {'value': pix_per_step * Ke / (ms_e2e * 1e-3) / 1e6, 'unit': 'Mpix/s', 'h2d_bytes_per_step': h2d,
+                'd2h_bytes_per_step': d2h, 'ms_per_step': ms_e2e / Ke, 'steps': Ke},
+        'gpu_launches': launches_timed, 'clocks': clocks,
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        torch.set_num_threads(os.cpu_count() or 1)
+        ns = args.cpu_sample
+        cpu_port_step(base, ns)
+        ts, t_start = [], time.perf_counter()
+        while len(ts) < 3 or (time.perf_counter() - t_start < 10 and len(ts) < 20):
+            ts.append(cpu_port_step(base, ns))
+        line['cpu_baseline'] = {'value': ns * H * W / float(np.mean(ts)) / 1e6, 'unit': 'Mpix/s', 'cores': torch.get_num_threads(),
+                                'kind': 'port', 'sample': '%d of %d frames of the same workload, fwd+bwd, mean of %d runs (%.1f s of CPU work)'
+                                % (ns, n, len(ts), sum(ts))}
+    print(json.dumps(line))
+
+
+if __name__ == '__main__':
+    main()

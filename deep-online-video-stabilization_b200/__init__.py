@@ -1,0 +1,13 @@
+"""B200-native multi-grid warp (StabNet's transformer / interpolate path) behind the reference's Python interface.
+
+Layout: csrc/ (CUDA kernels + C ABI, built into libmgw_b200.so), _lib.py (ctypes), ops.py (tensor carriers),
+functional.py (autograd), spatial_transformer3.py / spatial_transformer.py (reference-named operator modules),
+losses.py (vertex builder + fused loss epilogue), parallel.py (batch sharding + NCCL all-reduce).
+"""
+from . import _lib, functional, losses, ops, parallel, spatial_transformer, spatial_transformer3  # noqa: F401
+from ._lib import MgwError, launch_count, set_impl  # noqa: F401
+from .losses import feature_loss, get_4_pts, img_loss, temp_loss  # noqa: F401
+from .spatial_transformer import interpolate  # noqa: F401
+from .spatial_transformer3 import transformer  # noqa: F401
+
+__version__ = '0.1.0'

@@ -1,0 +1,80 @@
+"""ctypes loader of libmgw_b200.so -- the C ABI declared in include/mgw.h.
+
+There is NO fallback: if the shared library is missing (and cannot be built because nvcc is absent) importing
+this module raises, and every compute entry point returns an error without a CUDA device.
+"""
+import ctypes
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SO = os.path.join(HERE, 'libmgw_b200.so')
+
+c_f = ctypes.c_void_p      # device pointers travel as raw addresses
+c_i = ctypes.c_int
+c_fl = ctypes.c_float
+c_st = ctypes.c_void_p
+
+# name -> (restype, argtypes); mirrors include/mgw.h one to one (tests/test_abi.py checks the header against this)
+SIGNATURES = {
+    'mgw_version': (c_i, []),
+    'mgw_last_error': (ctypes.c_char_p, []),
+    'mgw_launch_count': (ctypes.c_uint64, []),
+    'mgw_set_impl': (c_i, [c_i]),
+    'mgw_vertices_fwd': (c_i, [c_f, c_i, c_i, c_i, c_fl, c_f, c_f, c_st]),
+    'mgw_vertices_bwd': (c_i, [c_f, c_f, c_f, c_i, c_i, c_i, c_fl, c_f, c_st]),
+    'mgw_solve_h_fwd': (c_i, [c_f, c_i, c_i, c_i, c_f, c_st]),
+    'mgw_solve_h_bwd': (c_i, [c_f, c_f, c_f, c_i, c_i, c_i, c_f, c_st]),
+    'mgw_warp_fwd': (c_i, [c_f, c_f] + [c_i] * 6 + [c_f, c_f, c_f, c_f, c_st]),
+    'mgw_warp_bwd_workspace_bytes': (ctypes.c_size_t, [c_i] * 6),
+    'mgw_warp_bwd': (c_i, [c_f, c_f, c_f, c_f] + [c_i] * 6 + [c_f, c_f, c_f, c_st]),
+    'mgw_mesh_warp_fwd': (c_i, [c_f, c_f] + [c_i] * 6 + [c_f, c_f, c_f, c_f, c_st]),
+    'mgw_mesh_warp_bwd_workspace_bytes': (ctypes.c_size_t, [c_i] * 6),
+    'mgw_mesh_warp_bwd': (c_i, [c_f, c_f, c_f, c_f, c_f] + [c_i] * 6 + [c_f, c_f, c_f, c_st]),
+    'mgw_interp_fwd': (c_i, [c_f, c_f, c_f] + [c_i] * 6 + [c_f, c_st]),
+    'mgw_interp_bwd': (c_i, [c_f, c_f, c_f, c_f] + [c_i] * 6 + [c_f, c_f, c_f, c_st]),
+    'mgw_homography_warp_fwd': (c_i, [c_f, c_f] + [c_i] * 6 + [c_f, c_f, c_f, c_st]),
+    'mgw_homography_warp_bwd': (c_i, [c_f, c_f, c_f] + [c_i] * 6 + [c_f, c_f, c_st]),
+    'mgw_img_loss_fwd': (c_i, [c_f, c_f, c_f] + [c_i] * 4 + [c_f, c_st]),
+    'mgw_img_loss_bwd': (c_i, [c_f, c_f, c_f, c_f, c_fl] + [c_i] * 4 + [c_f, c_st]),
+    'mgw_feature_loss_fwd': (c_i, [c_f, c_f, c_f] + [c_i] * 4 + [c_f, c_f, c_st]),
+    'mgw_feature_loss_bwd': (c_i, [c_f, c_f, c_f, c_fl] + [c_i] * 4 + [c_f, c_st]),
+    'mgw_temp_loss_fwd': (c_i, [c_f] * 5 + [c_i] * 4 + [c_f, c_st]),
+    'mgw_temp_loss_bwd': (c_i, [c_f] * 6 + [c_fl] + [c_i] * 4 + [c_f, c_f, c_st]),
+}
+
+
+class MgwError(RuntimeError):
+    pass
+
+
+def _load():
+    if not os.path.exists(SO):
+        try:
+            from . import build as _build
+            _build.build()
+        except Exception as e:      # noqa: BLE001
+            raise ImportError('libmgw_b200.so is missing and could not be built (%s). Run '
+                              '`python __graft_entry__.py build`; there is no CPU fallback.' % e) from e
+    lib = ctypes.CDLL(SO)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)     # AttributeError here = the .so does not match include/mgw.h
+        fn.restype = res
+        fn.argtypes = args
+    return lib
+
+
+lib = _load()
+
+
+def check(rc, what):
+    if rc != 0:
+        raise MgwError('%s failed (%d): %s' % (what, rc, lib.mgw_last_error().decode()))
+
+
+def launch_count():
+    return int(lib.mgw_launch_count())
+
+
+def set_impl(mode):
+    """'auto' | 'generic' | 'tma'"""
+    check(lib.mgw_set_impl({'auto': 0, 'generic': 1, 'tma': 2}[mode]), 'mgw_set_impl')

@@ -1,0 +1,313 @@
+// extern "C" entry points of libmgw_b200.so (see include/mgw.h): argument validation, workspace carving,
+// kernel selection.  No torch types, no hidden allocation, no CPU fallback.
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+
+#include "mgw_internal.h"
+
+namespace mgw {
+
+static thread_local char g_err[512] = "";
+static std::atomic<uint64_t> g_launches{0};
+static std::atomic<int> g_impl{0};
+
+int set_error(int code, const char* fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+void count_launches(int n) { g_launches.fetch_add((uint64_t)n, std::memory_order_relaxed); }
+
+int check_launch(const char* what)
+{
+    count_launches(1);
+    const cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return set_error(MGW_ERR_CUDA, "%s: %s", what, cudaGetErrorString(e));
+    return MGW_OK;
+}
+
+int impl_mode() { return g_impl.load(std::memory_order_relaxed); }
+
+static bool aligned(const void* p, size_t a) { return (reinterpret_cast<uintptr_t>(p) % a) == 0; }
+
+#define REQUIRE(cond, ...) do { if (!(cond)) return set_error(MGW_ERR_INVALID, __VA_ARGS__); } while (0)
+#define TRY(expr) do { const int rc_ = (expr); if (rc_ != MGW_OK) return rc_; } while (0)
+
+static int check_memset(cudaError_t e, const char* what)
+{
+    if (e != cudaSuccess) return set_error(MGW_ERR_CUDA, "%s: %s", what, cudaGetErrorString(e));
+    return MGW_OK;
+}
+
+static int validate_mesh_shape(const char* fn, int N, int H, int W, int C, int gh, int gw)
+{
+    REQUIRE(N > 0 && H > 1 && W > 1 && C > 0, "%s: need N>0, H>1, W>1, C>0 (got N=%d H=%d W=%d C=%d)", fn, N, H, W, C);
+    REQUIRE(gh > 0 && gw > 0 && gh <= H && gw <= W, "%s: need 1 <= gh <= H and 1 <= gw <= W (got gh=%d gw=%d)", fn, gh, gw);
+    REQUIRE((long long)N * H * W < (1LL << 31), "%s: N*H*W must fit in int32", fn);
+    return MGW_OK;
+}
+
+// dHs accumulators for the atomic reduction live either in the caller's dHs buffer (zeroed here)
+static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+__global__ void reduce_parts_kernel(const float* __restrict__ parts, int nparts, int ncell, float* __restrict__ dHs)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= ncell * 9) return;
+    const int cell = t / 9, k = t % 9;
+    double s = 0;
+    if (k < 8) for (int p = 0; p < nparts; ++p) s += (double)parts[((size_t)cell * nparts + p) * 8 + k];
+    dHs[t] = (float)s;
+}
+
+}  // namespace mgw
+
+using namespace mgw;
+
+extern "C" {
+
+int mgw_version(void) { return 100; }
+
+const char* mgw_last_error(void) { return g_err; }
+
+uint64_t mgw_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+int mgw_set_impl(int impl)
+{
+    REQUIRE(impl >= 0 && impl <= 2, "mgw_set_impl: impl must be 0 (auto), 1 (generic) or 2 (tma)");
+    g_impl.store(impl);
+    return MGW_OK;
+}
+
+int mgw_vertices_fwd(const float* head, int N, int gh, int gw, float do_crop_rate, float* pts2, float* pts1, void* stream)
+{
+    REQUIRE(head && pts2, "mgw_vertices_fwd: null pointer");
+    REQUIRE(N > 0 && gh > 0 && gw > 0 && do_crop_rate > 0.0f, "mgw_vertices_fwd: bad sizes");
+    return launch_vertices_fwd(head, N, gh, gw, do_crop_rate, pts2, pts1, (cudaStream_t)stream);
+}
+
+int mgw_vertices_bwd(const float* head, const float* d_pts2, const float* d_pts1, int N, int gh, int gw,
+                     float do_crop_rate, float* d_head, void* stream)
+{
+    REQUIRE(head && d_head, "mgw_vertices_bwd: null pointer");
+    REQUIRE(N > 0 && gh > 0 && gw > 0 && do_crop_rate > 0.0f, "mgw_vertices_bwd: bad sizes");
+    return launch_vertices_bwd(head, d_pts2, d_pts1, N, gh, gw, do_crop_rate, d_head, (cudaStream_t)stream);
+}
+
+int mgw_solve_h_fwd(const float* theta, int N, int gh, int gw, float* Hs, void* stream)
+{
+    REQUIRE(theta && Hs, "mgw_solve_h_fwd: null pointer");
+    REQUIRE(N > 0 && gh > 0 && gw > 0, "mgw_solve_h_fwd: bad sizes");
+    return launch_solve_h_fwd(theta, N, gh, gw, Hs, (cudaStream_t)stream);
+}
+
+int mgw_solve_h_bwd(const float* theta, const float* Hs, const float* dHs, int N, int gh, int gw, float* dtheta, void* stream)
+{
+    REQUIRE(theta && Hs && dHs && dtheta, "mgw_solve_h_bwd: null pointer");
+    REQUIRE(N > 0 && gh > 0 && gw > 0, "mgw_solve_h_bwd: bad sizes");
+    return launch_solve_h_bwd(theta, Hs, dHs, 1, 9, N, gh, gw, dtheta, (cudaStream_t)stream);
+}
+
+static bool use_tma_fwd(const WarpShape& s, const float* U, const float* out, const float* black, const float* img, int* rc)
+{
+    *rc = MGW_OK;
+    const int mode = impl_mode();
+    if (mode == 1) return false;
+    const bool ok = tma_fwd_supported(s) && aligned(U, 16) && (!out || aligned(out, 16)) && (!black || aligned(black, 16)) &&
+                    (!img || aligned(img, 16));
+    if (!ok && mode == 2) *rc = set_error(MGW_ERR_UNSUPPORTED, "TMA path required (mgw_set_impl(2)) but shape/alignment does not allow it");
+    return ok;
+}
+
+int mgw_warp_fwd(const float* U, const float* Hs, int N, int H, int W, int C, int gh, int gw, float* out, float* black,
+                 float* img, int32_t* cell_idx, void* stream)
+{
+    REQUIRE(U && Hs, "mgw_warp_fwd: null pointer");
+    TRY(validate_mesh_shape("mgw_warp_fwd", N, H, W, C, gh, gw));
+    REQUIRE(!img || aligned(img, 8), "mgw_warp_fwd: img must be 8-byte aligned");
+    const WarpShape s{N, H, W, C, H, W, gh, gw};
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc;
+    if (!cell_idx && use_tma_fwd(s, U, out, black, img, &rc)) return launch_warp_fwd_tma(U, Hs, s, out, black, img, st);
+    if (rc != MGW_OK) return rc;
+    return launch_warp_fwd_generic(U, Hs, s, false, out, black, img, cell_idx, st);
+}
+
+size_t mgw_warp_bwd_workspace_bytes(int N, int H, int W, int C, int gh, int gw)
+{
+    const WarpShape s{N, H, W, C, H, W, gh, gw};
+    return tma_bwd_supported(s) ? tma_bwd_workspace_bytes(s) : 0;
+}
+
+// shared by mgw_warp_bwd and mgw_mesh_warp_bwd: produces dH partials; returns their layout
+static int warp_bwd_core(const float* U, const float* Hs, const float* d_out, const float* d_img, const WarpShape& s,
+                         float* dU, float* dHs_acc /*[cells,9]*/, void* workspace, const float** parts, int* nparts,
+                         int* part_stride, cudaStream_t st)
+{
+    const size_t ncell = (size_t)s.N * s.gh * s.gw;
+    if (dU) TRY(check_memset(cudaMemsetAsync(dU, 0, sizeof(float) * (size_t)s.N * s.H * s.W * s.C, st), "memset dU"));
+    const int mode = impl_mode();
+    const bool tma_ok = mode != 1 && workspace && tma_bwd_supported(s) && aligned(U, 16) && aligned(d_out, 16) &&
+                        (!dU || aligned(dU, 16)) && (!d_img || aligned(d_img, 16));
+    if (!tma_ok && mode == 2)
+        return set_error(MGW_ERR_UNSUPPORTED, "TMA path required (mgw_set_impl(2)) but shape/alignment/workspace does not allow it");
+    if (tma_ok) {
+        int np = 0;
+        TRY(launch_warp_bwd_tma(U, Hs, d_out, d_img, s, dU, (float*)workspace, &np, st));
+        *parts = (const float*)workspace; *nparts = np; *part_stride = 8;
+        return MGW_OK;
+    }
+    TRY(check_memset(cudaMemsetAsync(dHs_acc, 0, sizeof(float) * ncell * 9, st), "memset dHs"));
+    TRY(launch_warp_bwd_generic(U, Hs, d_out, d_img, s, false, dU, dHs_acc, st));
+    *parts = dHs_acc; *nparts = 1; *part_stride = 9;
+    return MGW_OK;
+}
+
+int mgw_warp_bwd(const float* U, const float* Hs, const float* d_out, const float* d_img, int N, int H, int W, int C,
+                 int gh, int gw, float* dU, float* dHs, void* workspace, void* stream)
+{
+    REQUIRE(U && Hs && d_out && dHs, "mgw_warp_bwd: null pointer");
+    TRY(validate_mesh_shape("mgw_warp_bwd", N, H, W, C, gh, gw));
+    REQUIRE(!d_img || aligned(d_img, 8), "mgw_warp_bwd: d_img must be 8-byte aligned");
+    const WarpShape s{N, H, W, C, H, W, gh, gw};
+    cudaStream_t st = (cudaStream_t)stream;
+    const float* parts; int np, ps;
+    TRY(warp_bwd_core(U, Hs, d_out, d_img, s, dU, dHs, workspace, &parts, &np, &ps, st));
+    if (parts != dHs) {
+        const int ncell = N * gh * gw;
+        reduce_parts_kernel<<<(ncell * 9 + 127) / 128, 128, 0, st>>>(parts, np, ncell, dHs);
+        TRY(check_launch("reduce_parts"));
+    }
+    return MGW_OK;
+}
+
+int mgw_mesh_warp_fwd(const float* U, const float* theta, int N, int H, int W, int C, int gh, int gw, float* Hs,
+                      float* out, float* black, float* img, void* stream)
+{
+    REQUIRE(U && theta && Hs, "mgw_mesh_warp_fwd: null pointer");
+    TRY(validate_mesh_shape("mgw_mesh_warp_fwd", N, H, W, C, gh, gw));
+    TRY(launch_solve_h_fwd(theta, N, gh, gw, Hs, (cudaStream_t)stream));
+    return mgw_warp_fwd(U, Hs, N, H, W, C, gh, gw, out, black, img, nullptr, stream);
+}
+
+size_t mgw_mesh_warp_bwd_workspace_bytes(int N, int H, int W, int C, int gh, int gw)
+{
+    return align_up(sizeof(float) * (size_t)N * gh * gw * 9, 256) + mgw_warp_bwd_workspace_bytes(N, H, W, C, gh, gw);
+}
+
+int mgw_mesh_warp_bwd(const float* U, const float* theta, const float* Hs, const float* d_out, const float* d_img,
+                      int N, int H, int W, int C, int gh, int gw, float* dU, float* dtheta, void* workspace, void* stream)
+{
+    REQUIRE(U && theta && Hs && d_out && dtheta && workspace, "mgw_mesh_warp_bwd: null pointer");
+    TRY(validate_mesh_shape("mgw_mesh_warp_bwd", N, H, W, C, gh, gw));
+    REQUIRE(aligned(workspace, 256), "mgw_mesh_warp_bwd: workspace must be 256-byte aligned");
+    const WarpShape s{N, H, W, C, H, W, gh, gw};
+    cudaStream_t st = (cudaStream_t)stream;
+    float* dHs_acc = (float*)workspace;
+    const size_t off = align_up(sizeof(float) * (size_t)N * gh * gw * 9, 256);
+    void* tma_ws = mgw_warp_bwd_workspace_bytes(N, H, W, C, gh, gw) ? (void*)((char*)workspace + off) : nullptr;
+    const float* parts; int np, ps;
+    TRY(warp_bwd_core(U, Hs, d_out, d_img, s, dU, dHs_acc, tma_ws, &parts, &np, &ps, st));
+    return launch_solve_h_bwd(theta, Hs, parts, np, ps, N, gh, gw, dtheta, st);
+}
+
+int mgw_interp_fwd(const float* im, const float* x, const float* y, int N, int IH, int IW, int C, int OH, int OW,
+                   float* out, void* stream)
+{
+    REQUIRE(im && x && y && out, "mgw_interp_fwd: null pointer");
+    REQUIRE(N > 0 && IH > 0 && IW > 0 && C > 0 && OH > 0 && OW > 0, "mgw_interp_fwd: bad sizes");
+    return launch_interp_fwd(im, x, y, N, IH, IW, C, OH, OW, out, (cudaStream_t)stream);
+}
+
+int mgw_interp_bwd(const float* im, const float* x, const float* y, const float* d_out, int N, int IH, int IW, int C,
+                   int OH, int OW, float* d_im, float* dx, float* dy, void* stream)
+{
+    REQUIRE(im && x && y && d_out, "mgw_interp_bwd: null pointer");
+    REQUIRE(N > 0 && IH > 0 && IW > 0 && C > 0 && OH > 0 && OW > 0, "mgw_interp_bwd: bad sizes");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (d_im) TRY(check_memset(cudaMemsetAsync(d_im, 0, sizeof(float) * (size_t)N * IH * IW * C, st), "memset d_im"));
+    return launch_interp_bwd(im, x, y, d_out, N, IH, IW, C, OH, OW, d_im, dx, dy, st);
+}
+
+int mgw_homography_warp_fwd(const float* U, const float* theta, int N, int H, int W, int C, int OH, int OW, float* out,
+                            float* black, float* img, void* stream)
+{
+    REQUIRE(U && theta, "mgw_homography_warp_fwd: null pointer");
+    REQUIRE(N > 0 && H > 0 && W > 0 && C > 0 && OH > 1 && OW > 1, "mgw_homography_warp_fwd: bad sizes");
+    REQUIRE(!img || aligned(img, 8), "mgw_homography_warp_fwd: img must be 8-byte aligned");
+    const WarpShape s{N, H, W, C, OH, OW, 1, 1};
+    return launch_warp_fwd_generic(U, theta, s, true, out, black, img, nullptr, (cudaStream_t)stream);
+}
+
+int mgw_homography_warp_bwd(const float* U, const float* theta, const float* d_out, int N, int H, int W, int C, int OH,
+                            int OW, float* dU, float* dtheta, void* stream)
+{
+    REQUIRE(U && theta && d_out && dtheta, "mgw_homography_warp_bwd: null pointer");
+    REQUIRE(N > 0 && H > 0 && W > 0 && C > 0 && OH > 1 && OW > 1, "mgw_homography_warp_bwd: bad sizes");
+    const WarpShape s{N, H, W, C, OH, OW, 1, 1};
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dU) TRY(check_memset(cudaMemsetAsync(dU, 0, sizeof(float) * (size_t)N * H * W * C, st), "memset dU"));
+    // dtheta doubles as the dHn accumulator ([N,9]); finished in place
+    TRY(check_memset(cudaMemsetAsync(dtheta, 0, sizeof(float) * (size_t)N * 9, st), "memset dtheta"));
+    TRY(launch_warp_bwd_generic(U, theta, d_out, nullptr, s, true, dU, dtheta, st));
+    return launch_homography_finish_bwd(theta, dtheta, N, dtheta, st);
+}
+
+int mgw_img_loss_fwd(const float* out, const float* y, const float* black, int N, int H, int W, int C, float* sums, void* stream)
+{
+    REQUIRE(out && y && black && sums, "mgw_img_loss_fwd: null pointer");
+    REQUIRE(N > 0 && H > 0 && W > 0 && C > 0, "mgw_img_loss_fwd: bad sizes");
+    return launch_img_loss_fwd(out, y, black, N, H, W, C, sums, (cudaStream_t)stream);
+}
+
+int mgw_img_loss_bwd(const float* out, const float* y, const float* black, const float* sums, float upstream, int N,
+                     int H, int W, int C, float* d_out, void* stream)
+{
+    REQUIRE(out && y && black && sums && d_out, "mgw_img_loss_bwd: null pointer");
+    REQUIRE(N > 0 && H > 0 && W > 0 && C > 0, "mgw_img_loss_bwd: bad sizes");
+    return launch_img_loss_bwd(out, y, black, sums, upstream, N, H, W, C, d_out, (cudaStream_t)stream);
+}
+
+int mgw_feature_loss_fwd(const float* matches, const float* mask, const float* img, int N, int M, int H, int W,
+                         float* warpped, float* per_sample, void* stream)
+{
+    REQUIRE(matches && mask && img && per_sample, "mgw_feature_loss_fwd: null pointer");
+    REQUIRE(N > 0 && M > 0 && H > 0 && W > 0, "mgw_feature_loss_fwd: bad sizes");
+    REQUIRE(aligned(matches, 16) && aligned(img, 8) && (!warpped || aligned(warpped, 8)), "mgw_feature_loss_fwd: alignment");
+    return launch_feature_loss_fwd(matches, mask, img, N, M, H, W, warpped, per_sample, (cudaStream_t)stream);
+}
+
+int mgw_feature_loss_bwd(const float* matches, const float* mask, const float* img, float upstream, int N, int M, int H,
+                         int W, float* d_img, void* stream)
+{
+    REQUIRE(matches && mask && img && d_img, "mgw_feature_loss_bwd: null pointer");
+    REQUIRE(N > 0 && M > 0 && H > 0 && W > 0, "mgw_feature_loss_bwd: bad sizes");
+    REQUIRE(aligned(matches, 16) && aligned(img, 8), "mgw_feature_loss_bwd: alignment");
+    return launch_feature_loss_bwd(matches, mask, img, upstream, N, M, H, W, d_img, (cudaStream_t)stream);
+}
+
+int mgw_temp_loss_fwd(const float* out1, const float* black1, const float* out2, const float* black2, const float* flow,
+                      int N, int H, int W, int C, float* sums, void* stream)
+{
+    REQUIRE(out1 && black1 && out2 && black2 && flow && sums, "mgw_temp_loss_fwd: null pointer");
+    REQUIRE(N > 0 && H > 0 && W > 0 && C > 0, "mgw_temp_loss_fwd: bad sizes");
+    REQUIRE(aligned(flow, 8), "mgw_temp_loss_fwd: flow must be 8-byte aligned");
+    return launch_temp_loss_fwd(out1, black1, out2, black2, flow, N, H, W, C, sums, (cudaStream_t)stream);
+}
+
+int mgw_temp_loss_bwd(const float* out1, const float* black1, const float* out2, const float* black2, const float* flow,
+                      const float* sums, float upstream, int N, int H, int W, int C, float* d_out1, float* d_out2, void* stream)
+{
+    REQUIRE(out1 && black1 && out2 && black2 && flow && sums && d_out1 && d_out2, "mgw_temp_loss_bwd: null pointer");
+    REQUIRE(N > 0 && H > 0 && W > 0 && C > 0, "mgw_temp_loss_bwd: bad sizes");
+    REQUIRE(aligned(flow, 8), "mgw_temp_loss_bwd: flow must be 8-byte aligned");
+    return launch_temp_loss_bwd(out1, black1, out2, black2, flow, sums, upstream, N, H, W, C, d_out1, d_out2, (cudaStream_t)stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,69 @@
+// Internal declarations shared by the .cu files of libmgw_b200.so (not part of the ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stddef.h>
+
+#include "../../include/mgw.h"
+#include "mgw_device.cuh"
+
+namespace mgw {
+
+int set_error(int code, const char* fmt, ...);
+int check_launch(const char* what);          // counts the launch, maps cudaGetLastError() to MGW_ERR_CUDA
+void count_launches(int n);
+int impl_mode();                             // mgw_set_impl value
+
+struct WarpShape {
+    int N, H, W, C;          // source image (and output, for the mesh op)
+    int OH, OW;              // output size
+    int gh, gw;              // mesh cells (1x1 for the single-homography op)
+};
+
+// mgw_solve.cu
+int launch_vertices_fwd(const float* head, int N, int gh, int gw, float do_crop_rate, float* pts2, float* pts1, cudaStream_t st);
+int launch_vertices_bwd(const float* head, const float* d_pts2, const float* d_pts1, int N, int gh, int gw,
+                        float do_crop_rate, float* d_head, cudaStream_t st);
+int launch_solve_h_fwd(const float* theta, int N, int gh, int gw, float* Hs, cudaStream_t st);
+int launch_solve_h_bwd(const float* theta, const float* Hs, const float* dHs_part, int nparts, int part_stride,
+                       int N, int gh, int gw, float* dtheta, cudaStream_t st);
+
+// mgw_warp_generic.cu : any shape, global gather / global atomics
+// normalize: Hs holds raw [N,9] homographies to be divided by H[8] (spatial_transformer.py:151-153)
+int launch_warp_fwd_generic(const float* U, const float* Hs, const WarpShape& s, bool normalize, float* out,
+                            float* black, float* img, int32_t* cell_idx, cudaStream_t st);
+int launch_warp_bwd_generic(const float* U, const float* Hs, const float* d_out, const float* d_img,
+                            const WarpShape& s, bool normalize, float* dU, float* dHs /*[cells,9] zeroed*/,
+                            cudaStream_t st);
+int launch_homography_finish_bwd(const float* theta, const float* dHn, int N, float* dtheta, cudaStream_t st);
+
+// mgw_interp.cu
+int launch_interp_fwd(const float* im, const float* x, const float* y, int N, int IH, int IW, int C, int OH, int OW,
+                      float* out, cudaStream_t st);
+int launch_interp_bwd(const float* im, const float* x, const float* y, const float* d_out, int N, int IH, int IW,
+                      int C, int OH, int OW, float* d_im, float* dx, float* dy, cudaStream_t st);
+
+// mgw_loss.cu
+int launch_img_loss_fwd(const float* out, const float* y, const float* black, int N, int H, int W, int C, float* sums, cudaStream_t st);
+int launch_img_loss_bwd(const float* out, const float* y, const float* black, const float* sums, float upstream,
+                        int N, int H, int W, int C, float* d_out, cudaStream_t st);
+int launch_feature_loss_fwd(const float* matches, const float* mask, const float* img, int N, int M, int H, int W,
+                            float* warpped, float* per_sample, cudaStream_t st);
+int launch_feature_loss_bwd(const float* matches, const float* mask, const float* img, float upstream, int N, int M,
+                            int H, int W, float* d_img, cudaStream_t st);
+int launch_temp_loss_fwd(const float* out1, const float* black1, const float* out2, const float* black2,
+                         const float* flow, int N, int H, int W, int C, float* sums, cudaStream_t st);
+int launch_temp_loss_bwd(const float* out1, const float* black1, const float* out2, const float* black2,
+                         const float* flow, const float* sums, float upstream, int N, int H, int W, int C,
+                         float* d_out1, float* d_out2, cudaStream_t st);
+
+// mgw_warp_tma.cu : TMA-staged tiles (fast path)
+bool tma_fwd_supported(const WarpShape& s);
+int launch_warp_fwd_tma(const float* U, const float* Hs, const WarpShape& s, float* out, float* black, float* img,
+                        cudaStream_t st);
+bool tma_bwd_supported(const WarpShape& s);
+size_t tma_bwd_workspace_bytes(const WarpShape& s);
+int launch_warp_bwd_tma(const float* U, const float* Hs, const float* d_out, const float* d_img, const WarpShape& s,
+                        float* dU, float* dHs_part, int* nparts, cudaStream_t st);
+
+}  // namespace mgw

@@ -1,0 +1,305 @@
+// K0/K1/K4: mesh-vertex builder, batched per-cell 8x8 DLT homography solve, and its adjoint.
+//
+//   vertices_*  : get_4_pts, s_net_bundle_nobm.py:29-71
+//   solve_h_fwd : get_Hs/get_H/pinv, spatial_transformer3.py:144-198  (h = inverse(A + 1e-4 I) . b)
+//   solve_h_bwd : closed-form adjoint of the above, fp64 inside
+//
+// Work is tiny (N*gh*gw cells, 512 for config #2) and latency-bound, so a cell is solved by an 8-lane
+// group (lane = matrix row for the LU, lane = inverse column for the substitutions), four cells per warp,
+// with the LU/inverse exchanged through a few hundred bytes of shared memory.  The operation order is
+// exactly oracle/mgw_oracle.c's ORC_SOLVE, so Hs is bit-identical to the C oracle's.
+#include "mgw_internal.h"
+
+namespace mgw {
+
+// ---------------------------------------------------------------- K0: vertices
+__global__ void vertices_fwd_kernel(const float* __restrict__ head, int N, int gh, int gw, float do_crop_rate,
+                                    float* __restrict__ pts2, float* __restrict__ pts1)
+{
+    const int nv = (gh + 1) * (gw + 1);
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= N * nv * 2) return;
+    const int k = t & 1, tot = (t >> 1) % nv, n = (t >> 1) / nv;
+    const int i = tot / (gw + 1), j = tot % (gw + 1);
+    const double h = 2.0 / gh, w = 2.0 / gw;
+    const float base = k == 0 ? (float)(j * w - 1) : (float)(i * h - 1);        // :44-46
+    const float lim = __fdiv_rn(1.0f, do_crop_rate);                            // :37
+    float p = __fadd_rn(base, head[t]);                                         // :47,:55
+    p = fminf(fmaxf(p, -lim), lim);                                             // :58
+    pts2[t] = p;
+    if (pts1) {                                                                 // :63-68
+        // vertex (i,j) is TL of cell (i,j), TR of (i,j-1), BL of (i-1,j), BR of (i-1,j-1)
+        const int ci[4] = { i, i, i - 1, i - 1 }, cj[4] = { j, j - 1, j, j - 1 };
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+            if (ci[c] >= 0 && ci[c] < gh && cj[c] >= 0 && cj[c] < gw)
+                pts1[(((size_t)n * gh + ci[c]) * gw + cj[c]) * 8 + k * 4 + c] = p;
+    }
+}
+
+__global__ void vertices_bwd_kernel(const float* __restrict__ head, const float* __restrict__ d_pts2,
+                                    const float* __restrict__ d_pts1, int N, int gh, int gw, float do_crop_rate,
+                                    float* __restrict__ d_head)
+{
+    const int nv = (gh + 1) * (gw + 1);
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= N * nv * 2) return;
+    const int k = t & 1, tot = (t >> 1) % nv, n = (t >> 1) / nv;
+    const int i = tot / (gw + 1), j = tot % (gw + 1);
+    const double h = 2.0 / gh, w = 2.0 / gw;
+    const float base = k == 0 ? (float)(j * w - 1) : (float)(i * h - 1);
+    const float lim = __fdiv_rn(1.0f, do_crop_rate);
+    const float p = __fadd_rn(base, head[t]);
+    float g = d_pts2 ? d_pts2[t] : 0.0f;
+    if (d_pts1) {
+        const int ci[4] = { i, i, i - 1, i - 1 }, cj[4] = { j, j - 1, j, j - 1 };
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+            if (ci[c] >= 0 && ci[c] < gh && cj[c] >= 0 && cj[c] < gw)
+                g += d_pts1[(((size_t)n * gh + ci[c]) * gw + cj[c]) * 8 + k * 4 + c];
+    }
+    // tf.minimum(tf.maximum(p,-lim),lim): the gradient passes where the clamp is inactive.  At an exact tie
+    // TF's Maximum/Minimum gradients route to the first argument (x >= y / x <= y), i.e. they pass.
+    d_head[t] = (p >= -lim && p <= lim) ? g : 0.0f;
+}
+
+// ---------------------------------------------------------------- K1: per-cell DLT solve
+// cell corners in output space (ori) and the vertex ids of its 4 corners (TL,TR,BL,BR)
+__device__ __forceinline__ void cell_corner(int i, int j, int gh, int gw, int k, float& x, float& y, int& vid)
+{
+    const double h = 2.0 / gh, w = 2.0 / gw, hh = i * h - 1, ww = j * w - 1;      // spatial_transformer3.py:182-188
+    x = (float)((k & 1) ? ww + w : ww);
+    y = (float)((k & 2) ? hh + h : hh);
+    vid = (i + (k >> 1)) * (gw + 1) + j + (k & 1);
+}
+
+template <typename T> __device__ __forceinline__ T tfma(T a, T b, T c);
+template <> __device__ __forceinline__ float tfma<float>(float a, float b, float c) { return __fmaf_rn(a, b, c); }
+template <> __device__ __forceinline__ double tfma<double>(double a, double b, double c) { return fma(a, b, c); }
+template <typename T> __device__ __forceinline__ T tabs(T a) { return a < 0 ? -a : a; }
+
+// In-group (8 lanes) LU with partial pivoting of the row-distributed matrix `row` (lane g holds row g).
+// Mirrors ORC_SOLVE: first-max pivot, reciprocal scaling, fma updates.  piv[] is group-uniform.
+template <typename T>
+__device__ __forceinline__ void group_lu(T (&row)[8], int (&piv)[8], int g)
+{
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        T best = (g >= k) ? tabs(row[k]) : (T)-1;
+        int p = g;
+#pragma unroll
+        for (int o = 4; o > 0; o >>= 1) {
+            const T ob = __shfl_xor_sync(0xffffffffu, best, o, 8);
+            const int op = __shfl_xor_sync(0xffffffffu, p, o, 8);
+            if (ob > best || (ob == best && op < p)) { best = ob; p = op; }
+        }
+        piv[k] = p;
+        const int src = (g == k) ? p : ((g == p) ? k : g);
+        T pr[8];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            row[c] = __shfl_sync(0xffffffffu, row[c], src, 8);
+            pr[c] = __shfl_sync(0xffffffffu, row[c], k, 8);
+        }
+        const T rp = (T)1 / pr[k];
+        if (g > k) {
+            const T l = row[k] * rp;
+            row[k] = l;
+#pragma unroll
+            for (int c = k + 1; c < 8; ++c) row[c] = tfma<T>(-l, pr[c], row[c]);
+        }
+    }
+}
+
+// Solve LU x = P e (getrs): lane g owns one right-hand side `col`; LU is read from shared memory.
+template <typename T>
+__device__ __forceinline__ void group_getrs(const T* __restrict__ LU, const int (&piv)[8], T (&col)[8])
+{
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+#pragma unroll
+        for (int r = k + 1; r < 8; ++r)
+            if (piv[k] == r) { const T t = col[k]; col[k] = col[r]; col[r] = t; }
+    }
+#pragma unroll
+    for (int r = 1; r < 8; ++r)
+#pragma unroll
+        for (int k = 0; k < r; ++k) col[r] = tfma<T>(-LU[r * 8 + k], col[k], col[r]);
+#pragma unroll
+    for (int r = 7; r >= 0; --r) {
+#pragma unroll
+        for (int k = r + 1; k < 8; ++k) col[r] = tfma<T>(-LU[r * 8 + k], col[k], col[r]);
+        col[r] = col[r] / LU[r * 8 + r];
+    }
+}
+
+// DLT row g of A + 1e-4 I (spatial_transformer3.py:145,160-167) and its right-hand side b[g] (:169)
+template <typename T>
+__device__ __forceinline__ void dlt_row(const float* __restrict__ theta_n, int i, int j, int gh, int gw, int g,
+                                        T (&row)[8], T& b)
+{
+    float xf, yf; int vid;
+    cell_corner(i, j, gh, gw, g & 3, xf, yf, vid);
+    const T x = xf, y = yf, u = theta_n[vid * 2], v = theta_n[vid * 2 + 1];
+    const T t = (g < 4) ? u : v;
+    const T nx = -x * t, ny = -y * t;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) row[c] = 0;
+    if (g < 4) { row[0] = x; row[1] = y; row[2] = 1; } else { row[3] = x; row[4] = y; row[5] = 1; }
+    row[6] = nx; row[7] = ny;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) if (c == g) row[c] = row[c] + (T)1e-4f;
+    b = t;
+}
+
+constexpr int kCellsPerBlock = 16;      // 128 threads
+
+__global__ void __launch_bounds__(kCellsPerBlock * 8)
+solve_h_fwd_kernel(const float* __restrict__ theta, int N, int gh, int gw, float* __restrict__ Hs)
+{
+    __shared__ float sLU[kCellsPerBlock][64];
+    __shared__ float sINV[kCellsPerBlock][64];
+    const int slot = threadIdx.x >> 3, g = threadIdx.x & 7;
+    const int ncell = N * gh * gw;
+    int cell = blockIdx.x * kCellsPerBlock + slot;
+    const bool live = cell < ncell;
+    if (!live) cell = ncell - 1;                       // keep the whole warp converged for the shuffles
+    const int n = cell / (gh * gw), ij = cell % (gh * gw), i = ij / gw, j = ij % gw;
+    const float* theta_n = theta + (size_t)n * (gh + 1) * (gw + 1) * 2;
+
+    float row[8], b; int piv[8];
+    dlt_row<float>(theta_n, i, j, gh, gw, g, row, b);
+    group_lu<float>(row, piv, g);
+#pragma unroll
+    for (int c = 0; c < 8; ++c) sLU[slot][g * 8 + c] = row[c];
+    __syncwarp();
+    float col[8];
+#pragma unroll
+    for (int r = 0; r < 8; ++r) col[r] = (r == g) ? 1.0f : 0.0f;
+    group_getrs<float>(sLU[slot], piv, col);
+#pragma unroll
+    for (int r = 0; r < 8; ++r) sINV[slot][r * 8 + g] = col[r];
+    __syncwarp();
+    // matmul(pinv(A), b): FMA chain over k (spatial_transformer3.py:173)
+    float acc = __fmul_rn(sINV[slot][g * 8], __shfl_sync(0xffffffffu, b, 0, 8));
+#pragma unroll
+    for (int k = 1; k < 8; ++k) acc = __fmaf_rn(sINV[slot][g * 8 + k], __shfl_sync(0xffffffffu, b, k, 8), acc);
+    if (live) {
+        Hs[(size_t)cell * 9 + g] = acc;
+        if (g == 0) Hs[(size_t)cell * 9 + 8] = 1.0f;
+    }
+}
+
+// ---------------------------------------------------------------- K4: adjoint of the solve
+// dHs_part [N*gh*gw, nparts, 8] tile partials (nparts may be 1) -> dtheta [N,gh+1,gw+1,2].
+// Per cell (8-lane group, fp64): g = sum of partials, lambda = (A+1e-4 I)^-T g,
+// d u_k = lambda_k * s_k, d v_k = lambda_{4+k} * s_k, s_k = 1 + h6 x_k + h7 y_k; then each vertex gathers its
+// (up to) four cells in a fixed order -> deterministic, no atomics.  One block per sample.
+__global__ void solve_h_bwd_kernel(const float* __restrict__ theta, const float* __restrict__ Hs,
+                                   const float* __restrict__ dHs_part, int nparts, int part_stride,
+                                   int N, int gh, int gw, float* __restrict__ dtheta)
+{
+    extern __shared__ double sm[];
+    const int ncell_s = gh * gw;
+    double* sLU = sm;                                  // [ncell_s][64]
+    double* sDuv = sm + (size_t)ncell_s * 64;          // [ncell_s][8]  (du0..3, dv0..3)
+    const int n = blockIdx.x;
+    const int g = threadIdx.x & 7;
+    const float* theta_n = theta + (size_t)n * (gh + 1) * (gw + 1) * 2;
+
+    for (int base = 0; base < ncell_s; base += blockDim.x >> 3) {
+        int ij = base + (threadIdx.x >> 3);
+        const bool live = ij < ncell_s;
+        if (!live) ij = ncell_s - 1;
+        const int i = ij / gw, j = ij % gw;
+        const size_t cell = (size_t)n * ncell_s + ij;
+        // transpose system: lane g holds row g of M^T = column g of M
+        double mrow[8], bdummy, trow[8];
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+            double tmp[8];
+            dlt_row<double>(theta_n, i, j, gh, gw, r, tmp, bdummy);
+            double pick = 0;
+#pragma unroll
+            for (int c = 0; c < 8; ++c) if (c == g) pick = tmp[c];
+            trow[r] = pick;
+        }
+#pragma unroll
+        for (int c = 0; c < 8; ++c) mrow[c] = trow[c];
+        int piv[8];
+        group_lu<double>(mrow, piv, g);
+        double* LU = sLU + (size_t)ij * 64;
+        if (live) {
+#pragma unroll
+            for (int c = 0; c < 8; ++c) LU[g * 8 + c] = mrow[c];
+        }
+        __syncwarp();
+        // right-hand side: the summed dH[0:8] of this cell (every lane builds the full vector)
+        double rhs[8];
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+            double s = 0;
+            for (int p = 0; p < nparts; ++p) s += (double)dHs_part[(cell * nparts + p) * part_stride + r];
+            rhs[r] = s;
+        }
+        if (live) group_getrs<double>(LU, piv, rhs);    // rhs -> lambda (all lanes compute the same thing)
+        const double h6 = Hs[cell * 9 + 6], h7 = Hs[cell * 9 + 7];
+        float xf, yf; int vid;
+        cell_corner(i, j, gh, gw, g & 3, xf, yf, vid);
+        const double s = 1.0 + h6 * (double)xf + h7 * (double)yf;
+        double lam = 0;
+#pragma unroll
+        for (int r = 0; r < 8; ++r) if (r == g) lam = rhs[r];
+        if (live) sDuv[(size_t)ij * 8 + g] = lam * s;
+    }
+    __syncthreads();
+    const int nv2 = (gh + 1) * (gw + 1) * 2;
+    for (int t = threadIdx.x; t < nv2; t += blockDim.x) {
+        const int k = t & 1, tot = t >> 1, i = tot / (gw + 1), j = tot % (gw + 1);
+        const int ci[4] = { i, i, i - 1, i - 1 }, cj[4] = { j, j - 1, j, j - 1 };
+        double acc = 0;
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+            if (ci[c] >= 0 && ci[c] < gh && cj[c] >= 0 && cj[c] < gw)
+                acc += sDuv[(size_t)(ci[c] * gw + cj[c]) * 8 + k * 4 + c];
+        dtheta[(size_t)n * nv2 + t] = (float)acc;
+    }
+}
+
+// ---------------------------------------------------------------- launchers
+int launch_vertices_fwd(const float* head, int N, int gh, int gw, float do_crop_rate, float* pts2, float* pts1,
+                        cudaStream_t st)
+{
+    const int tot = N * (gh + 1) * (gw + 1) * 2;
+    vertices_fwd_kernel<<<(tot + 127) / 128, 128, 0, st>>>(head, N, gh, gw, do_crop_rate, pts2, pts1);
+    return check_launch("vertices_fwd");
+}
+
+int launch_vertices_bwd(const float* head, const float* d_pts2, const float* d_pts1, int N, int gh, int gw,
+                        float do_crop_rate, float* d_head, cudaStream_t st)
+{
+    const int tot = N * (gh + 1) * (gw + 1) * 2;
+    vertices_bwd_kernel<<<(tot + 127) / 128, 128, 0, st>>>(head, d_pts2, d_pts1, N, gh, gw, do_crop_rate, d_head);
+    return check_launch("vertices_bwd");
+}
+
+int launch_solve_h_fwd(const float* theta, int N, int gh, int gw, float* Hs, cudaStream_t st)
+{
+    const int ncell = N * gh * gw;
+    solve_h_fwd_kernel<<<(ncell + kCellsPerBlock - 1) / kCellsPerBlock, kCellsPerBlock * 8, 0, st>>>(theta, N, gh, gw, Hs);
+    return check_launch("solve_h_fwd");
+}
+
+int launch_solve_h_bwd(const float* theta, const float* Hs, const float* dHs_part, int nparts, int part_stride,
+                       int N, int gh, int gw, float* dtheta, cudaStream_t st)
+{
+    const int ncell_s = gh * gw;
+    int threads = ((ncell_s * 8 + 31) / 32) * 32;
+    if (threads > 256) threads = 256;
+    const size_t smem = (size_t)ncell_s * (64 + 8) * sizeof(double);
+    if (smem > 48 * 1024) return set_error(MGW_ERR_UNSUPPORTED, "solve_h_bwd: grid too large (gh*gw > 85)");
+    solve_h_bwd_kernel<<<N, threads, smem, st>>>(theta, Hs, dHs_part, nparts, part_stride, N, gh, gw, dtheta);
+    return check_launch("solve_h_bwd");
+}
+
+}  // namespace mgw

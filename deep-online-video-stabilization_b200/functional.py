@@ -1,0 +1,132 @@
+"""torch.autograd glue: each Function is one forward C-ABI call and one backward C-ABI call (see ops.py)."""
+import torch
+
+from . import ops
+
+
+class MeshWarp(torch.autograd.Function):
+    """spatial_transformer3.transformer(U, theta) (reference spatial_transformer3.py:19-365)."""
+
+    @staticmethod
+    def forward(ctx, U, theta):
+        out, black, img, Hs = ops.mesh_warp_fwd(U, theta)
+        ctx.save_for_backward(U, theta, Hs)
+        ctx.mark_non_differentiable(black, Hs)
+        return out, black, img, Hs
+
+    @staticmethod
+    def backward(ctx, d_out, _d_black, d_img, _d_Hs):
+        U, theta, Hs = ctx.saved_tensors
+        if d_out is None:
+            d_out = torch.zeros_like(U)
+        dU, dtheta = ops.mesh_warp_bwd(U, theta, Hs, d_out.contiguous(), None if d_img is None else d_img.contiguous(),
+                                       want_dU=ctx.needs_input_grad[0])
+        return dU, dtheta
+
+
+class HomographyWarp(torch.autograd.Function):
+    """spatial_transformer.transformer(U, theta[N,9], out_size) (reference spatial_transformer.py:18-197)."""
+
+    @staticmethod
+    def forward(ctx, U, theta, out_size):
+        out, black, _ = ops.homography_warp_fwd(U, theta, out_size)
+        ctx.save_for_backward(U, theta)
+        ctx.out_size = out_size
+        ctx.mark_non_differentiable(black)
+        return out, black
+
+    @staticmethod
+    def backward(ctx, d_out, _d_black):
+        U, theta = ctx.saved_tensors
+        dU, dtheta = ops.homography_warp_bwd(U, theta, d_out.contiguous(), ctx.out_size, want_dU=ctx.needs_input_grad[0])
+        return dU, dtheta, None
+
+
+class Interpolate(torch.autograd.Function):
+    """interpolate(im, x, y, out_size) (reference spatial_transformer.py:200-281)."""
+
+    @staticmethod
+    def forward(ctx, im, x, y, out_size):
+        out = ops.interp_fwd(im, x, y, out_size)
+        ctx.save_for_backward(im, x, y)
+        ctx.out_size = out_size
+        return out
+
+    @staticmethod
+    def backward(ctx, d_out):
+        im, x, y = ctx.saved_tensors
+        need = ctx.needs_input_grad
+        d_im, dx, dy = ops.interp_bwd(im, x, y, d_out.contiguous(), ctx.out_size, want_dim=need[0], want_dxy=need[1] or need[2])
+        return d_im, dx, dy, None
+
+
+class Vertices(torch.autograd.Function):
+    """get_4_pts (reference s_net_bundle_nobm.py:29-71)."""
+
+    @staticmethod
+    def forward(ctx, head, gh, gw, do_crop_rate):
+        pts1, pts2 = ops.vertices_fwd(head, gh, gw, do_crop_rate)
+        ctx.save_for_backward(head)
+        ctx.cfg = (gh, gw, do_crop_rate)
+        return pts1, pts2
+
+    @staticmethod
+    def backward(ctx, d_pts1, d_pts2):
+        (head,) = ctx.saved_tensors
+        gh, gw, rate = ctx.cfg
+        d_head = ops.vertices_bwd(head, None if d_pts2 is None else d_pts2.contiguous(),
+                                  None if d_pts1 is None else d_pts1.contiguous(), gh, gw, rate)
+        return d_head, None, None, None
+
+
+class ImgLoss(torch.autograd.Function):
+    """img_loss (reference s_net_bundle_nobm.py:347-352); batch = the divisor (global batch under data parallelism)."""
+
+    @staticmethod
+    def forward(ctx, out, y, black, batch):
+        sums = ops.img_loss_fwd(out, y, black)
+        ctx.save_for_backward(out, y, black, sums)
+        ctx.batch = batch
+        return (sums[:, 0] / (sums[:, 1] + 1e-8)).sum() / batch
+
+    @staticmethod
+    def backward(ctx, g):
+        out, y, black, sums = ctx.saved_tensors
+        d_out = ops.img_loss_bwd(out, y, black, sums, float(g) * out.shape[0] / ctx.batch)
+        return d_out, (-d_out if ctx.needs_input_grad[1] else None), None, None
+
+
+class FeatureLoss(torch.autograd.Function):
+    """feature_loss with warp_pts (reference s_net_bundle_nobm.py:215-230,335-343)."""
+
+    @staticmethod
+    def forward(ctx, matches, mask, flow, batch):
+        per, warpped = ops.feature_loss_fwd(matches, mask, flow)
+        ctx.save_for_backward(matches, mask, flow)
+        ctx.batch = batch
+        ctx.mark_non_differentiable(warpped)
+        return per.sum() / batch, warpped
+
+    @staticmethod
+    def backward(ctx, g, _gw):
+        matches, mask, flow = ctx.saved_tensors
+        d_flow = ops.feature_loss_bwd(matches, mask, flow, float(g) * flow.shape[0] / ctx.batch)
+        return None, None, d_flow, None
+
+
+class TempLoss(torch.autograd.Function):
+    """temp_loss (reference train_bundle_nobm.py:115-125)."""
+
+    @staticmethod
+    def forward(ctx, out1, black1, out2, black2, flow, batch, use_temp_loss):
+        sums = ops.temp_loss_fwd(out1, black1, out2, black2, flow)
+        ctx.save_for_backward(out1, black1, out2, black2, flow, sums)
+        ctx.cfg = (batch, use_temp_loss)
+        return (sums[:, 0] / (sums[:, 1] + 1e-8)).sum() / batch * use_temp_loss
+
+    @staticmethod
+    def backward(ctx, g):
+        out1, black1, out2, black2, flow, sums = ctx.saved_tensors
+        batch, use = ctx.cfg
+        d1, d2 = ops.temp_loss_bwd(out1, black1, out2, black2, flow, sums, float(g) * use * out1.shape[0] / batch)
+        return d1, None, d2, None, None, None, None

@@ -1,0 +1,255 @@
+"""Thin host wrappers over the C ABI: torch tensors are only carriers of device memory and the current stream.
+
+Every function takes/returns contiguous fp32 CUDA tensors in the reference's layouts (NHWC images,
+mesh [N,gh+1,gw+1,2], Hs [N,gh,gw,9]).  No computation happens in Python and nothing falls back to torch.
+"""
+import torch
+
+from ._lib import check, lib
+
+
+def _chk(t, name, dtype=torch.float32):
+    if not isinstance(t, torch.Tensor):
+        raise TypeError('%s must be a torch.Tensor' % name)
+    if not t.is_cuda:
+        raise RuntimeError('%s must live on a CUDA device: this library has no CPU path' % name)
+    if t.dtype != dtype:
+        raise TypeError('%s must be %s (got %s)' % (name, dtype, t.dtype))
+    return t if t.is_contiguous() else t.contiguous()
+
+
+def _p(t):
+    return None if t is None else t.data_ptr()
+
+
+def _st():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _mesh_dims(U, grid_tensor, what):
+    n, h, w, c = U.shape
+    if grid_tensor.dim() != 4 or grid_tensor.shape[0] != n:
+        raise ValueError('%s has shape %s, batch %d expected' % (what, tuple(grid_tensor.shape), n))
+    return n, h, w, c
+
+
+def vertices_fwd(head, gh, gw, do_crop_rate=0.8, want_pts1=True):
+    head = _chk(head, 'head')
+    n = head.shape[0]
+    if head.numel() != n * 2 * (gh + 1) * (gw + 1):
+        raise ValueError('head must be [N, %d]' % (2 * (gh + 1) * (gw + 1)))
+    pts2 = torch.empty((n, gh + 1, gw + 1, 2), device=head.device, dtype=torch.float32)
+    pts1 = torch.empty((n, gh, gw, 8), device=head.device, dtype=torch.float32) if want_pts1 else None
+    with torch.cuda.device(head.device):
+        check(lib.mgw_vertices_fwd(_p(head), n, gh, gw, do_crop_rate, _p(pts2), _p(pts1), _st()), 'mgw_vertices_fwd')
+    return pts1, pts2
+
+
+def vertices_bwd(head, d_pts2, d_pts1, gh, gw, do_crop_rate=0.8):
+    head = _chk(head, 'head')
+    d_pts2 = None if d_pts2 is None else _chk(d_pts2, 'd_pts2')
+    d_pts1 = None if d_pts1 is None else _chk(d_pts1, 'd_pts1')
+    d_head = torch.empty_like(head)
+    with torch.cuda.device(head.device):
+        check(lib.mgw_vertices_bwd(_p(head), _p(d_pts2), _p(d_pts1), head.shape[0], gh, gw, do_crop_rate, _p(d_head), _st()),
+              'mgw_vertices_bwd')
+    return d_head
+
+
+def solve_h_fwd(theta):
+    theta = _chk(theta, 'theta')
+    n, gh1, gw1, two = theta.shape
+    assert two == 2
+    Hs = torch.empty((n, gh1 - 1, gw1 - 1, 9), device=theta.device, dtype=torch.float32)
+    with torch.cuda.device(theta.device):
+        check(lib.mgw_solve_h_fwd(_p(theta), n, gh1 - 1, gw1 - 1, _p(Hs), _st()), 'mgw_solve_h_fwd')
+    return Hs
+
+
+def solve_h_bwd(theta, Hs, dHs):
+    theta, Hs, dHs = _chk(theta, 'theta'), _chk(Hs, 'Hs'), _chk(dHs, 'dHs')
+    n, gh, gw, _ = Hs.shape
+    dtheta = torch.empty_like(theta)
+    with torch.cuda.device(theta.device):
+        check(lib.mgw_solve_h_bwd(_p(theta), _p(Hs), _p(dHs), n, gh, gw, _p(dtheta), _st()), 'mgw_solve_h_bwd')
+    return dtheta
+
+
+def warp_fwd(U, Hs, want_out=True, want_black=True, want_img=True, want_cell=False):
+    U, Hs = _chk(U, 'U'), _chk(Hs, 'Hs')
+    n, h, w, c = _mesh_dims(U, Hs, 'Hs')
+    gh, gw = Hs.shape[1:3]
+    dev = U.device
+    out = torch.empty((n, h, w, c), device=dev, dtype=torch.float32) if want_out else None
+    black = torch.empty((n, h, w), device=dev, dtype=torch.float32) if want_black else None
+    img = torch.empty((n, h, w, 2), device=dev, dtype=torch.float32) if want_img else None
+    cell = torch.empty((n, h, w), device=dev, dtype=torch.int32) if want_cell else None
+    with torch.cuda.device(dev):
+        check(lib.mgw_warp_fwd(_p(U), _p(Hs), n, h, w, c, gh, gw, _p(out), _p(black), _p(img), _p(cell), _st()), 'mgw_warp_fwd')
+    return out, black, img, cell
+
+
+def _workspace(nbytes, dev):
+    return torch.empty((max(nbytes, 256) + 255) // 256 * 64, device=dev, dtype=torch.float32) if nbytes else None
+
+
+def warp_bwd(U, Hs, d_out, d_img=None, want_dU=True):
+    U, Hs, d_out = _chk(U, 'U'), _chk(Hs, 'Hs'), _chk(d_out, 'd_out')
+    d_img = None if d_img is None else _chk(d_img, 'd_img')
+    n, h, w, c = _mesh_dims(U, Hs, 'Hs')
+    gh, gw = Hs.shape[1:3]
+    dU = torch.empty_like(U) if want_dU else None
+    dHs = torch.empty_like(Hs)
+    ws = _workspace(lib.mgw_warp_bwd_workspace_bytes(n, h, w, c, gh, gw), U.device)
+    with torch.cuda.device(U.device):
+        check(lib.mgw_warp_bwd(_p(U), _p(Hs), _p(d_out), _p(d_img), n, h, w, c, gh, gw, _p(dU), _p(dHs), _p(ws), _st()),
+              'mgw_warp_bwd')
+    return dU, dHs
+
+
+def mesh_warp_fwd(U, theta, want_out=True, want_black=True, want_img=True):
+    U, theta = _chk(U, 'U'), _chk(theta, 'theta')
+    n, h, w, c = _mesh_dims(U, theta, 'theta')
+    gh, gw = theta.shape[1] - 1, theta.shape[2] - 1
+    if theta.shape[3] != 2 or gh < 1 or gw < 1:
+        raise ValueError('theta must be [N, gh+1, gw+1, 2] mesh vertices, got %s' % (tuple(theta.shape),))
+    dev = U.device
+    Hs = torch.empty((n, gh, gw, 9), device=dev, dtype=torch.float32)
+    out = torch.empty((n, h, w, c), device=dev, dtype=torch.float32) if want_out else None
+    black = torch.empty((n, h, w), device=dev, dtype=torch.float32) if want_black else None
+    img = torch.empty((n, h, w, 2), device=dev, dtype=torch.float32) if want_img else None
+    with torch.cuda.device(dev):
+        check(lib.mgw_mesh_warp_fwd(_p(U), _p(theta), n, h, w, c, gh, gw, _p(Hs), _p(out), _p(black), _p(img), _st()),
+              'mgw_mesh_warp_fwd')
+    return out, black, img, Hs
+
+
+def mesh_warp_bwd(U, theta, Hs, d_out, d_img=None, want_dU=True):
+    U, theta, Hs, d_out = _chk(U, 'U'), _chk(theta, 'theta'), _chk(Hs, 'Hs'), _chk(d_out, 'd_out')
+    d_img = None if d_img is None else _chk(d_img, 'd_img')
+    n, h, w, c = _mesh_dims(U, theta, 'theta')
+    gh, gw = Hs.shape[1:3]
+    dU = torch.empty_like(U) if want_dU else None
+    dtheta = torch.empty_like(theta)
+    ws = _workspace(lib.mgw_mesh_warp_bwd_workspace_bytes(n, h, w, c, gh, gw), U.device)
+    with torch.cuda.device(U.device):
+        check(lib.mgw_mesh_warp_bwd(_p(U), _p(theta), _p(Hs), _p(d_out), _p(d_img), n, h, w, c, gh, gw, _p(dU), _p(dtheta),
+                                    _p(ws), _st()), 'mgw_mesh_warp_bwd')
+    return dU, dtheta
+
+
+def interp_fwd(im, x, y, out_size):
+    im, x, y = _chk(im, 'im'), _chk(x, 'x'), _chk(y, 'y')
+    n, ih, iw, c = im.shape
+    oh, ow = int(out_size[0]), int(out_size[1])
+    if x.numel() != n * oh * ow or y.numel() != n * oh * ow:
+        raise ValueError('x and y must hold N*out_h*out_w coordinates')
+    out = torch.empty((n, oh, ow, c), device=im.device, dtype=torch.float32)
+    with torch.cuda.device(im.device):
+        check(lib.mgw_interp_fwd(_p(im), _p(x), _p(y), n, ih, iw, c, oh, ow, _p(out), _st()), 'mgw_interp_fwd')
+    return out
+
+
+def interp_bwd(im, x, y, d_out, out_size, want_dim=True, want_dxy=True):
+    im, x, y, d_out = _chk(im, 'im'), _chk(x, 'x'), _chk(y, 'y'), _chk(d_out, 'd_out')
+    n, ih, iw, c = im.shape
+    oh, ow = int(out_size[0]), int(out_size[1])
+    d_im = torch.empty_like(im) if want_dim else None
+    dx = torch.empty_like(x) if want_dxy else None
+    dy = torch.empty_like(y) if want_dxy else None
+    with torch.cuda.device(im.device):
+        check(lib.mgw_interp_bwd(_p(im), _p(x), _p(y), _p(d_out), n, ih, iw, c, oh, ow, _p(d_im), _p(dx), _p(dy), _st()),
+              'mgw_interp_bwd')
+    return d_im, dx, dy
+
+
+def homography_warp_fwd(U, theta, out_size, want_img=False):
+    U, theta = _chk(U, 'U'), _chk(theta, 'theta')
+    n, h, w, c = U.shape
+    if theta.numel() != n * 9:
+        raise ValueError('theta must be [N, 9]')
+    oh, ow = int(out_size[0]), int(out_size[1])
+    out = torch.empty((n, oh, ow, c), device=U.device, dtype=torch.float32)
+    black = torch.empty((n, oh, ow), device=U.device, dtype=torch.float32)
+    img = torch.empty((n, oh, ow, 2), device=U.device, dtype=torch.float32) if want_img else None
+    with torch.cuda.device(U.device):
+        check(lib.mgw_homography_warp_fwd(_p(U), _p(theta), n, h, w, c, oh, ow, _p(out), _p(black), _p(img), _st()),
+              'mgw_homography_warp_fwd')
+    return out, black, img
+
+
+def homography_warp_bwd(U, theta, d_out, out_size, want_dU=True):
+    U, theta, d_out = _chk(U, 'U'), _chk(theta, 'theta'), _chk(d_out, 'd_out')
+    n, h, w, c = U.shape
+    oh, ow = int(out_size[0]), int(out_size[1])
+    dU = torch.empty_like(U) if want_dU else None
+    dtheta = torch.empty((n, 9), device=U.device, dtype=torch.float32)
+    with torch.cuda.device(U.device):
+        check(lib.mgw_homography_warp_bwd(_p(U), _p(theta), _p(d_out), n, h, w, c, oh, ow, _p(dU), _p(dtheta), _st()),
+              'mgw_homography_warp_bwd')
+    return dU, dtheta.reshape(theta.shape)
+
+
+def img_loss_fwd(out, y, black):
+    out, y, black = _chk(out, 'out'), _chk(y, 'y'), _chk(black, 'black')
+    n, h, w, c = out.shape
+    sums = torch.empty((n, 2), device=out.device, dtype=torch.float32)
+    with torch.cuda.device(out.device):
+        check(lib.mgw_img_loss_fwd(_p(out), _p(y), _p(black), n, h, w, c, _p(sums), _st()), 'mgw_img_loss_fwd')
+    return sums
+
+
+def img_loss_bwd(out, y, black, sums, upstream):
+    out, y, black, sums = _chk(out, 'out'), _chk(y, 'y'), _chk(black, 'black'), _chk(sums, 'sums')
+    n, h, w, c = out.shape
+    d_out = torch.empty_like(out)
+    with torch.cuda.device(out.device):
+        check(lib.mgw_img_loss_bwd(_p(out), _p(y), _p(black), _p(sums), float(upstream), n, h, w, c, _p(d_out), _st()),
+              'mgw_img_loss_bwd')
+    return d_out
+
+
+def feature_loss_fwd(matches, mask, img, want_warpped=True):
+    matches, mask, img = _chk(matches, 'matches'), _chk(mask, 'mask'), _chk(img, 'img')
+    n, m, _ = matches.shape
+    _, h, w, _ = img.shape
+    warpped = torch.empty((n, m, 2), device=img.device, dtype=torch.float32) if want_warpped else None
+    per = torch.empty((n,), device=img.device, dtype=torch.float32)
+    with torch.cuda.device(img.device):
+        check(lib.mgw_feature_loss_fwd(_p(matches), _p(mask), _p(img), n, m, h, w, _p(warpped), _p(per), _st()),
+              'mgw_feature_loss_fwd')
+    return per, warpped
+
+
+def feature_loss_bwd(matches, mask, img, upstream, d_img=None):
+    matches, mask, img = _chk(matches, 'matches'), _chk(mask, 'mask'), _chk(img, 'img')
+    n, m, _ = matches.shape
+    _, h, w, _ = img.shape
+    if d_img is None:
+        d_img = torch.zeros_like(img)
+    with torch.cuda.device(img.device):
+        check(lib.mgw_feature_loss_bwd(_p(matches), _p(mask), _p(img), float(upstream), n, m, h, w, _p(d_img), _st()),
+              'mgw_feature_loss_bwd')
+    return d_img
+
+
+def temp_loss_fwd(out1, black1, out2, black2, flow):
+    out1, black1, out2, black2, flow = (_chk(t, nm) for t, nm in ((out1, 'out1'), (black1, 'black1'), (out2, 'out2'),
+                                                                     (black2, 'black2'), (flow, 'flow')))
+    n, h, w, c = out1.shape
+    sums = torch.empty((n, 2), device=out1.device, dtype=torch.float32)
+    with torch.cuda.device(out1.device):
+        check(lib.mgw_temp_loss_fwd(_p(out1), _p(black1), _p(out2), _p(black2), _p(flow), n, h, w, c, _p(sums), _st()),
+              'mgw_temp_loss_fwd')
+    return sums
+
+
+def temp_loss_bwd(out1, black1, out2, black2, flow, sums, upstream):
+    out1, black1, out2, black2, flow, sums = (_chk(t, nm) for t, nm in ((out1, 'out1'), (black1, 'black1'), (out2, 'out2'),
+                                                                           (black2, 'black2'), (flow, 'flow'), (sums, 'sums')))
+    n, h, w, c = out1.shape
+    d1, d2 = torch.empty_like(out1), torch.empty_like(out2)
+    with torch.cuda.device(out1.device):
+        check(lib.mgw_temp_loss_bwd(_p(out1), _p(black1), _p(out2), _p(black2), _p(flow), _p(sums), float(upstream), n, h, w, c,
+                                    _p(d1), _p(d2), _st()), 'mgw_temp_loss_bwd')
+    return d1, d2

@@ -1,0 +1,78 @@
+"""Data parallelism for the warp path: one process per GPU, frames/clips sharded along the batch, NO communication
+in the forward pass; the only collective is an all-reduce of the mesh-head gradient.
+
+The reference is single-GPU (no collective anywhere).  Under data parallelism every sample is independent through
+the whole path (theta is a per-sample activation), so the only cross-rank quantity downstream of the path is the
+gradient of the regression head that produces theta: fc_weights [512, 2*(gh+1)*(gw+1)] + bias (reference
+resnet.py:51-53 via s_net_bundle_nobm.py:259) = 25 650 fp32 = 100.2 KB for the 4x4 mesh -- latency-bound, so it is
+issued on a side stream and overlapped with the next step's forward.
+"""
+import os
+
+import torch
+import torch.distributed as dist
+
+
+def init_from_env(backend=None):
+    """(rank, world, local_rank); initialises torch.distributed when WORLD_SIZE > 1 (torchrun env)."""
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    if world > 1 and not dist.is_initialized():
+        if backend is None:
+            backend = 'nccl' if torch.cuda.is_available() else 'gloo'
+        if backend == 'nccl':
+            torch.cuda.set_device(local)
+        dist.init_process_group(backend=backend, rank=rank, world_size=world)
+    return rank, world, local
+
+
+def shard_bounds(n_global, rank, world):
+    """contiguous batch slice [lo, hi) of rank `rank`; the first n_global % world ranks take one extra sample."""
+    base, extra = divmod(n_global, world)
+    lo = rank * base + min(rank, extra)
+    return lo, lo + base + (1 if rank < extra else 0)
+
+
+def shard(t, rank, world):
+    lo, hi = shard_bounds(t.shape[0], rank, world)
+    return t[lo:hi].contiguous()
+
+
+class MeshHeadGradReducer:
+    """Sums the mesh-head gradient over ranks with one all-reduce per step on a side stream.
+
+    head_grad(features [n_local,F], dtheta [n_local,gh+1,gw+1,2]) -> flat [F*V + V] buffer (dW = features^T . dtheta,
+    db = sum_n dtheta), already scaled for the GLOBAL batch by the losses.  launch() starts the all-reduce after the
+    producing stream; wait() makes the current stream wait for it (call it right before the optimizer step).
+    """
+
+    def __init__(self, n_features, n_out, device):
+        self.buf = torch.zeros(n_features * n_out + n_out, device=device, dtype=torch.float32)
+        self.nf, self.no = n_features, n_out
+        self.side = torch.cuda.Stream(device=device) if torch.device(device).type == 'cuda' else None
+        self.work = None
+
+    def head_grad(self, features, dtheta):
+        d = dtheta.reshape(dtheta.shape[0], self.no)
+        torch.mm(features.t(), d, out=self.buf[:self.nf * self.no].view(self.nf, self.no))
+        torch.sum(d, dim=0, out=self.buf[self.nf * self.no:])
+        return self.buf
+
+    def launch(self):
+        if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+            return
+        if self.side is None:
+            self.work = dist.all_reduce(self.buf, op=dist.ReduceOp.SUM, async_op=True)
+            return
+        self.side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(self.side):
+            dist.all_reduce(self.buf, op=dist.ReduceOp.SUM)
+
+    def wait(self):
+        if self.side is not None:
+            torch.cuda.current_stream().wait_stream(self.side)
+        elif self.work is not None:
+            self.work.wait()
+            self.work = None
+        return self.buf

