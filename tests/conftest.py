@@ -37,7 +37,7 @@ def golden_inputs(name, g):
         return g['U'], g['d_out'], g['d_img']
     n, h, w, c = (int(v) for v in g['shape'])
     seed = int(g['seed'])
-    U = synth.noise_image(n, h, w, c, seed) if 'noise' in name else synth.smooth_image(n, h, w, c, seed)
+    U = synth.noise_image(n, h, w, c, seed) if str(g['kind']) == 'noise' else synth.smooth_image(n, h, w, c, seed)
     return U, synth.randn((n, h, w, c), seed + 100), synth.randn((n, h, w, 2), seed + 200, 0.1)
 
 
@@ -52,9 +52,11 @@ def bits_equal(a, b):
     return (a.view(np.int32) == b.view(np.int32)) | (np.isnan(a) & np.isnan(b))
 
 
-MESH_CASES = ['mesh_smooth_s03', 'mesh_noise_s08', 'mesh_identity', 'mesh_ragged_c1', 'mesh_grid23_c4',
-              'mesh_fold_clamp_shift', 'mesh_full_noise_s05', 'mesh_full_identity']
-SMALL_MESH_CASES = MESH_CASES[:6]
+SMALL_MESH_CASES = ['mesh_smooth_s03', 'mesh_noise_s08', 'mesh_identity', 'mesh_ragged_c1', 'mesh_grid23_c4',
+                    'mesh_fold_clamp_shift']
+TMA_MESH_CASES = ['mesh_tma_ragged', 'mesh_tma_fold_clamp_shift', 'mesh_tma_c1', 'mesh_tma_c4_g22']     # cells >= 8 x 32 px
+FULL_MESH_CASES = ['mesh_full_noise_s05', 'mesh_full_identity']
+MESH_CASES = SMALL_MESH_CASES + TMA_MESH_CASES + FULL_MESH_CASES
 
 
 def relmax(a, b):

@@ -10,7 +10,8 @@ import pytest
 import torch
 
 import c_oracle
-from conftest import (MESH_CASES, SMALL_MESH_CASES, bits_equal, golden_black, golden_inputs, load_golden, relmax)
+from conftest import (FULL_MESH_CASES, MESH_CASES, SMALL_MESH_CASES, TMA_MESH_CASES, bits_equal, golden_black, golden_inputs,
+                      load_golden, relmax)
 
 pytestmark = pytest.mark.gpu
 
@@ -84,14 +85,55 @@ def test_transformer_forward(mgw, name, impl):
     rb = golden_black(g)
     knife = (np.abs(np.abs(g['ref_img']) - 1).min(-1) < 2e-5)          # |coord| within a few ulp of the +-1 edge
     assert ((black != rb) & ~knife & fin).sum() == 0
-    if 'smooth' in name or 'identity' in name:
+    if str(g['kind']) == 'smooth':
         assert np.abs(out - g['ref_out'])[fin].max() < 1e-5
 
 
 # ------------------------------------------------------------------ backward
+BWD_CASES = SMALL_MESH_CASES[:5] + ['mesh_tma_ragged', 'mesh_tma_c1', 'mesh_tma_c4_g22'] + FULL_MESH_CASES
+
+
 @pytest.mark.parametrize('impl', IMPLS)
-@pytest.mark.parametrize('name', SMALL_MESH_CASES[:5] + ['mesh_full_noise_s05', 'mesh_full_identity'])
-def test_transformer_backward(mgw, name, impl):
+@pytest.mark.parametrize('name', BWD_CASES)
+def test_warp_backward_given_reference_hs(mgw, name, impl):
+    """stage K3: with the reference's own Hs the taps are identical, so dU / dHs differ from the reference's autograd
+    only by fp32 summation order."""
+    mgw.set_impl(impl)
+    g = load_golden(name)
+    U, d_out, d_img = golden_inputs(name, g)
+    dU, dHs = mgw.ops.warp_bwd(dev(U), dev(g['ref_Hs']), dev(d_out), dev(d_img))
+    assert relmax(dHs.cpu().numpy()[..., :8], g['ref_dHs'][..., :8]) < 1e-4
+    assert (dHs.cpu().numpy()[..., 8] == 0).all()
+    if 'ref_dU' in g:
+        assert relmax(dU.cpu().numpy(), g['ref_dU']) < 1e-4
+    # d_img = None and dU skipped are the same numbers minus those terms
+    dU0, dHs0 = mgw.ops.warp_bwd(dev(U), dev(g['ref_Hs']), dev(d_out), dev(np.zeros_like(d_img)), want_dU=False)
+    dU1, dHs1 = mgw.ops.warp_bwd(dev(U), dev(g['ref_Hs']), dev(d_out), None)
+    assert dU0 is None and relmax(dHs0.cpu().numpy(), dHs1.cpu().numpy()) < 1e-5
+
+
+@pytest.mark.parametrize('name', BWD_CASES)
+def test_solve_h_backward(mgw, name):
+    """stage K4: dtheta from (theta, Hs, dHs) against fp64 autograd of the oracle's solve (the reference's own fp32
+    inverse is the less accurate side here; its distance from fp64 is printed next to ours)."""
+    import mesh_warp_ref as ref
+    g = load_golden(name)
+    th64 = torch.tensor(g['theta'], dtype=torch.float64, requires_grad=True)
+    H64 = ref.solve_h(th64)
+    up = torch.tensor(g['ref_dHs'], dtype=torch.float64)
+    up[..., 8] = 0
+    (H64 * up).sum().backward()
+    got = mgw.ops.solve_h_bwd(dev(g['theta']), dev(g['ref_Hs']), dev(g['ref_dHs'])).cpu().numpy()
+    e = relmax(got, th64.grad.numpy())
+    assert e < 2e-5, 'dtheta (K4) rel err vs fp64 %.3g' % e
+
+
+@pytest.mark.parametrize('impl', IMPLS)
+@pytest.mark.parametrize('name', BWD_CASES)
+def test_transformer_backward_end_to_end(mgw, name, impl):
+    """autograd through transformer(): <= 1e-4 relative on smooth images.  On white-noise images the gradient is a
+    discontinuous function of Hs (a 1e-6 change of H moves taps across pixel boundaries): the reference's own fp32
+    result is then ~1e-2 away from its fp64 run, so the bar there is 'no worse than 4x the reference's own error'."""
     mgw.set_impl(impl)
     g = load_golden(name)
     U, d_out, d_img = golden_inputs(name, g)
@@ -99,18 +141,46 @@ def test_transformer_backward(mgw, name, impl):
     th = dev(g['theta']).requires_grad_(True)
     out, black, img = mgw.transformer(Ut, th)
     ((out * dev(d_out)).sum() + (img * dev(d_img)).sum()).backward()
-    ok, e = grad_ok(th.grad.cpu().numpy(), g['ref_dtheta'], g.get('f64_dtheta'))
-    assert ok, 'dtheta rel err %.3g' % e
-    if 'ref_dU' in g:
-        ok, e = grad_ok(Ut.grad.cpu().numpy(), g['ref_dU'], g.get('f64_dU'))
-        assert ok, 'dU rel err %.3g' % e
-    # stage-wise: dHs given the reference's Hs
-    dU, dHs = mgw.ops.warp_bwd(dev(U), dev(g['ref_Hs']), dev(d_out), dev(d_img))
-    ok, e = grad_ok(dHs.cpu().numpy()[..., :8], g['ref_dHs'][..., :8], g['f64_dHs'][..., :8] if 'f64_dHs' in g else None)
-    assert ok, 'dHs rel err %.3g' % e
-    if 'ref_dU' in g:
-        ok, e = grad_ok(dU.cpu().numpy(), g['ref_dU'], g.get('f64_dU'))
-        assert ok, 'dU(stage) rel err %.3g' % e
+    got = th.grad.cpu().numpy()
+    e64, r64 = relmax(got, g['f64_dtheta']), relmax(g['ref_dtheta'], g['f64_dtheta'])
+    smooth = str(g['kind']) == 'smooth'
+    assert e64 <= (max(1e-4, 2 * r64) if smooth else max(1e-4, 4 * r64)), 'dtheta: ours %.3g, reference %.3g (vs fp64)' % (e64, r64)
+    if 'f64_dU' in g:
+        eu, ru = relmax(Ut.grad.cpu().numpy(), g['f64_dU']), relmax(g['ref_dU'], g['f64_dU'])
+        assert eu <= max(1e-4, 4 * ru), 'dU: ours %.3g, reference %.3g (vs fp64)' % (eu, ru)
+
+
+@pytest.mark.parametrize('name', TMA_MESH_CASES + FULL_MESH_CASES)
+def test_tma_path_is_taken_and_matches_generic(mgw, name):
+    """set_impl('tma') errors out instead of falling back; TMA forward == generic forward bit for bit."""
+    g = load_golden(name)
+    U, d_out, d_img = golden_inputs(name, g)
+    Ud, Hd = dev(U), dev(g['ref_Hs'])
+    mgw.set_impl('generic')
+    o_g, b_g, i_g, _ = mgw.ops.warp_fwd(Ud, Hd)
+    dU_g, dH_g = mgw.ops.warp_bwd(Ud, Hd, dev(d_out), dev(d_img))
+    mgw.set_impl('tma')
+    o_t, b_t, i_t, _ = mgw.ops.warp_fwd(Ud, Hd)
+    dU_t, dH_t = mgw.ops.warp_bwd(Ud, Hd, dev(d_out), dev(d_img))
+    only_img = mgw.ops.warp_fwd(Ud, Hd, want_out=False, want_black=False)[2]
+    assert torch.equal(o_g.view(torch.int32), o_t.view(torch.int32)) and torch.equal(b_g, b_t)
+    assert torch.equal(i_g.view(torch.int32), i_t.view(torch.int32)) and torch.equal(only_img.view(torch.int32), i_t.view(torch.int32))
+    fin = torch.isfinite(dU_g) & torch.isfinite(dU_t)
+    assert relmax(dU_t[fin].cpu().numpy(), dU_g[fin].cpu().numpy()) < 1e-5
+    if 'fold' not in name:
+        assert relmax(dH_t.cpu().numpy(), dH_g.cpu().numpy()) < 1e-5
+    dU_n, dH_n = mgw.ops.warp_bwd(Ud, Hd, dev(d_out), None, want_dU=False)      # the no-dU / no-d_img variant of the kernel
+    assert dU_n is None and torch.isfinite(dH_n).all() or 'fold' in name
+    mgw.set_impl('auto')
+
+
+def test_tma_rejects_shapes_it_cannot_serve(mgw):
+    g = load_golden('mesh_ragged_c1')            # 50 x 70: row pitch not a multiple of 16 bytes
+    U, _, _ = golden_inputs('mesh_ragged_c1', g)
+    mgw.set_impl('tma')
+    with pytest.raises(mgw.MgwError):
+        mgw.ops.warp_fwd(dev(U), dev(g['ref_Hs']))
+    mgw.set_impl('auto')
 
 
 def test_backward_without_dU_and_without_dimg(mgw):

@@ -135,7 +135,7 @@ def test_golden_is_reference_output():
     import make_golden
     import synth
     name, fx = make_golden.mesh_case('mesh_smooth_s03', synth.smooth_image(2, 48, 64, 3, 10),
-                                     synth.random_mesh(2, 4, 4, 0.03, 11), 4, 4, 10, f64=False)
+                                     synth.random_mesh(2, 4, 4, 0.03, 11), 4, 4, 10, f64=None)
     g = load_golden(name)
     for k in ('ref_Hs', 'ref_out', 'ref_img', 'ref_dtheta', 'ref_dU'):
         assert bits_equal(fx[k], g[k]).all(), k
