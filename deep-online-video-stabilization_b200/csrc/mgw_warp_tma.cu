@@ -31,6 +31,7 @@ struct TileCfg {
     int SBH, SBW;                   // staged source box (pixels)
     int nty, ntx;                   // tiles per image
     int parts_y, parts_x;           // max tiles per cell (backward partial layout)
+    int xalign;                     // box / tile start columns must be multiples of this (16-byte TMA start address)
 };
 
 struct TilePos {
@@ -94,6 +95,9 @@ __device__ __forceinline__ void source_box(const float (&Hc)[9], const TileCfg& 
     const int needw = ix1 - ix0 + 1, needh = iy1 - iy0 + 1;
     bx0 = needw <= c.SBW ? ix0 : ix0 + (needw - c.SBW) / 2;
     by0 = needh <= c.SBH ? iy0 : iy0 + (needh - c.SBH) / 2;
+    // TMA needs the box to start on a 16-byte boundary of global memory (measured on B200: a start that is not a
+    // multiple of 4 floats raises "illegal instruction"): round the first column down to a multiple of xalign pixels
+    bx0 -= bx0 % c.xalign;
 }
 
 __host__ __device__ constexpr int up32(int v) { return (v + 31) / 32 * 32; }     // 128-byte chunks of floats
@@ -383,11 +387,15 @@ static bool plan(const WarpShape& s, TileCfg* out)
     TileCfg c;
     c.N = s.N; c.H = s.H; c.W = s.W; c.gh = s.gh; c.gw = s.gw;
     c.cell_h = s.H / s.gh; c.cell_w = s.W / s.gw;
+    // tiles start at cell boundaries (or cell end - TW) and every TMA start address must be 16-byte aligned for
+    // out (C floats/px), black (1) and x/y maps (2): columns of cell boundaries must be multiples of 4
+    if (s.W % 4 != 0 || c.cell_w % 4 != 0) return false;
+    c.xalign = (s.C % 4 == 0) ? 1 : ((s.C % 2 == 0) ? 2 : 4);
     const int max_inner = 256;                                                               // TMA box dim limit
     c.TW = 0;
     for (int tw : {64, 32}) {
         if (tw > c.cell_w) continue;
-        int sbw = ((tw * 13 + 9) / 10 + 4 + 3) / 4 * 4;
+        int sbw = ((tw * 13 + 9) / 10 + 4 + (c.xalign - 1) + 3) / 4 * 4;
         const int cap = (max_inner / s.C) / 4 * 4;
         if (sbw > cap) sbw = cap;
         if (sbw < tw + 4) continue;

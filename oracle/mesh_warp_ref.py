@@ -29,7 +29,8 @@ def get_4_pts(head, gh, gw, do_crop_rate=0.8):
     """s_net_bundle_nobm.py:29-71: head [N,2*(gh+1)*(gw+1)] -> (pts1 [N,gh,gw,8], pts2 [N,gh+1,gw+1,2])."""
     n, dt = head.shape[0], head.dtype
     h, w = 2.0 / gh, 2.0 / gw
-    base = torch.tensor([[[j * w - 1, i * h - 1] for j in range(gw + 1)] for i in range(gh + 1)], dtype=dt)   # :44-46
+    base = torch.tensor([[[j * w - 1, i * h - 1] for j in range(gw + 1)] for i in range(gh + 1)],
+                        dtype=torch.float32).to(dt)                                                             # :44-46 (fp32 constants)
     lim = (torch.ones((), dtype=dt) / torch.tensor(do_crop_rate, dtype=dt))                                    # :37
     p = base[None] + head.reshape(n, gh + 1, gw + 1, 2)                                                        # :47,:55
     pts2 = torch.minimum(torch.maximum(p, -1 * lim), lim)                                                      # :58
@@ -44,7 +45,7 @@ def solve_h(theta):
     gh, gw, dt = gh1 - 1, gw1 - 1, theta.dtype
     h, w = 2.0 / gh, 2.0 / gw
     ori = torch.tensor([[[j * w - 1, i * h - 1, j * w - 1 + w, i * h - 1, j * w - 1, i * h - 1 + h, j * w - 1 + w, i * h - 1 + h]
-                         for j in range(gw)] for i in range(gh)], dtype=dt)                                    # :182-189
+                         for j in range(gw)] for i in range(gh)], dtype=torch.float32).to(dt)                  # :182-189 (fp32 constants)
     x, y = ori[..., 0::2].expand(n, gh, gw, 4), ori[..., 1::2].expand(n, gh, gw, 4)                            # :154-155
     tar = torch.stack([theta[:, :-1, :-1], theta[:, :-1, 1:], theta[:, 1:, :-1], theta[:, 1:, 1:]], dim=3)    # :191-193
     u, v = tar[..., 0], tar[..., 1]                                                                            # :156-157

@@ -133,8 +133,12 @@ def ones_like(t):
 
 
 def constant(value, shape=None, dtype=None):   # noqa: A002
-    t = torch.tensor(np.asarray(value, dtype=np.float64 if _dt(dtype).is_floating_point else None),
-                     dtype=_dt(dtype))
+    if _dt(dtype).is_floating_point:
+        # a tf.float32 constant is an fp32 INPUT of the graph: in the fp64 arbiter run it keeps its fp32-rounded value
+        arr = np.asarray(value, dtype=np.float32 if dtype in (torch.float32, 'float32') else np.float64).astype(np.float64)
+    else:
+        arr = np.asarray(value)
+    t = torch.tensor(arr, dtype=_dt(dtype))
     if shape is not None:
         t = t.reshape(_ints(shape))
     return t
