@@ -46,7 +46,7 @@ interp_bwd_kernel(const float* __restrict__ im, const float* __restrict__ x, con
     const size_t ia = ((size_t)t.y0 * IW + t.x0) * C, ib = ((size_t)t.y1 * IW + t.x0) * C;
     const size_t ic = ((size_t)t.y0 * IW + t.x1) * C, id = ((size_t)t.y1 * IW + t.x1) * C;
     const float* imn = im + (size_t)n * IH * IW * C;
-    float* dn = d_im ? d_im + (size_t)n * IH * IW * C : nullptr;
+    float* dn = (d_im && taps_scatter(t)) ? d_im + (size_t)n * IH * IW * C : nullptr;
     const float wa = t.ax * t.ay, wb = t.ax * t.by, wc = t.bx * t.ay, wd = t.bx * t.by;
     float gx = 0.0f, gy = 0.0f;
 #pragma unroll

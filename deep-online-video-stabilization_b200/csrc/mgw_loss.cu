@@ -146,6 +146,7 @@ temp_loss_kernel(const float* __restrict__ out1, const float* __restrict__ black
             } else {
                 const float g1 = k * e * m;
                 d_out1[p * C + ch] = g1;
+                if (!taps_scatter(t)) continue;
                 float* d2 = d_out2 + (size_t)n * HW * C;
                 atomicAdd(d2 + ia * C + ch, -g1 * wa);
                 atomicAdd(d2 + ib * C + ch, -g1 * wb);

@@ -90,7 +90,7 @@ warp_bwd_generic_kernel(const float* __restrict__ U, const float* __restrict__ H
         const size_t ia = ((size_t)t.y0 * s.W + t.x0) * C, ib = ((size_t)t.y1 * s.W + t.x0) * C;
         const size_t ic = ((size_t)t.y0 * s.W + t.x1) * C, id = ((size_t)t.y1 * s.W + t.x1) * C;
         const float* Un = U + (size_t)px.n * s.H * s.W * C;
-        float* dUn = dU ? dU + (size_t)px.n * s.H * s.W * C : nullptr;
+        float* dUn = (dU && taps_scatter(t)) ? dU + (size_t)px.n * s.H * s.W * C : nullptr;
         const float wa = t.ax * t.ay, wb = t.ax * t.by, wc = t.bx * t.ay, wd = t.bx * t.by;
         float gx = 0.0f, gy = 0.0f;
 #pragma unroll

@@ -342,18 +342,19 @@ warp_bwd_tma_kernel(const __grid_constant__ CUtensorMap mapU, const __grid_const
             const int o = lr * TW + tx;
             const float wa = t.ax * t.ay, wb = t.ax * t.by, wc = t.bx * t.ay, wd = t.bx * t.by;
             float gx = 0.0f, gy = 0.0f;
+            const bool scatter = (dU != nullptr) && taps_scatter(t);
             if (inbox) {
                 const int ia = (sy0 * G::SBW + sx0) * C, ib = (sy1 * G::SBW + sx0) * C;
                 const int ic = (sy0 * G::SBW + sx1) * C, id = (sy1 * G::SBW + sx1) * C;
-                // weights from clipped integers leave [-1,1] only for out-of-range samples: those go the fp32 way
-                const bool q_ok = fixed && (fabsf(t.ax) <= 1.0f) && (fabsf(t.bx) <= 1.0f) && (fabsf(t.ay) <= 1.0f) && (fabsf(t.by) <= 1.0f);
+                // unclipped taps have weights in [0,1] (taps_scatter() drops every clipped pixel), so |w*g| <= max|d_out|
+                const bool q_ok = fixed != 0;
 #pragma unroll
                 for (int ch = 0; ch < C; ++ch) {
                     const float gch = s_dout[o * C + ch];
                     const float Ia = s_src[ia + ch], Ib = s_src[ib + ch], Ic = s_src[ic + ch], Id = s_src[id + ch];
                     gx = fmaf(gch, fmaf(Ic - Ia, t.ay, (Id - Ib) * t.by), gx);
                     gy = fmaf(gch, fmaf(Ib - Ia, t.ax, (Id - Ic) * t.bx), gy);
-                    if (dU) {
+                    if (scatter) {
                         if (q_ok) {
                             const float gs = gch * scale;
                             atomicAdd(s_acc + ia + ch, __float2int_rn(wa * gs));
@@ -377,7 +378,7 @@ warp_bwd_tma_kernel(const __grid_constant__ CUtensorMap mapU, const __grid_const
                     const float Ia = __ldg(Un + ia + ch), Ib = __ldg(Un + ib + ch), Ic = __ldg(Un + ic + ch), Id = __ldg(Un + id + ch);
                     gx = fmaf(gch, fmaf(Ic - Ia, t.ay, (Id - Ib) * t.by), gx);
                     gy = fmaf(gch, fmaf(Ib - Ia, t.ax, (Id - Ic) * t.bx), gy);
-                    if (dU) {
+                    if (scatter) {
                         atomicAdd(dUn + ia + ch, wa * gch);
                         atomicAdd(dUn + ib + ch, wb * gch);
                         atomicAdd(dUn + ic + ch, wc * gch);
@@ -390,7 +391,7 @@ warp_bwd_tma_kernel(const __grid_constant__ CUtensorMap mapU, const __grid_const
                 const float2 di = reinterpret_cast<const float2*>(s_dimg)[o];
                 gxn += di.x; gyn += di.y;
             }
-            const float rz = 1.0f / zs;
+            const float rz = __frcp_rn(zs);
             const float dxs = gxn * rz, dys = gyn * rz;
             const float dzs = -(gxn * xn + gyn * yn) * rz;
             dh[0] = fmaf(dxs, xt, dh[0]); dh[1] = fmaf(dxs, yt, dh[1]); dh[2] += dxs;

@@ -165,8 +165,8 @@ def test_tma_path_is_taken_and_matches_generic(mgw, name):
     only_img = mgw.ops.warp_fwd(Ud, Hd, want_out=False, want_black=False)[2]
     assert torch.equal(o_g.view(torch.int32), o_t.view(torch.int32)) and torch.equal(b_g, b_t)
     assert torch.equal(i_g.view(torch.int32), i_t.view(torch.int32)) and torch.equal(only_img.view(torch.int32), i_t.view(torch.int32))
-    s0 = 1 if 'fold' in name else 0      # a folded cell scatters 1e5-weighted, cancelling terms: order-dependent garbage in any implementation
-    assert relmax(dU_t[s0:].cpu().numpy(), dU_g[s0:].cpu().numpy()) < 1e-5
+    s0 = 1 if 'fold' in name else 0      # a folded cell scatters 1e5-weighted terms: order-dependent garbage in any implementation
+    assert relmax(dU_t[s0:].cpu().numpy(), dU_g[s0:].cpu().numpy()) < 2e-5      # fixed-point (tile) vs fp32 atomics (generic)
     if 'fold' not in name:
         assert relmax(dH_t.cpu().numpy(), dH_g.cpu().numpy()) < 1e-5
     dU_n, dH_n = mgw.ops.warp_bwd(Ud, Hd, dev(d_out), None, want_dU=False)      # the no-dU / no-d_img variant of the kernel
