@@ -29,12 +29,21 @@ namespace mgw {
 
 constexpr int kThreads = 256;
 
+constexpr int kMaxTilesPerAxis = 128;
+
+// One tile row (or column) of the image: which cell it lies in, where it starts, and from where it OWNS pixels
+// (edge tiles are shifted inward so that every tile is full; the overlap is owned by the earlier tile).
+struct AxisTab {
+    unsigned short start[kMaxTilesPerAxis];
+    unsigned short vstart[kMaxTilesPerAxis];
+    unsigned char cell[kMaxTilesPerAxis];
+    unsigned char part[kMaxTilesPerAxis];
+};
+
 struct TileCfg {
     int N, H, W, gh, gw;
-    int cell_h, cell_w;             // floor(H/gh), floor(W/gw): spatial_transformer3.py:227-228
-    int nty, ntx;                   // tiles per image
     int parts_y, parts_x;           // max tiles per cell (backward partial layout)
-    int xalign;                     // box start columns must be multiples of this (16-byte TMA start address)
+    AxisTab rows, cols;             // grid = (cols, rows, N): blockIdx is the tile, no index arithmetic on the device
 };
 
 template <int C, int TW, int K>
@@ -48,63 +57,43 @@ struct Geo {
     static constexpr int SBH = (TH * 13 + 9) / 10 + 4;
     static constexpr int kBoxF = (SBH * SBW * C + 31) / 32 * 32;                     // floats, 128-byte chunks
     static constexpr int kOutF = (TH * TW * C + 31) / 32 * 32;
-    static constexpr int kImgF = (TH * TW * 2 + 31) / 32 * 32;
-    static constexpr int kBlkF = (TH * TW + 31) / 32 * 32;
     static_assert(SBW >= TW + 4, "source box too narrow for this tile width / channel count");
 };
 
-// what warp 0 works out once per tile and every thread then reads from shared memory
+// what warp 0 works out per tile for everyone else
 struct TileInfo {
-    float H[9];
-    int n, r0, c0, vr0, vc0, part, cell;
-    int bx0, by0;
-    int fixed;                      // backward: 1 = fixed-point shared accumulation is usable for this tile
-    float scale, inv_scale;
+    int bx0, by0;                   // first column / row of the staged source box
+    int area_ok;                    // backward: the tile is not magnified beyond what the fixed-point headroom covers
+    float wmax[kThreads / 32];      // backward: per-warp max|d_out|
 };
 
-__device__ __forceinline__ void decode_axis(int t, int ncell, int cell_px, int total, int T, int& cell, int& start, int& vstart, int& part)
+struct Tile {
+    int n, r0, c0, vr0, vc0, cell, part;
+};
+
+__device__ __forceinline__ Tile this_tile(const TileCfg& cfg)
 {
-    cell = 0; start = 0; vstart = 0; part = 0;
-    for (int c = 0; c < ncell; ++c) {
-        const int s = c * cell_px;
-        const int len = (c == ncell - 1) ? total - s : cell_px;         // the last cell absorbs the remainder (:240-243)
-        const int nt = (len + T - 1) / T;
-        if (t < nt) {
-            cell = c;
-            vstart = s + t * T;                 // first row/col this tile OWNS
-            start = min(vstart, s + len - T);   // edge tiles are shifted inward and overlap their neighbour
-            part = t;
-            return;
-        }
-        t -= nt;
-    }
+    Tile t;
+    const int ty = blockIdx.y, tx = blockIdx.x;
+    t.n = blockIdx.z;
+    t.r0 = cfg.rows.start[ty]; t.vr0 = cfg.rows.vstart[ty];
+    t.c0 = cfg.cols.start[tx]; t.vc0 = cfg.cols.vstart[tx];
+    t.cell = (t.n * cfg.gh + cfg.rows.cell[ty]) * cfg.gw + cfg.cols.cell[tx];
+    t.part = cfg.rows.part[ty] * cfg.parts_x + cfg.cols.part[tx];
+    return t;
 }
 
-// Tile decode + source box, by warp 0 (lanes 0-3 project one corner each).  The box is the bbox of the 4 projected
-// corners (+1 px for rounding, +1 for the x1/y1 taps), clipped to the image like the taps are.  A projective map with
-// no pole inside the tile (z of one sign at the corners) sends the rectangle into the convex hull of its corner
-// images, so the box holds every tap; otherwise any box will do (per-tap fallback).
+// Source box of the tile, by warp 0 (lanes 0-3 project one corner each): bbox of the 4 projected corners (+1 px for
+// rounding, +1 for the x1/y1 taps), clipped to the image like the taps are.  A projective map with no pole inside the
+// tile (z of one sign at the corners) sends the rectangle into the convex hull of its corner images, so the box holds
+// every tap; otherwise any box will do (per-tap fallback).
 template <int C, int TW, int K>
-__device__ __forceinline__ void setup_tile(const TileCfg& cfg, const float* __restrict__ Hs, TileInfo* ti, float* area_out)
+__device__ __forceinline__ void source_box(const TileCfg& cfg, const Tile& tl, const float (&Hc)[9], float stepx, float stepy,
+                                           int& bx0, int& by0, int& area_ok)
 {
     using G = Geo<C, TW, K>;
-    const int lane = threadIdx.x;
-    int n, ci, cj, r0, c0, vr0, vc0, py, px;
-    {
-        const int per = cfg.nty * cfg.ntx;
-        const int b = blockIdx.x;
-        n = b / per;
-        const int rem = b - n * per;
-        decode_axis(rem / cfg.ntx, cfg.gh, cfg.cell_h, cfg.H, G::TH, ci, r0, vr0, py);
-        decode_axis(rem % cfg.ntx, cfg.gw, cfg.cell_w, cfg.W, TW, cj, c0, vc0, px);
-    }
-    const int cell = (n * cfg.gh + ci) * cfg.gw + cj;
-    float Hc[9];
-#pragma unroll
-    for (int k = 0; k < 9; ++k) Hc[k] = __ldg(Hs + (size_t)cell * 9 + k);
-    const float stepx = lin_step(cfg.W), stepy = lin_step(cfg.H);
-    const int k4 = lane & 3;
-    const int rr = r0 + ((k4 & 2) ? G::TH - 1 : 0), cc = c0 + ((k4 & 1) ? TW - 1 : 0);
+    const int k4 = threadIdx.x & 3;
+    const int rr = tl.r0 + ((k4 & 2) ? G::TH - 1 : 0), cc = tl.c0 + ((k4 & 1) ? TW - 1 : 0);
     const Proj q = project(Hc, lin_at(cc, stepx), lin_at(rr, stepy));
     const float x = (q.xn + 1.0f) * (float)cfg.W * 0.5f, y = (q.yn + 1.0f) * (float)cfg.H * 0.5f;
     bool ok = (fabsf(x) < 1.0e8f) && (fabsf(y) < 1.0e8f);
@@ -120,8 +109,7 @@ __device__ __forceinline__ void setup_tile(const TileCfg& cfg, const float* __re
         ok = ok && (__shfl_xor_sync(0xffffffffu, (int)ok, o) != 0);
     }
     ok = ok && (sgn == 4 || sgn == -4);
-    int bx0 = 0, by0 = 0;
-    float area = 0.0f;
+    bx0 = 0; by0 = 0; area_ok = 0;
     if (ok) {
         const int ix0 = clipi((int)floorf(xmin) - 1, 0, cfg.W - 1), ix1 = clipi((int)floorf(xmax) + 2, 0, cfg.W - 1);
         const int iy0 = clipi((int)floorf(ymin) - 1, 0, cfg.H - 1), iy1 = clipi((int)floorf(ymax) + 2, 0, cfg.H - 1);
@@ -131,105 +119,95 @@ __device__ __forceinline__ void setup_tile(const TileCfg& cfg, const float* __re
         // TMA needs the box to start on a 16-byte boundary of global memory (measured on B200: a start that is not
         // a multiple of 4 floats raises "illegal instruction"): round the first column down
         bx0 -= bx0 % G::kXalign;
-        area = (xmax - xmin + 1.0f) * (ymax - ymin + 1.0f);
+        // magnification guard for the fixed-point accumulator: bbox area >= 1/16 of the tile area
+        area_ok = ((xmax - xmin + 1.0f) * (ymax - ymin + 1.0f) * 16.0f >= (float)(G::TH * TW)) ? 1 : 0;
     }
-    if (lane == 0) {
-#pragma unroll
-        for (int k = 0; k < 9; ++k) ti->H[k] = Hc[k];
-        ti->n = n; ti->r0 = r0; ti->c0 = c0; ti->vr0 = vr0; ti->vc0 = vc0;
-        ti->part = py * cfg.parts_x + px; ti->cell = cell;
-        ti->bx0 = bx0; ti->by0 = by0;
-    }
-    *area_out = area;
 }
 
 // ------------------------------------------------------------------------------------------------ forward
 template <int C, int TW, int K>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, 4)
 warp_fwd_tma_kernel(const __grid_constant__ CUtensorMap mapU, const __grid_constant__ CUtensorMap mapOut,
-                    const __grid_constant__ CUtensorMap mapImg, const __grid_constant__ CUtensorMap mapBlack,
-                    const float* __restrict__ U, const float* __restrict__ Hs, const TileCfg cfg, const int want_out,
-                    const int want_img, const int want_black)
+                    const float* __restrict__ U, const float* __restrict__ Hs, const __grid_constant__ TileCfg cfg,
+                    float* __restrict__ out, float* __restrict__ img, float* __restrict__ black)
 {
     using G = Geo<C, TW, K>;
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     float* s_src = reinterpret_cast<float*>(smem_raw);
     float* s_out = s_src + G::kBoxF;
-    float* s_img = s_out + G::kOutF;
-    float* s_blk = s_img + G::kImgF;
-    uint64_t* bar = reinterpret_cast<uint64_t*>(s_blk + G::kBlkF);
+    uint64_t* bar = reinterpret_cast<uint64_t*>(s_out + G::kOutF);
     TileInfo* ti = reinterpret_cast<TileInfo*>(bar + 2);
 
     const int tid = threadIdx.x;
-    if (tid < 32) {
-        float area;
-        setup_tile<C, TW, K>(cfg, Hs, ti, &area);
-        if (tid == 0) {
-            tma::mbar_init(bar, 1);
-            tma::fence_barrier_init();
-            if (want_out) {
-                tma::mbar_expect_tx(bar, (uint32_t)(G::SBH * G::SBW * C * sizeof(float)));
-                tma::load_3d(s_src, &mapU, bar, ti->bx0 * C, ti->by0, ti->n);
-            }
-        }
+    if (tid == 0) {
+        tma::mbar_init(bar, 1);
+        tma::fence_barrier_init();
     }
-    __syncthreads();
+    const Tile tl = this_tile(cfg);
     float Hc[9];
 #pragma unroll
-    for (int k = 0; k < 9; ++k) Hc[k] = ti->H[k];
-    const int n = ti->n, r0 = ti->r0, c0 = ti->c0, bx0 = ti->bx0, by0 = ti->by0;
+    for (int k = 0; k < 9; ++k) Hc[k] = __ldg(Hs + (size_t)tl.cell * 9 + k);
+    const float stepx = lin_step(cfg.W), stepy = lin_step(cfg.H);
+    __syncthreads();                                  // barrier initialised; nobody has waited on anything long yet
+    if (tid < 32 && out) {
+        int bx0, by0, area_ok;
+        source_box<C, TW, K>(cfg, tl, Hc, stepx, stepy, bx0, by0, area_ok);
+        if (tid == 0) {
+            ti->bx0 = bx0; ti->by0 = by0;
+            tma::mbar_expect_tx(bar, (uint32_t)(G::SBH * G::SBW * C * sizeof(float)));     // release: publishes ti
+            tma::load_3d(s_src, &mapU, bar, bx0 * C, by0, tl.n);
+        }
+    }
 
     const int tx = tid % TW, g = tid / TW;
-    const float stepx = lin_step(cfg.W), stepy = lin_step(cfg.H);
-    const float xt = lin_at(c0 + tx, stepx);
+    const float xt = lin_at(tl.c0 + tx, stepx);
     const float hx0 = __fmul_rn(Hc[0], xt), hx3 = __fmul_rn(Hc[3], xt), hx6 = __fmul_rn(Hc[6], xt);   // first term of hrow()
     float xn[K], yn[K];
 #pragma unroll
     for (int k = 0; k < K; ++k) {
-        const int lr = g * K + k;
-        const float yt = lin_at(r0 + lr, stepy);
+        const int row = tl.r0 + g * K + k;
+        const float yt = lin_at(row, stepy);
         const float xs = __fadd_rn(__fmaf_rn(Hc[1], yt, hx0), Hc[2]);
         const float ys = __fadd_rn(__fmaf_rn(Hc[4], yt, hx3), Hc[5]);
         float zs = __fadd_rn(__fmaf_rn(Hc[7], yt, hx6), Hc[8]);
         zs = __fadd_rn(zs, (zs >= 0.0f) ? 1e-8f : -1e-8f);
         xn[k] = __fdiv_rn(xs, zs);
         yn[k] = __fdiv_rn(ys, zs);
-        const int o = lr * TW + tx;
-        reinterpret_cast<float2*>(s_img)[o] = make_float2(xn[k], yn[k]);
-        s_blk[o] = black_of(xn[k], yn[k]);
+        // x_map,y_map and black_pix are 8 / 4 contiguous bytes per lane: plain coalesced stores, no staging
+        const size_t p = ((size_t)tl.n * cfg.H + row) * cfg.W + tl.c0 + tx;
+        if (img) reinterpret_cast<float2*>(img)[p] = make_float2(xn[k], yn[k]);
+        if (black) black[p] = black_of(xn[k], yn[k]);
     }
-    if (want_out) {
-        tma::mbar_wait(bar, 0);
-        const float* Un = U + (size_t)n * cfg.H * cfg.W * C;
+    if (!out) return;
+    tma::mbar_wait(bar, 0);                           // acquire: the source box has landed and ti is visible
+    const int bx0 = ti->bx0, by0 = ti->by0;
+    const float* Un = U + (size_t)tl.n * cfg.H * cfg.W * C;
 #pragma unroll
-        for (int k = 0; k < K; ++k) {
-            const int lr = g * K + k;
-            const Taps t = make_taps(xn[k], yn[k], cfg.H, cfg.W);
-            const int sx0 = t.x0 - bx0, sx1 = t.x1 - bx0, sy0 = t.y0 - by0, sy1 = t.y1 - by0;
-            float* o = s_out + (lr * TW + tx) * C;
-            if (sx0 >= 0 && sx1 < G::SBW && sy0 >= 0 && sy1 < G::SBH) {
-                const float* pa = s_src + (sy0 * G::SBW + sx0) * C;
-                const float* pb = s_src + (sy1 * G::SBW + sx0) * C;
-                const float* pc = s_src + (sy0 * G::SBW + sx1) * C;
-                const float* pd = s_src + (sy1 * G::SBW + sx1) * C;
+    for (int k = 0; k < K; ++k) {
+        const int lr = g * K + k;
+        const Taps t = make_taps(xn[k], yn[k], cfg.H, cfg.W);
+        const int sx0 = t.x0 - bx0, sx1 = t.x1 - bx0, sy0 = t.y0 - by0, sy1 = t.y1 - by0;
+        float* o = s_out + (lr * TW + tx) * C;
+        if (sx0 >= 0 && sx1 < G::SBW && sy0 >= 0 && sy1 < G::SBH) {
+            const float* pa = s_src + (sy0 * G::SBW + sx0) * C;
+            const float* pb = s_src + (sy1 * G::SBW + sx0) * C;
+            const float* pc = s_src + (sy0 * G::SBW + sx1) * C;
+            const float* pd = s_src + (sy1 * G::SBW + sx1) * C;
 #pragma unroll
-                for (int ch = 0; ch < C; ++ch) o[ch] = blend(t, pa[ch], pb[ch], pc[ch], pd[ch]);
-            } else {
-                const float* pa = Un + ((size_t)t.y0 * cfg.W + t.x0) * C;
-                const float* pb = Un + ((size_t)t.y1 * cfg.W + t.x0) * C;
-                const float* pc = Un + ((size_t)t.y0 * cfg.W + t.x1) * C;
-                const float* pd = Un + ((size_t)t.y1 * cfg.W + t.x1) * C;
+            for (int ch = 0; ch < C; ++ch) o[ch] = blend(t, pa[ch], pb[ch], pc[ch], pd[ch]);
+        } else {
+            const float* pa = Un + ((size_t)t.y0 * cfg.W + t.x0) * C;
+            const float* pb = Un + ((size_t)t.y1 * cfg.W + t.x0) * C;
+            const float* pc = Un + ((size_t)t.y0 * cfg.W + t.x1) * C;
+            const float* pd = Un + ((size_t)t.y1 * cfg.W + t.x1) * C;
 #pragma unroll
-                for (int ch = 0; ch < C; ++ch) o[ch] = blend(t, __ldg(pa + ch), __ldg(pb + ch), __ldg(pc + ch), __ldg(pd + ch));
-            }
+            for (int ch = 0; ch < C; ++ch) o[ch] = blend(t, __ldg(pa + ch), __ldg(pb + ch), __ldg(pc + ch), __ldg(pd + ch));
         }
     }
     tma::fence_proxy_async();
     __syncthreads();
     if (tid == 0) {
-        if (want_out) tma::store_3d(&mapOut, s_out, c0 * C, r0, n);
-        if (want_img) tma::store_3d(&mapImg, s_img, c0 * 2, r0, n);
-        if (want_black) tma::store_3d(&mapBlack, s_blk, c0, r0, n);
+        tma::store_3d(&mapOut, s_out, tl.c0 * C, tl.r0, tl.n);
         tma::commit_group();
         tma::wait_group_read0();
     }
@@ -237,45 +215,62 @@ warp_fwd_tma_kernel(const __grid_constant__ CUtensorMap mapU, const __grid_const
 
 // ------------------------------------------------------------------------------------------------ backward
 template <int C, int TW, int K>
-__global__ void __launch_bounds__(kThreads)
-warp_bwd_tma_kernel(const __grid_constant__ CUtensorMap mapU, const __grid_constant__ CUtensorMap mapDout,
-                    const __grid_constant__ CUtensorMap mapDimg, const __grid_constant__ CUtensorMap mapDU,
-                    const float* __restrict__ U, const float* __restrict__ Hs, const TileCfg cfg, float* __restrict__ dU,
-                    const int has_dimg, float* __restrict__ parts)
+__global__ void __launch_bounds__(kThreads, 3)
+warp_bwd_tma_kernel(const __grid_constant__ CUtensorMap mapU, const __grid_constant__ CUtensorMap mapDU,
+                    const float* __restrict__ U, const float* __restrict__ Hs, const float* __restrict__ d_out,
+                    const float* __restrict__ d_img, const __grid_constant__ TileCfg cfg, float* __restrict__ dU,
+                    float* __restrict__ parts)
 {
     using G = Geo<C, TW, K>;
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     float* s_src = reinterpret_cast<float*>(smem_raw);
-    float* s_dout = s_src + G::kBoxF;
-    float* s_dimg = s_dout + G::kOutF;
-    float* s_red = s_dimg + G::kImgF;                                  // [8 warps][8] floats + [8] warp maxima
-    uint64_t* bar = reinterpret_cast<uint64_t*>(s_red + 96);
+    float* s_red = s_src + G::kBoxF;                                   // [8 warps][8] dH partials
+    uint64_t* bar = reinterpret_cast<uint64_t*>(s_red + 64);
     TileInfo* ti = reinterpret_cast<TileInfo*>(bar + 2);
     int* s_acc = reinterpret_cast<int*>(s_red + 128);                  // fixed-point dU box (only when dU != nullptr)
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    float area = 0.0f;
-    if (tid < 32) {
-        setup_tile<C, TW, K>(cfg, Hs, ti, &area);
-        if (tid == 0) {
-            tma::mbar_init(bar, 1);
-            tma::fence_barrier_init();
-            const uint32_t bytes = (uint32_t)((G::SBH * G::SBW * C + G::TH * TW * C + (has_dimg ? G::TH * TW * 2 : 0)) * sizeof(float));
-            tma::mbar_expect_tx(bar, bytes);
-            tma::load_3d(s_src, &mapU, bar, ti->bx0 * C, ti->by0, ti->n);
-            tma::load_3d(s_dout, &mapDout, bar, ti->c0 * C, ti->r0, ti->n);
-            if (has_dimg) tma::load_3d(s_dimg, &mapDimg, bar, ti->c0 * 2, ti->r0, ti->n);
+    if (tid == 0) {
+        tma::mbar_init(bar, 1);
+        tma::fence_barrier_init();
+    }
+    const Tile tl = this_tile(cfg);
+    float Hc[9];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) Hc[k] = __ldg(Hs + (size_t)tl.cell * 9 + k);
+    const float stepx = lin_step(cfg.W), stepy = lin_step(cfg.H);
+    const int tx = tid % TW, g = tid / TW;
+    const int col = tl.c0 + tx;
+
+    // this thread's K pixels of d_out / d_img: 12 / 8 contiguous bytes per lane, coalesced, all loads in flight at once
+    float gout[K][C], gimg[K][2];
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        const size_t p = ((size_t)tl.n * cfg.H + tl.r0 + g * K + k) * cfg.W + col;
+#pragma unroll
+        for (int ch = 0; ch < C; ++ch) gout[k][ch] = __ldg(d_out + p * C + ch);
+        if (d_img) {
+            const float2 di = __ldg(reinterpret_cast<const float2*>(d_img) + p);
+            gimg[k][0] = di.x; gimg[k][1] = di.y;
+        } else {
+            gimg[k][0] = 0.0f; gimg[k][1] = 0.0f;
         }
     }
     if (dU) {
         int4* a4 = reinterpret_cast<int4*>(s_acc);
         for (int i = tid; i < G::kBoxF / 4; i += kThreads) a4[i] = make_int4(0, 0, 0, 0);
     }
-    __syncthreads();                                                   // barrier init + TileInfo visible to everyone
-    const int tx = tid % TW, g = tid / TW;
-
-    // ---- per-tile fixed-point scale from max|d_out| (after the TMA data has landed)
-    tma::mbar_wait(bar, 0);
+    __syncthreads();                                  // barrier initialised
+    if (tid < 32) {
+        int bx0, by0, area_ok;
+        source_box<C, TW, K>(cfg, tl, Hc, stepx, stepy, bx0, by0, area_ok);
+        if (tid == 0) {
+            ti->bx0 = bx0; ti->by0 = by0; ti->area_ok = area_ok;
+            tma::mbar_expect_tx(bar, (uint32_t)(G::SBH * G::SBW * C * sizeof(float)));
+            tma::load_3d(s_src, &mapU, bar, bx0 * C, by0, tl.n);
+        }
+    }
+    // ---- per-tile fixed-point scale from max|d_out| (Inf/NaN anywhere in the tile disables the fixed-point path)
     if (dU) {
         float m = 0.0f;
         bool bad = false;
@@ -283,53 +278,45 @@ warp_bwd_tma_kernel(const __grid_constant__ CUtensorMap mapU, const __grid_const
         for (int k = 0; k < K; ++k)
 #pragma unroll
             for (int ch = 0; ch < C; ++ch) {
-                const float v = fabsf(s_dout[((g * K + k) * TW + tx) * C + ch]);
+                const float v = fabsf(gout[k][ch]);
                 m = fmaxf(m, v);
                 bad = bad || !(v <= 3.0e38f);
             }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
         bad = __any_sync(0xffffffffu, bad);
-        if (lane == 0) s_red[64 + warp] = bad ? __int_as_float(0x7f800000) : m;
-        __syncthreads();
-        if (tid == 0) {
-            float mm = 0.0f;
+        if (lane == 0) ti->wmax[warp] = bad ? __int_as_float(0x7f800000) : m;
+    }
+    __syncthreads();                                  // wmax, box and the zeroed accumulator are visible
+    const int bx0 = ti->bx0, by0 = ti->by0;
+    int fixed = 0;
+    float scale = 0.0f, inv_scale = 0.0f;
+    if (dU) {
+        float mm = 0.0f;
 #pragma unroll
-            for (int w = 0; w < kThreads / 32; ++w) mm = fmaxf(mm, s_red[64 + w]);
-            const int e = ((__float_as_int(mm) >> 23) & 0xff) - 127;        // floor(log2 mm) for normal mm
-            // quantum = 2^-23 of the tile's max|d_out| (weights are <= 1 on this path), 8 bits of headroom: up to 256
-            // coincident full-size taps per word; tiles magnified more than 4x4 (area test) take the fp32 path instead
-            const bool usable = (mm > 0.0f) && (e > -100) && (e < 100) && (area * 16.0f >= (float)(G::TH * TW));
-            ti->fixed = usable ? 1 : 0;
-            ti->scale = usable ? __int_as_float((22 - e + 127) << 23) : 0.0f;
-            ti->inv_scale = usable ? __int_as_float((e - 22 + 127) << 23) : 0.0f;
-        }
-        __syncthreads();
+        for (int w = 0; w < kThreads / 32; ++w) mm = fmaxf(mm, ti->wmax[w]);
+        const int e = ((__float_as_int(mm) >> 23) & 0xff) - 127;            // floor(log2 mm) for normal mm
+        // quantum = 2^-23 of the tile's max|d_out| (tap weights are in [0,1] on this path), 8 bits of headroom = up to
+        // 256 coincident full-size taps per word; tiles magnified beyond ~4x4 (area test) take the fp32 path instead
+        fixed = (mm > 0.0f) && (e > -100) && (e < 100) && ti->area_ok;
+        scale = __int_as_float((22 - e + 127) << 23);
+        inv_scale = __int_as_float((e - 22 + 127) << 23);
     }
 
-    float Hc[9];
-#pragma unroll
-    for (int k = 0; k < 9; ++k) Hc[k] = ti->H[k];
-    const int n = ti->n, r0 = ti->r0, c0 = ti->c0, bx0 = ti->bx0, by0 = ti->by0, vr0 = ti->vr0, vc0 = ti->vc0;
-    const int fixed = dU ? ti->fixed : 0;
-    const float scale = ti->scale;
-
-    const int col = c0 + tx;
-    const float stepx = lin_step(cfg.W), stepy = lin_step(cfg.H);
     const float xt = lin_at(col, stepx);
     const float hx0 = __fmul_rn(Hc[0], xt), hx3 = __fmul_rn(Hc[3], xt), hx6 = __fmul_rn(Hc[6], xt);
-    const float* Un = U + (size_t)n * cfg.H * cfg.W * C;
-    float* dUn = dU ? dU + (size_t)n * cfg.H * cfg.W * C : nullptr;
+    const float* Un = U + (size_t)tl.n * cfg.H * cfg.W * C;
+    float* dUn = dU ? dU + (size_t)tl.n * cfg.H * cfg.W * C : nullptr;
     float dh[8];
 #pragma unroll
     for (int k = 0; k < 8; ++k) dh[k] = 0.0f;
     const float halfW = 0.5f * (float)cfg.W, halfH = 0.5f * (float)cfg.H;
 
+    tma::mbar_wait(bar, 0);
 #pragma unroll
     for (int k = 0; k < K; ++k) {
-        const int lr = g * K + k;
-        const int row = r0 + lr;
-        if (row >= vr0 && col >= vc0) {
+        const int row = tl.r0 + g * K + k;
+        if (row >= tl.vr0 && col >= tl.vc0) {
             const float yt = lin_at(row, stepy);
             const float xs = __fadd_rn(__fmaf_rn(Hc[1], yt, hx0), Hc[2]);
             const float ys = __fadd_rn(__fmaf_rn(Hc[4], yt, hx3), Hc[5]);
@@ -339,23 +326,20 @@ warp_bwd_tma_kernel(const __grid_constant__ CUtensorMap mapU, const __grid_const
             const Taps t = make_taps(xn, yn, cfg.H, cfg.W);
             const int sx0 = t.x0 - bx0, sx1 = t.x1 - bx0, sy0 = t.y0 - by0, sy1 = t.y1 - by0;
             const bool inbox = sx0 >= 0 && sx1 < G::SBW && sy0 >= 0 && sy1 < G::SBH;
-            const int o = lr * TW + tx;
             const float wa = t.ax * t.ay, wb = t.ax * t.by, wc = t.bx * t.ay, wd = t.bx * t.by;
             float gx = 0.0f, gy = 0.0f;
             const bool scatter = (dU != nullptr) && taps_scatter(t);
             if (inbox) {
                 const int ia = (sy0 * G::SBW + sx0) * C, ib = (sy1 * G::SBW + sx0) * C;
                 const int ic = (sy0 * G::SBW + sx1) * C, id = (sy1 * G::SBW + sx1) * C;
-                // unclipped taps have weights in [0,1] (taps_scatter() drops every clipped pixel), so |w*g| <= max|d_out|
-                const bool q_ok = fixed != 0;
 #pragma unroll
                 for (int ch = 0; ch < C; ++ch) {
-                    const float gch = s_dout[o * C + ch];
+                    const float gch = gout[k][ch];
                     const float Ia = s_src[ia + ch], Ib = s_src[ib + ch], Ic = s_src[ic + ch], Id = s_src[id + ch];
                     gx = fmaf(gch, fmaf(Ic - Ia, t.ay, (Id - Ib) * t.by), gx);
                     gy = fmaf(gch, fmaf(Ib - Ia, t.ax, (Id - Ic) * t.bx), gy);
                     if (scatter) {
-                        if (q_ok) {
+                        if (fixed) {           // unclipped taps have weights in [0,1], so |w*g| <= max|d_out|
                             const float gs = gch * scale;
                             atomicAdd(s_acc + ia + ch, __float2int_rn(wa * gs));
                             atomicAdd(s_acc + ib + ch, __float2int_rn(wb * gs));
@@ -374,7 +358,7 @@ warp_bwd_tma_kernel(const __grid_constant__ CUtensorMap mapU, const __grid_const
                 const size_t ic = ((size_t)t.y0 * cfg.W + t.x1) * C, id = ((size_t)t.y1 * cfg.W + t.x1) * C;
 #pragma unroll
                 for (int ch = 0; ch < C; ++ch) {
-                    const float gch = s_dout[o * C + ch];
+                    const float gch = gout[k][ch];
                     const float Ia = __ldg(Un + ia + ch), Ib = __ldg(Un + ib + ch), Ic = __ldg(Un + ic + ch), Id = __ldg(Un + id + ch);
                     gx = fmaf(gch, fmaf(Ic - Ia, t.ay, (Id - Ib) * t.by), gx);
                     gy = fmaf(gch, fmaf(Ib - Ia, t.ax, (Id - Ic) * t.bx), gy);
@@ -386,11 +370,7 @@ warp_bwd_tma_kernel(const __grid_constant__ CUtensorMap mapU, const __grid_const
                     }
                 }
             }
-            float gxn = gx * halfW, gyn = gy * halfH;
-            if (has_dimg) {
-                const float2 di = reinterpret_cast<const float2*>(s_dimg)[o];
-                gxn += di.x; gyn += di.y;
-            }
+            const float gxn = fmaf(gx, halfW, gimg[k][0]), gyn = fmaf(gy, halfH, gimg[k][1]);
             const float rz = __frcp_rn(zs);
             const float dxs = gxn * rz, dys = gyn * rz;
             const float dzs = -(gxn * xn + gyn * yn) * rz;
@@ -405,25 +385,25 @@ warp_bwd_tma_kernel(const __grid_constant__ CUtensorMap mapU, const __grid_const
         const float v = warp_sum(dh[k]);
         if (lane == 0) s_red[warp * 8 + k] = v;
     }
-    __syncthreads();
+    __syncthreads();                                  // also orders every shared atomic before the conversion below
     if (tid < 8) {
         float v = 0.0f;
 #pragma unroll
         for (int w = 0; w < kThreads / 32; ++w) v += s_red[w * 8 + tid];
-        parts[((size_t)ti->cell * (cfg.parts_y * cfg.parts_x) + ti->part) * 8 + tid] = v;
+        parts[((size_t)tl.cell * (cfg.parts_y * cfg.parts_x) + tl.part) * 8 + tid] = v;
     }
     if (fixed) {
-        // fixed point -> fp32 in place, then one TMA reduce-add of the whole box
-        const float inv = ti->inv_scale;
+        // fixed point -> fp32 in place, then ONE TMA reduce-add of the whole box into dU
         int4* a4 = reinterpret_cast<int4*>(s_acc);
         for (int i = tid; i < G::kBoxF / 4; i += kThreads) {
             const int4 v = a4[i];
-            reinterpret_cast<float4*>(s_acc)[i] = make_float4((float)v.x * inv, (float)v.y * inv, (float)v.z * inv, (float)v.w * inv);
+            reinterpret_cast<float4*>(s_acc)[i] = make_float4((float)v.x * inv_scale, (float)v.y * inv_scale,
+                                                              (float)v.z * inv_scale, (float)v.w * inv_scale);
         }
         tma::fence_proxy_async();
         __syncthreads();
         if (tid == 0) {
-            tma::reduce_add_3d(&mapDU, s_acc, bx0 * C, by0, n);
+            tma::reduce_add_3d(&mapDU, s_acc, bx0 * C, by0, tl.n);
             tma::commit_group();
             tma::wait_group_read0();
         }
@@ -464,13 +444,21 @@ static int make_map(CUtensorMap* m, const void* base, int inner, int rows, int N
     return MGW_OK;
 }
 
-static int tiles_along(int ncell, int cell_px, int total, int T, int* max_per_cell)
+// fills the axis table; returns the tile count (or -1 if it does not fit) and the max tiles per cell
+static int fill_axis(AxisTab* tab, int ncell, int cell_px, int total, int T, int* max_per_cell)
 {
     int n = 0, mx = 0;
     for (int c = 0; c < ncell; ++c) {
-        const int s = c * cell_px, len = (c == ncell - 1) ? total - s : cell_px;
+        const int s = c * cell_px, len = (c == ncell - 1) ? total - s : cell_px;      // the last cell absorbs the remainder
         const int nt = (len + T - 1) / T;
-        n += nt;
+        for (int t = 0; t < nt; ++t) {
+            if (n >= kMaxTilesPerAxis) return -1;
+            const int vstart = s + t * T;                          // first row/col the tile OWNS
+            const int start = vstart < s + len - T ? vstart : s + len - T;      // edge tiles are shifted inward
+            tab->start[n] = (unsigned short)start; tab->vstart[n] = (unsigned short)vstart;
+            tab->cell[n] = (unsigned char)c; tab->part[n] = (unsigned char)t;
+            ++n;
+        }
         mx = nt > mx ? nt : mx;
     }
     *max_per_cell = mx;
@@ -479,7 +467,7 @@ static int tiles_along(int ncell, int cell_px, int total, int T, int* max_per_ce
 
 struct Plan {
     TileCfg cfg;
-    int TW, K, TH;
+    int TW, K, TH, nty, ntx;
 };
 
 // compiled (TW, K) variants: TH = K * 256/TW
@@ -490,8 +478,9 @@ static bool plan(const WarpShape& s, Plan* out)
 {
     if (s.OH != s.H || s.OW != s.W) return false;
     if (s.C != 1 && s.C != 3 && s.C != 4) return false;
+    if (s.H > 65535 || s.W > 65535 || s.gh > 255 || s.gw > 255 || s.N > 65535) return false;
     // tiles start at cell boundaries (or cell end - TW) and every TMA start address must be 16-byte aligned for
-    // out (C floats/px), black (1) and x/y maps (2): columns of cell boundaries must be multiples of 4
+    // out (C floats/px): columns of cell boundaries must be multiples of 4
     const int cell_h = s.H / s.gh, cell_w = s.W / s.gw;
     if (s.W % 4 != 0 || cell_w % 4 != 0) return false;
     double best_eff = 0;
@@ -509,11 +498,9 @@ static bool plan(const WarpShape& s, Plan* out)
     p.TW = kVariants[best][0]; p.K = kVariants[best][1]; p.TH = (kThreads / p.TW) * p.K;
     TileCfg& c = p.cfg;
     c.N = s.N; c.H = s.H; c.W = s.W; c.gh = s.gh; c.gw = s.gw;
-    c.cell_h = cell_h; c.cell_w = cell_w;
-    c.xalign = (s.C % 4 == 0) ? 1 : ((s.C % 2 == 0) ? 2 : 4);
-    c.nty = tiles_along(s.gh, cell_h, s.H, p.TH, &c.parts_y);
-    c.ntx = tiles_along(s.gw, cell_w, s.W, p.TW, &c.parts_x);
-    if ((long long)c.N * c.nty * c.ntx > 0x7fffffffLL) return false;
+    p.nty = fill_axis(&c.rows, s.gh, cell_h, s.H, p.TH, &c.parts_y);
+    p.ntx = fill_axis(&c.cols, s.gw, cell_w, s.W, p.TW, &c.parts_x);
+    if (p.nty < 0 || p.ntx < 0 || c.parts_y > 255 || c.parts_x > 255) return false;
     *out = p;
     return true;
 }
@@ -542,50 +529,45 @@ static int allow_smem(KernelT kernel, bool* done_for_device, const char* what)
 }
 
 template <int C, int TW, int K>
-static int launch_fwd_v(const float* U, const float* Hs, const TileCfg& c, float* out, float* black, float* img, cudaStream_t st)
+static int launch_fwd_v(const float* U, const float* Hs, const Plan& p, float* out, float* black, float* img, cudaStream_t st)
 {
     using G = Geo<C, TW, K>;
-    CUtensorMap mU, mOut, mImg, mBlk;
+    const TileCfg& c = p.cfg;
+    CUtensorMap mU, mOut;
     TRY_RC(make_map(&mU, U, c.W * C, c.H, c.N, G::SBW * C, G::SBH));
     TRY_RC(make_map(&mOut, out ? out : U, c.W * C, c.H, c.N, TW * C, G::TH));
-    if (img) TRY_RC(make_map(&mImg, img, c.W * 2, c.H, c.N, TW * 2, G::TH)); else mImg = mOut;
-    if (black) TRY_RC(make_map(&mBlk, black, c.W, c.H, c.N, TW, G::TH)); else mBlk = mOut;
-    const size_t smem = (size_t)(G::kBoxF + G::kOutF + G::kImgF + G::kBlkF) * 4 + 16 + sizeof(TileInfo) + 64;
+    const size_t smem = (size_t)(G::kBoxF + G::kOutF) * 4 + 16 + sizeof(TileInfo) + 64;
     static bool attr[64] = {};
     TRY_RC(allow_smem(warp_fwd_tma_kernel<C, TW, K>, attr, "warp_fwd_tma"));
-    const unsigned grid = (unsigned)(c.N * c.nty * c.ntx);
-    warp_fwd_tma_kernel<C, TW, K><<<grid, kThreads, smem, st>>>(mU, mOut, mImg, mBlk, U, Hs, c, out != nullptr, img != nullptr, black != nullptr);
+    warp_fwd_tma_kernel<C, TW, K><<<dim3(p.ntx, p.nty, c.N), kThreads, smem, st>>>(mU, mOut, U, Hs, c, out, img, black);
     return check_launch("warp_fwd_tma");
 }
 
 template <int C, int TW, int K>
-static int launch_bwd_v(const float* U, const float* Hs, const float* d_out, const float* d_img, const TileCfg& c, float* dU,
+static int launch_bwd_v(const float* U, const float* Hs, const float* d_out, const float* d_img, const Plan& p, float* dU,
                         float* parts, cudaStream_t st)
 {
     using G = Geo<C, TW, K>;
-    CUtensorMap mU, mDout, mDimg, mDU;
+    const TileCfg& c = p.cfg;
+    CUtensorMap mU, mDU;
     TRY_RC(make_map(&mU, U, c.W * C, c.H, c.N, G::SBW * C, G::SBH));
-    TRY_RC(make_map(&mDout, d_out, c.W * C, c.H, c.N, TW * C, G::TH));
-    if (d_img) TRY_RC(make_map(&mDimg, d_img, c.W * 2, c.H, c.N, TW * 2, G::TH)); else mDimg = mDout;
     if (dU) TRY_RC(make_map(&mDU, dU, c.W * C, c.H, c.N, G::SBW * C, G::SBH)); else mDU = mU;
-    const size_t smem = (size_t)(G::kBoxF + G::kOutF + G::kImgF + 128 + (dU ? G::kBoxF : 0)) * 4 + 64;
+    const size_t smem = (size_t)(G::kBoxF + 128 + (dU ? G::kBoxF : 0)) * 4 + 64;
     static bool attr[64] = {};
     TRY_RC(allow_smem(warp_bwd_tma_kernel<C, TW, K>, attr, "warp_bwd_tma"));
-    const unsigned grid = (unsigned)(c.N * c.nty * c.ntx);
-    warp_bwd_tma_kernel<C, TW, K><<<grid, kThreads, smem, st>>>(mU, mDout, mDimg, mDU, U, Hs, c, dU, d_img != nullptr, parts);
+    warp_bwd_tma_kernel<C, TW, K><<<dim3(p.ntx, p.nty, c.N), kThreads, smem, st>>>(mU, mDU, U, Hs, d_out, d_img, c, dU, parts);
     return check_launch("warp_bwd_tma");
 }
 
 template <int C>
 static int launch_fwd_c(const Plan& p, const float* U, const float* Hs, float* out, float* black, float* img, cudaStream_t st)
 {
-    const TileCfg& c = p.cfg;
-    if (p.TW == 32 && p.K == 3) return launch_fwd_v<C, 32, 3>(U, Hs, c, out, black, img, st);
-    if (p.TW == 32 && p.K == 2) return launch_fwd_v<C, 32, 2>(U, Hs, c, out, black, img, st);
-    if (p.TW == 32 && p.K == 1) return launch_fwd_v<C, 32, 1>(U, Hs, c, out, black, img, st);
+    if (p.TW == 32 && p.K == 3) return launch_fwd_v<C, 32, 3>(U, Hs, p, out, black, img, st);
+    if (p.TW == 32 && p.K == 2) return launch_fwd_v<C, 32, 2>(U, Hs, p, out, black, img, st);
+    if (p.TW == 32 && p.K == 1) return launch_fwd_v<C, 32, 1>(U, Hs, p, out, black, img, st);
     if constexpr (C != 4) {
-        if (p.TW == 64 && p.K == 6) return launch_fwd_v<C, 64, 6>(U, Hs, c, out, black, img, st);
-        if (p.TW == 64 && p.K == 3) return launch_fwd_v<C, 64, 3>(U, Hs, c, out, black, img, st);
+        if (p.TW == 64 && p.K == 6) return launch_fwd_v<C, 64, 6>(U, Hs, p, out, black, img, st);
+        if (p.TW == 64 && p.K == 3) return launch_fwd_v<C, 64, 3>(U, Hs, p, out, black, img, st);
     }
     return set_error(MGW_ERR_UNSUPPORTED, "warp_fwd_tma: no tile variant");
 }
@@ -594,13 +576,12 @@ template <int C>
 static int launch_bwd_c(const Plan& p, const float* U, const float* Hs, const float* d_out, const float* d_img, float* dU,
                         float* parts, cudaStream_t st)
 {
-    const TileCfg& c = p.cfg;
-    if (p.TW == 32 && p.K == 3) return launch_bwd_v<C, 32, 3>(U, Hs, d_out, d_img, c, dU, parts, st);
-    if (p.TW == 32 && p.K == 2) return launch_bwd_v<C, 32, 2>(U, Hs, d_out, d_img, c, dU, parts, st);
-    if (p.TW == 32 && p.K == 1) return launch_bwd_v<C, 32, 1>(U, Hs, d_out, d_img, c, dU, parts, st);
+    if (p.TW == 32 && p.K == 3) return launch_bwd_v<C, 32, 3>(U, Hs, d_out, d_img, p, dU, parts, st);
+    if (p.TW == 32 && p.K == 2) return launch_bwd_v<C, 32, 2>(U, Hs, d_out, d_img, p, dU, parts, st);
+    if (p.TW == 32 && p.K == 1) return launch_bwd_v<C, 32, 1>(U, Hs, d_out, d_img, p, dU, parts, st);
     if constexpr (C != 4) {
-        if (p.TW == 64 && p.K == 6) return launch_bwd_v<C, 64, 6>(U, Hs, d_out, d_img, c, dU, parts, st);
-        if (p.TW == 64 && p.K == 3) return launch_bwd_v<C, 64, 3>(U, Hs, d_out, d_img, c, dU, parts, st);
+        if (p.TW == 64 && p.K == 6) return launch_bwd_v<C, 64, 6>(U, Hs, d_out, d_img, p, dU, parts, st);
+        if (p.TW == 64 && p.K == 3) return launch_bwd_v<C, 64, 3>(U, Hs, d_out, d_img, p, dU, parts, st);
     }
     return set_error(MGW_ERR_UNSUPPORTED, "warp_bwd_tma: no tile variant");
 }
