@@ -19,6 +19,8 @@
 // out-of-range pixels) and weights outside [-1,1] fall back to global loads / global fp32 atomics, so results never
 // depend on the box heuristic.  Arithmetic is mgw_device.cuh's, bit-identical to the generic kernels and the C oracle.
 #include <cuda.h>
+#include <cstdio>
+#include <cstdlib>
 
 #include "mgw_internal.h"
 #include "mgw_tma.cuh"
@@ -63,6 +65,7 @@ struct Geo {
 // what warp 0 works out per tile for everyone else
 struct TileInfo {
     int bx0, by0;                   // first column / row of the staged source box
+    int interior;                   // every tap of every pixel of the tile is unclipped AND inside the staged box
     int area_ok;                    // backward: the tile is not magnified beyond what the fixed-point headroom covers
     float wmax[kThreads / 32];      // backward: per-warp max|d_out|
 };
@@ -86,10 +89,12 @@ __device__ __forceinline__ Tile this_tile(const TileCfg& cfg)
 // Source box of the tile, by warp 0 (lanes 0-3 project one corner each): bbox of the 4 projected corners (+1 px for
 // rounding, +1 for the x1/y1 taps), clipped to the image like the taps are.  A projective map with no pole inside the
 // tile (z of one sign at the corners) sends the rectangle into the convex hull of its corner images, so the box holds
-// every tap; otherwise any box will do (per-tap fallback).
+// every tap.  `interior` says so, and additionally that no tap is clipped: such tiles (the vast majority) run a
+// per-pixel path without clipping, bounds tests or address arithmetic; all other tiles test every tap and fall back
+// to global memory for the ones outside the box.
 template <int C, int TW, int K>
 __device__ __forceinline__ void source_box(const TileCfg& cfg, const Tile& tl, const float (&Hc)[9], float stepx, float stepy,
-                                           int& bx0, int& by0, int& area_ok)
+                                           int& bx0, int& by0, int& interior, int& area_ok)
 {
     using G = Geo<C, TW, K>;
     const int k4 = threadIdx.x & 3;
@@ -109,19 +114,48 @@ __device__ __forceinline__ void source_box(const TileCfg& cfg, const Tile& tl, c
         ok = ok && (__shfl_xor_sync(0xffffffffu, (int)ok, o) != 0);
     }
     ok = ok && (sgn == 4 || sgn == -4);
-    bx0 = 0; by0 = 0; area_ok = 0;
+    bx0 = 0; by0 = 0; interior = 0; area_ok = 0;
     if (ok) {
-        const int ix0 = clipi((int)floorf(xmin) - 1, 0, cfg.W - 1), ix1 = clipi((int)floorf(xmax) + 2, 0, cfg.W - 1);
-        const int iy0 = clipi((int)floorf(ymin) - 1, 0, cfg.H - 1), iy1 = clipi((int)floorf(ymax) + 2, 0, cfg.H - 1);
+        const int ux0 = (int)floorf(xmin) - 1, ux1 = (int)floorf(xmax) + 2;      // unclipped tap range, 1 px of slack
+        const int uy0 = (int)floorf(ymin) - 1, uy1 = (int)floorf(ymax) + 2;
+        const int ix0 = clipi(ux0, 0, cfg.W - 1), ix1 = clipi(ux1, 0, cfg.W - 1);
+        const int iy0 = clipi(uy0, 0, cfg.H - 1), iy1 = clipi(uy1, 0, cfg.H - 1);
         const int needw = ix1 - ix0 + 1, needh = iy1 - iy0 + 1;
         bx0 = needw <= G::SBW ? ix0 : ix0 + (needw - G::SBW) / 2;
         by0 = needh <= G::SBH ? iy0 : iy0 + (needh - G::SBH) / 2;
         // TMA needs the box to start on a 16-byte boundary of global memory (measured on B200: a start that is not
         // a multiple of 4 floats raises "illegal instruction"): round the first column down
         bx0 -= bx0 % G::kXalign;
+        interior = (ux0 >= 0 && ux1 <= cfg.W - 1 && uy0 >= 0 && uy1 <= cfg.H - 1 &&
+                    ux1 - bx0 < G::SBW && uy1 - by0 < G::SBH) ? 1 : 0;
         // magnification guard for the fixed-point accumulator: bbox area >= 1/16 of the tile area
         area_ok = ((xmax - xmin + 1.0f) * (ymax - ymin + 1.0f) * 16.0f >= (float)(G::TH * TW)) ? 1 : 0;
     }
+}
+
+// taps of an INTERIOR pixel: no clipping can occur, so x0f = floor(x), x1f = x0f + 1 (exact) and the reference's
+// weights (spatial_transformer3.py:114-121) reduce to these expressions bit for bit
+struct FastTaps { int x0, y0; float ax, bx, ay, by; };
+__device__ __forceinline__ FastTaps make_taps_interior(float xn, float yn, int IH, int IW)
+{
+    const float x = __fmul_rn(__fmul_rn(__fadd_rn(xn, 1.0f), (float)IW), 0.5f);
+    const float y = __fmul_rn(__fmul_rn(__fadd_rn(yn, 1.0f), (float)IH), 0.5f);
+    const float fx = floorf(x), fy = floorf(y);
+    FastTaps t;
+    t.x0 = __float2int_rz(fx); t.y0 = __float2int_rz(fy);
+    t.ax = __fsub_rn(__fadd_rn(fx, 1.0f), x); t.bx = __fsub_rn(x, fx);
+    t.ay = __fsub_rn(__fadd_rn(fy, 1.0f), y); t.by = __fsub_rn(y, fy);
+    return t;
+}
+
+__device__ __forceinline__ float blend4(float ax, float bx, float ay, float by, float Ia, float Ib, float Ic, float Id)
+{
+    const float wa = __fmul_rn(ax, ay), wb = __fmul_rn(ax, by), wc = __fmul_rn(bx, ay), wd = __fmul_rn(bx, by);
+    float s = __fmul_rn(wa, Ia);
+    s = __fadd_rn(s, __fmul_rn(wb, Ib));
+    s = __fadd_rn(s, __fmul_rn(wc, Ic));
+    s = __fadd_rn(s, __fmul_rn(wd, Id));
+    return s;
 }
 
 // ------------------------------------------------------------------------------------------------ forward
@@ -150,10 +184,10 @@ warp_fwd_tma_kernel(const __grid_constant__ CUtensorMap mapU, const __grid_const
     const float stepx = lin_step(cfg.W), stepy = lin_step(cfg.H);
     __syncthreads();                                  // barrier initialised; nobody has waited on anything long yet
     if (tid < 32 && out) {
-        int bx0, by0, area_ok;
-        source_box<C, TW, K>(cfg, tl, Hc, stepx, stepy, bx0, by0, area_ok);
+        int bx0, by0, interior, area_ok;
+        source_box<C, TW, K>(cfg, tl, Hc, stepx, stepy, bx0, by0, interior, area_ok);
         if (tid == 0) {
-            ti->bx0 = bx0; ti->by0 = by0;
+            ti->bx0 = bx0; ti->by0 = by0; ti->interior = interior;
             tma::mbar_expect_tx(bar, (uint32_t)(G::SBH * G::SBW * C * sizeof(float)));     // release: publishes ti
             tma::load_3d(s_src, &mapU, bar, bx0 * C, by0, tl.n);
         }
@@ -163,45 +197,57 @@ warp_fwd_tma_kernel(const __grid_constant__ CUtensorMap mapU, const __grid_const
     const float xt = lin_at(tl.c0 + tx, stepx);
     const float hx0 = __fmul_rn(Hc[0], xt), hx3 = __fmul_rn(Hc[3], xt), hx6 = __fmul_rn(Hc[6], xt);   // first term of hrow()
     float xn[K], yn[K];
+    {
+        size_t p = ((size_t)tl.n * cfg.H + tl.r0 + g * K) * cfg.W + tl.c0 + tx;
 #pragma unroll
-    for (int k = 0; k < K; ++k) {
-        const int row = tl.r0 + g * K + k;
-        const float yt = lin_at(row, stepy);
-        const float xs = __fadd_rn(__fmaf_rn(Hc[1], yt, hx0), Hc[2]);
-        const float ys = __fadd_rn(__fmaf_rn(Hc[4], yt, hx3), Hc[5]);
-        float zs = __fadd_rn(__fmaf_rn(Hc[7], yt, hx6), Hc[8]);
-        zs = __fadd_rn(zs, (zs >= 0.0f) ? 1e-8f : -1e-8f);
-        xn[k] = __fdiv_rn(xs, zs);
-        yn[k] = __fdiv_rn(ys, zs);
-        // x_map,y_map and black_pix are 8 / 4 contiguous bytes per lane: plain coalesced stores, no staging
-        const size_t p = ((size_t)tl.n * cfg.H + row) * cfg.W + tl.c0 + tx;
-        if (img) reinterpret_cast<float2*>(img)[p] = make_float2(xn[k], yn[k]);
-        if (black) black[p] = black_of(xn[k], yn[k]);
+        for (int k = 0; k < K; ++k, p += cfg.W) {
+            const float yt = lin_at(tl.r0 + g * K + k, stepy);
+            const float xs = __fadd_rn(__fmaf_rn(Hc[1], yt, hx0), Hc[2]);
+            const float ys = __fadd_rn(__fmaf_rn(Hc[4], yt, hx3), Hc[5]);
+            float zs = __fadd_rn(__fmaf_rn(Hc[7], yt, hx6), Hc[8]);
+            zs = __fadd_rn(zs, (zs >= 0.0f) ? 1e-8f : -1e-8f);
+            xn[k] = __fdiv_rn(xs, zs);
+            yn[k] = __fdiv_rn(ys, zs);
+            // x_map,y_map and black_pix are 8 / 4 contiguous bytes per lane: plain coalesced stores, no staging
+            if (img) reinterpret_cast<float2*>(img)[p] = make_float2(xn[k], yn[k]);
+            if (black) black[p] = black_of(xn[k], yn[k]);
+        }
     }
     if (!out) return;
     tma::mbar_wait(bar, 0);                           // acquire: the source box has landed and ti is visible
     const int bx0 = ti->bx0, by0 = ti->by0;
-    const float* Un = U + (size_t)tl.n * cfg.H * cfg.W * C;
+    if (ti->interior) {
 #pragma unroll
-    for (int k = 0; k < K; ++k) {
-        const int lr = g * K + k;
-        const Taps t = make_taps(xn[k], yn[k], cfg.H, cfg.W);
-        const int sx0 = t.x0 - bx0, sx1 = t.x1 - bx0, sy0 = t.y0 - by0, sy1 = t.y1 - by0;
-        float* o = s_out + (lr * TW + tx) * C;
-        if (sx0 >= 0 && sx1 < G::SBW && sy0 >= 0 && sy1 < G::SBH) {
-            const float* pa = s_src + (sy0 * G::SBW + sx0) * C;
-            const float* pb = s_src + (sy1 * G::SBW + sx0) * C;
-            const float* pc = s_src + (sy0 * G::SBW + sx1) * C;
-            const float* pd = s_src + (sy1 * G::SBW + sx1) * C;
+        for (int k = 0; k < K; ++k) {
+            const FastTaps t = make_taps_interior(xn[k], yn[k], cfg.H, cfg.W);
+            const float* pa = s_src + ((t.y0 - by0) * G::SBW + (t.x0 - bx0)) * C;
+            float* o = s_out + ((g * K + k) * TW + tx) * C;
 #pragma unroll
-            for (int ch = 0; ch < C; ++ch) o[ch] = blend(t, pa[ch], pb[ch], pc[ch], pd[ch]);
-        } else {
-            const float* pa = Un + ((size_t)t.y0 * cfg.W + t.x0) * C;
-            const float* pb = Un + ((size_t)t.y1 * cfg.W + t.x0) * C;
-            const float* pc = Un + ((size_t)t.y0 * cfg.W + t.x1) * C;
-            const float* pd = Un + ((size_t)t.y1 * cfg.W + t.x1) * C;
+            for (int ch = 0; ch < C; ++ch)
+                o[ch] = blend4(t.ax, t.bx, t.ay, t.by, pa[ch], pa[G::SBW * C + ch], pa[C + ch], pa[G::SBW * C + C + ch]);
+        }
+    } else {
+        const float* Un = U + (size_t)tl.n * cfg.H * cfg.W * C;
 #pragma unroll
-            for (int ch = 0; ch < C; ++ch) o[ch] = blend(t, __ldg(pa + ch), __ldg(pb + ch), __ldg(pc + ch), __ldg(pd + ch));
+        for (int k = 0; k < K; ++k) {
+            const Taps t = make_taps(xn[k], yn[k], cfg.H, cfg.W);
+            const int sx0 = t.x0 - bx0, sx1 = t.x1 - bx0, sy0 = t.y0 - by0, sy1 = t.y1 - by0;
+            float* o = s_out + ((g * K + k) * TW + tx) * C;
+            if (sx0 >= 0 && sx1 < G::SBW && sy0 >= 0 && sy1 < G::SBH) {
+                const float* pa = s_src + (sy0 * G::SBW + sx0) * C;
+                const float* pb = s_src + (sy1 * G::SBW + sx0) * C;
+                const float* pc = s_src + (sy0 * G::SBW + sx1) * C;
+                const float* pd = s_src + (sy1 * G::SBW + sx1) * C;
+#pragma unroll
+                for (int ch = 0; ch < C; ++ch) o[ch] = blend(t, pa[ch], pb[ch], pc[ch], pd[ch]);
+            } else {
+                const float* pa = Un + ((size_t)t.y0 * cfg.W + t.x0) * C;
+                const float* pb = Un + ((size_t)t.y1 * cfg.W + t.x0) * C;
+                const float* pc = Un + ((size_t)t.y0 * cfg.W + t.x1) * C;
+                const float* pd = Un + ((size_t)t.y1 * cfg.W + t.x1) * C;
+#pragma unroll
+                for (int ch = 0; ch < C; ++ch) o[ch] = blend(t, __ldg(pa + ch), __ldg(pb + ch), __ldg(pc + ch), __ldg(pd + ch));
+            }
         }
     }
     tma::fence_proxy_async();
@@ -214,6 +260,17 @@ warp_fwd_tma_kernel(const __grid_constant__ CUtensorMap mapU, const __grid_const
 }
 
 // ------------------------------------------------------------------------------------------------ backward
+// dH terms of one pixel accumulated into the thread's 8 partial sums
+__device__ __forceinline__ void accumulate_dh(float (&dh)[8], float gxn, float gyn, float xn, float yn, float zs, float xt, float yt)
+{
+    const float rz = __frcp_rn(zs);
+    const float dxs = gxn * rz, dys = gyn * rz;
+    const float dzs = -(gxn * xn + gyn * yn) * rz;
+    dh[0] = fmaf(dxs, xt, dh[0]); dh[1] = fmaf(dxs, yt, dh[1]); dh[2] += dxs;
+    dh[3] = fmaf(dys, xt, dh[3]); dh[4] = fmaf(dys, yt, dh[4]); dh[5] += dys;
+    dh[6] = fmaf(dzs, xt, dh[6]); dh[7] = fmaf(dzs, yt, dh[7]);
+}
+
 template <int C, int TW, int K>
 __global__ void __launch_bounds__(kThreads, 3)
 warp_bwd_tma_kernel(const __grid_constant__ CUtensorMap mapU, const __grid_constant__ CUtensorMap mapDU,
@@ -244,16 +301,18 @@ warp_bwd_tma_kernel(const __grid_constant__ CUtensorMap mapU, const __grid_const
 
     // this thread's K pixels of d_out / d_img: 12 / 8 contiguous bytes per lane, coalesced, all loads in flight at once
     float gout[K][C], gimg[K][2];
+    {
+        size_t p = ((size_t)tl.n * cfg.H + tl.r0 + g * K) * cfg.W + col;
 #pragma unroll
-    for (int k = 0; k < K; ++k) {
-        const size_t p = ((size_t)tl.n * cfg.H + tl.r0 + g * K + k) * cfg.W + col;
+        for (int k = 0; k < K; ++k, p += cfg.W) {
 #pragma unroll
-        for (int ch = 0; ch < C; ++ch) gout[k][ch] = __ldg(d_out + p * C + ch);
-        if (d_img) {
-            const float2 di = __ldg(reinterpret_cast<const float2*>(d_img) + p);
-            gimg[k][0] = di.x; gimg[k][1] = di.y;
-        } else {
-            gimg[k][0] = 0.0f; gimg[k][1] = 0.0f;
+            for (int ch = 0; ch < C; ++ch) gout[k][ch] = __ldg(d_out + p * C + ch);
+            if (d_img) {
+                const float2 di = __ldg(reinterpret_cast<const float2*>(d_img) + p);
+                gimg[k][0] = di.x; gimg[k][1] = di.y;
+            } else {
+                gimg[k][0] = 0.0f; gimg[k][1] = 0.0f;
+            }
         }
     }
     if (dU) {
@@ -262,10 +321,10 @@ warp_bwd_tma_kernel(const __grid_constant__ CUtensorMap mapU, const __grid_const
     }
     __syncthreads();                                  // barrier initialised
     if (tid < 32) {
-        int bx0, by0, area_ok;
-        source_box<C, TW, K>(cfg, tl, Hc, stepx, stepy, bx0, by0, area_ok);
+        int bx0, by0, interior, area_ok;
+        source_box<C, TW, K>(cfg, tl, Hc, stepx, stepy, bx0, by0, interior, area_ok);
         if (tid == 0) {
-            ti->bx0 = bx0; ti->by0 = by0; ti->area_ok = area_ok;
+            ti->bx0 = bx0; ti->by0 = by0; ti->interior = interior; ti->area_ok = area_ok;
             tma::mbar_expect_tx(bar, (uint32_t)(G::SBH * G::SBW * C * sizeof(float)));
             tma::load_3d(s_src, &mapU, bar, bx0 * C, by0, tl.n);
         }
@@ -305,78 +364,95 @@ warp_bwd_tma_kernel(const __grid_constant__ CUtensorMap mapU, const __grid_const
 
     const float xt = lin_at(col, stepx);
     const float hx0 = __fmul_rn(Hc[0], xt), hx3 = __fmul_rn(Hc[3], xt), hx6 = __fmul_rn(Hc[6], xt);
-    const float* Un = U + (size_t)tl.n * cfg.H * cfg.W * C;
-    float* dUn = dU ? dU + (size_t)tl.n * cfg.H * cfg.W * C : nullptr;
     float dh[8];
 #pragma unroll
     for (int k = 0; k < 8; ++k) dh[k] = 0.0f;
     const float halfW = 0.5f * (float)cfg.W, halfH = 0.5f * (float)cfg.H;
 
     tma::mbar_wait(bar, 0);
+    if (ti->interior && (fixed || !dU)) {
+        // ---- fast path: every tap unclipped and inside the box; shared-memory offsets are compile-time constants
 #pragma unroll
-    for (int k = 0; k < K; ++k) {
-        const int row = tl.r0 + g * K + k;
-        if (row >= tl.vr0 && col >= tl.vc0) {
-            const float yt = lin_at(row, stepy);
-            const float xs = __fadd_rn(__fmaf_rn(Hc[1], yt, hx0), Hc[2]);
-            const float ys = __fadd_rn(__fmaf_rn(Hc[4], yt, hx3), Hc[5]);
-            float zs = __fadd_rn(__fmaf_rn(Hc[7], yt, hx6), Hc[8]);
-            zs = __fadd_rn(zs, (zs >= 0.0f) ? 1e-8f : -1e-8f);
-            const float xn = __fdiv_rn(xs, zs), yn = __fdiv_rn(ys, zs);
-            const Taps t = make_taps(xn, yn, cfg.H, cfg.W);
-            const int sx0 = t.x0 - bx0, sx1 = t.x1 - bx0, sy0 = t.y0 - by0, sy1 = t.y1 - by0;
-            const bool inbox = sx0 >= 0 && sx1 < G::SBW && sy0 >= 0 && sy1 < G::SBH;
-            const float wa = t.ax * t.ay, wb = t.ax * t.by, wc = t.bx * t.ay, wd = t.bx * t.by;
-            float gx = 0.0f, gy = 0.0f;
-            const bool scatter = (dU != nullptr) && taps_scatter(t);
-            if (inbox) {
+        for (int k = 0; k < K; ++k) {
+            const int row = tl.r0 + g * K + k;
+            if (row >= tl.vr0 && col >= tl.vc0) {
+                const float yt = lin_at(row, stepy);
+                const float xs = __fadd_rn(__fmaf_rn(Hc[1], yt, hx0), Hc[2]);
+                const float ys = __fadd_rn(__fmaf_rn(Hc[4], yt, hx3), Hc[5]);
+                float zs = __fadd_rn(__fmaf_rn(Hc[7], yt, hx6), Hc[8]);
+                zs = __fadd_rn(zs, (zs >= 0.0f) ? 1e-8f : -1e-8f);
+                const float xn = __fdiv_rn(xs, zs), yn = __fdiv_rn(ys, zs);
+                const FastTaps t = make_taps_interior(xn, yn, cfg.H, cfg.W);
+                const int ia = ((t.y0 - by0) * G::SBW + (t.x0 - bx0)) * C;
+                const float* pa = s_src + ia;
+                int* qa = s_acc + ia;
+                const float wa = t.ax * t.ay, wb = t.ax * t.by, wc = t.bx * t.ay, wd = t.bx * t.by;
+                float gx = 0.0f, gy = 0.0f;
+#pragma unroll
+                for (int ch = 0; ch < C; ++ch) {
+                    const float gch = gout[k][ch];
+                    const float Ia = pa[ch], Ib = pa[G::SBW * C + ch], Ic = pa[C + ch], Id = pa[G::SBW * C + C + ch];
+                    gx = fmaf(gch, fmaf(Ic - Ia, t.ay, (Id - Ib) * t.by), gx);
+                    gy = fmaf(gch, fmaf(Ib - Ia, t.ax, (Id - Ic) * t.bx), gy);
+                    if (dU) {
+                        const float gs = gch * scale;
+                        atomicAdd(qa + ch, __float2int_rn(wa * gs));
+                        atomicAdd(qa + G::SBW * C + ch, __float2int_rn(wb * gs));
+                        atomicAdd(qa + C + ch, __float2int_rn(wc * gs));
+                        atomicAdd(qa + G::SBW * C + C + ch, __float2int_rn(wd * gs));
+                    }
+                }
+                accumulate_dh(dh, fmaf(gx, halfW, gimg[k][0]), fmaf(gy, halfH, gimg[k][1]), xn, yn, zs, xt, yt);
+            }
+        }
+    } else {
+        const float* Un = U + (size_t)tl.n * cfg.H * cfg.W * C;
+        float* dUn = dU ? dU + (size_t)tl.n * cfg.H * cfg.W * C : nullptr;
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            const int row = tl.r0 + g * K + k;
+            if (row >= tl.vr0 && col >= tl.vc0) {
+                const float yt = lin_at(row, stepy);
+                const float xs = __fadd_rn(__fmaf_rn(Hc[1], yt, hx0), Hc[2]);
+                const float ys = __fadd_rn(__fmaf_rn(Hc[4], yt, hx3), Hc[5]);
+                float zs = __fadd_rn(__fmaf_rn(Hc[7], yt, hx6), Hc[8]);
+                zs = __fadd_rn(zs, (zs >= 0.0f) ? 1e-8f : -1e-8f);
+                const float xn = __fdiv_rn(xs, zs), yn = __fdiv_rn(ys, zs);
+                const Taps t = make_taps(xn, yn, cfg.H, cfg.W);
+                const int sx0 = t.x0 - bx0, sx1 = t.x1 - bx0, sy0 = t.y0 - by0, sy1 = t.y1 - by0;
+                const bool inbox = sx0 >= 0 && sx1 < G::SBW && sy0 >= 0 && sy1 < G::SBH;
+                const float wa = t.ax * t.ay, wb = t.ax * t.by, wc = t.bx * t.ay, wd = t.bx * t.by;
+                float gx = 0.0f, gy = 0.0f;
+                const bool scatter = (dU != nullptr) && taps_scatter(t);
+                const size_t ga = ((size_t)t.y0 * cfg.W + t.x0) * C, gb = ((size_t)t.y1 * cfg.W + t.x0) * C;
+                const size_t gc = ((size_t)t.y0 * cfg.W + t.x1) * C, gd = ((size_t)t.y1 * cfg.W + t.x1) * C;
                 const int ia = (sy0 * G::SBW + sx0) * C, ib = (sy1 * G::SBW + sx0) * C;
                 const int ic = (sy0 * G::SBW + sx1) * C, id = (sy1 * G::SBW + sx1) * C;
 #pragma unroll
                 for (int ch = 0; ch < C; ++ch) {
                     const float gch = gout[k][ch];
-                    const float Ia = s_src[ia + ch], Ib = s_src[ib + ch], Ic = s_src[ic + ch], Id = s_src[id + ch];
+                    float Ia, Ib, Ic, Id;
+                    if (inbox) { Ia = s_src[ia + ch]; Ib = s_src[ib + ch]; Ic = s_src[ic + ch]; Id = s_src[id + ch]; }
+                    else { Ia = __ldg(Un + ga + ch); Ib = __ldg(Un + gb + ch); Ic = __ldg(Un + gc + ch); Id = __ldg(Un + gd + ch); }
                     gx = fmaf(gch, fmaf(Ic - Ia, t.ay, (Id - Ib) * t.by), gx);
                     gy = fmaf(gch, fmaf(Ib - Ia, t.ax, (Id - Ic) * t.bx), gy);
                     if (scatter) {
-                        if (fixed) {           // unclipped taps have weights in [0,1], so |w*g| <= max|d_out|
+                        if (inbox && fixed) {      // unclipped taps have weights in [0,1], so |w*g| <= max|d_out|
                             const float gs = gch * scale;
                             atomicAdd(s_acc + ia + ch, __float2int_rn(wa * gs));
                             atomicAdd(s_acc + ib + ch, __float2int_rn(wb * gs));
                             atomicAdd(s_acc + ic + ch, __float2int_rn(wc * gs));
                             atomicAdd(s_acc + id + ch, __float2int_rn(wd * gs));
                         } else {
-                            atomicAdd(dUn + ((size_t)t.y0 * cfg.W + t.x0) * C + ch, wa * gch);
-                            atomicAdd(dUn + ((size_t)t.y1 * cfg.W + t.x0) * C + ch, wb * gch);
-                            atomicAdd(dUn + ((size_t)t.y0 * cfg.W + t.x1) * C + ch, wc * gch);
-                            atomicAdd(dUn + ((size_t)t.y1 * cfg.W + t.x1) * C + ch, wd * gch);
+                            atomicAdd(dUn + ga + ch, wa * gch);
+                            atomicAdd(dUn + gb + ch, wb * gch);
+                            atomicAdd(dUn + gc + ch, wc * gch);
+                            atomicAdd(dUn + gd + ch, wd * gch);
                         }
                     }
                 }
-            } else {
-                const size_t ia = ((size_t)t.y0 * cfg.W + t.x0) * C, ib = ((size_t)t.y1 * cfg.W + t.x0) * C;
-                const size_t ic = ((size_t)t.y0 * cfg.W + t.x1) * C, id = ((size_t)t.y1 * cfg.W + t.x1) * C;
-#pragma unroll
-                for (int ch = 0; ch < C; ++ch) {
-                    const float gch = gout[k][ch];
-                    const float Ia = __ldg(Un + ia + ch), Ib = __ldg(Un + ib + ch), Ic = __ldg(Un + ic + ch), Id = __ldg(Un + id + ch);
-                    gx = fmaf(gch, fmaf(Ic - Ia, t.ay, (Id - Ib) * t.by), gx);
-                    gy = fmaf(gch, fmaf(Ib - Ia, t.ax, (Id - Ic) * t.bx), gy);
-                    if (scatter) {
-                        atomicAdd(dUn + ia + ch, wa * gch);
-                        atomicAdd(dUn + ib + ch, wb * gch);
-                        atomicAdd(dUn + ic + ch, wc * gch);
-                        atomicAdd(dUn + id + ch, wd * gch);
-                    }
-                }
+                accumulate_dh(dh, fmaf(gx, halfW, gimg[k][0]), fmaf(gy, halfH, gimg[k][1]), xn, yn, zs, xt, yt);
             }
-            const float gxn = fmaf(gx, halfW, gimg[k][0]), gyn = fmaf(gy, halfH, gimg[k][1]);
-            const float rz = __frcp_rn(zs);
-            const float dxs = gxn * rz, dys = gyn * rz;
-            const float dzs = -(gxn * xn + gyn * yn) * rz;
-            dh[0] = fmaf(dxs, xt, dh[0]); dh[1] = fmaf(dxs, yt, dh[1]); dh[2] += dxs;
-            dh[3] = fmaf(dys, xt, dh[3]); dh[4] = fmaf(dys, yt, dh[4]); dh[5] += dys;
-            dh[6] = fmaf(dzs, xt, dh[6]); dh[7] = fmaf(dzs, yt, dh[7]);
         }
     }
     // dH: warp shuffle -> shared -> one partial per tile
@@ -492,6 +568,12 @@ static bool plan(const WarpShape& s, Plan* out)
         const double ey = (double)cell_h / (((cell_h + th - 1) / th) * th), ex = (double)cell_w / (((cell_w + tw - 1) / tw) * tw);
         const double eff = ey * ex * (tw == 64 ? 1.0 : 0.93) * (th >= 12 ? 1.0 : 0.9);      // larger tiles amortise the halo
         if (eff > best_eff) { best_eff = eff; best = v; }
+    }
+    if (const char* force = getenv("MGW_TILE")) {                  // tuning aid: MGW_TILE=64x3 forces a compiled variant if it fits
+        int tw = 0, k = 0;
+        if (sscanf(force, "%dx%d", &tw, &k) == 2)
+            for (int v = 0; v < 5; ++v)
+                if (kVariants[v][0] == tw && kVariants[v][1] == k && tw <= cell_w && (kThreads / tw) * k <= cell_h && !(s.C == 4 && tw == 64)) best = v;
     }
     if (best < 0) return false;
     Plan p;
