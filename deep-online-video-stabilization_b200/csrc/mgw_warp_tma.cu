@@ -29,7 +29,7 @@ namespace mgw {
 
 #define TRY_RC(expr) do { const int rc_ = (expr); if (rc_ != MGW_OK) return rc_; } while (0)
 
-constexpr int kThreads = 256;
+constexpr int kMaxWarps = 16;
 
 constexpr int kMaxTilesPerAxis = 128;
 
@@ -48,16 +48,20 @@ struct TileCfg {
     AxisTab rows, cols;             // grid = (cols, rows, N): blockIdx is the tile, no index arithmetic on the device
 };
 
-template <int C, int TW, int K>
+template <int C, int TW, int K, int NT>
 struct Geo {
-    static constexpr int kGroups = kThreads / TW;
+    static constexpr int kGroups = NT / TW;
     static constexpr int TH = kGroups * K;
     static constexpr int kXalign = (C % 4 == 0) ? 1 : ((C % 2 == 0) ? 2 : 4);
-    static constexpr int kCap = (256 / C) / 4 * 4;                                   // TMA box dims are <= 256 elements
-    static constexpr int kWant = ((TW * 13 + 9) / 10 + 4 + (kXalign - 1) + 3) / 4 * 4;
-    static constexpr int SBW = kWant < kCap ? kWant : kCap;                          // staged source box, pixels
+    // Row pitch of the staged box in floats = TMA box inner dimension (<= 256 elements).  It is a multiple of 32 so
+    // that a tap's bank depends only on its column: lanes of a warp that sit on different source rows (rotation,
+    // shear) then never collide (a 252-float pitch made 40-50 % of the shared wavefronts conflict replays).  The
+    // box need not hold a whole number of pixels; SBW is the number of complete pixels in a row.
+    static constexpr int kWantF = (((TW * 13 + 9) / 10 + 4 + (kXalign - 1)) * C + 31) / 32 * 32;
+    static constexpr int kRowF = kWantF < 256 ? kWantF : 256;
+    static constexpr int SBW = kRowF / C;                                            // staged source box, pixels
     static constexpr int SBH = (TH * 13 + 9) / 10 + 4;
-    static constexpr int kBoxF = (SBH * SBW * C + 31) / 32 * 32;                     // floats, 128-byte chunks
+    static constexpr int kBoxF = SBH * kRowF;                                        // floats (multiple of 32)
     static constexpr int kOutF = (TH * TW * C + 31) / 32 * 32;
     static_assert(SBW >= TW + 4, "source box too narrow for this tile width / channel count");
 };
@@ -67,7 +71,7 @@ struct TileInfo {
     int bx0, by0;                   // first column / row of the staged source box
     int interior;                   // every tap of every pixel of the tile is unclipped AND inside the staged box
     int area_ok;                    // backward: the tile is not magnified beyond what the fixed-point headroom covers
-    float wmax[kThreads / 32];      // backward: per-warp max|d_out|
+    float wmax[kMaxWarps];          // backward: per-warp max|d_out|
 };
 
 struct Tile {
@@ -92,11 +96,11 @@ __device__ __forceinline__ Tile this_tile(const TileCfg& cfg)
 // every tap.  `interior` says so, and additionally that no tap is clipped: such tiles (the vast majority) run a
 // per-pixel path without clipping, bounds tests or address arithmetic; all other tiles test every tap and fall back
 // to global memory for the ones outside the box.
-template <int C, int TW, int K>
+template <int C, int TW, int K, int NT>
 __device__ __forceinline__ void source_box(const TileCfg& cfg, const Tile& tl, const float (&Hc)[9], float stepx, float stepy,
                                            int& bx0, int& by0, int& interior, int& area_ok)
 {
-    using G = Geo<C, TW, K>;
+    using G = Geo<C, TW, K, NT>;
     const int k4 = threadIdx.x & 3;
     const int rr = tl.r0 + ((k4 & 2) ? G::TH - 1 : 0), cc = tl.c0 + ((k4 & 1) ? TW - 1 : 0);
     const Proj q = project(Hc, lin_at(cc, stepx), lin_at(rr, stepy));
@@ -159,13 +163,13 @@ __device__ __forceinline__ float blend4(float ax, float bx, float ay, float by, 
 }
 
 // ------------------------------------------------------------------------------------------------ forward
-template <int C, int TW, int K>
-__global__ void __launch_bounds__(kThreads, 4)
+template <int C, int TW, int K, int NT>
+__global__ void __launch_bounds__(NT, NT == 256 ? 4 : 2)
 warp_fwd_tma_kernel(const __grid_constant__ CUtensorMap mapU, const __grid_constant__ CUtensorMap mapOut,
                     const float* __restrict__ U, const float* __restrict__ Hs, const __grid_constant__ TileCfg cfg,
                     float* __restrict__ out, float* __restrict__ img, float* __restrict__ black)
 {
-    using G = Geo<C, TW, K>;
+    using G = Geo<C, TW, K, NT>;
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     float* s_src = reinterpret_cast<float*>(smem_raw);
     float* s_out = s_src + G::kBoxF;
@@ -185,10 +189,10 @@ warp_fwd_tma_kernel(const __grid_constant__ CUtensorMap mapU, const __grid_const
     __syncthreads();                                  // barrier initialised; nobody has waited on anything long yet
     if (tid < 32 && out) {
         int bx0, by0, interior, area_ok;
-        source_box<C, TW, K>(cfg, tl, Hc, stepx, stepy, bx0, by0, interior, area_ok);
+        source_box<C, TW, K, NT>(cfg, tl, Hc, stepx, stepy, bx0, by0, interior, area_ok);
         if (tid == 0) {
             ti->bx0 = bx0; ti->by0 = by0; ti->interior = interior;
-            tma::mbar_expect_tx(bar, (uint32_t)(G::SBH * G::SBW * C * sizeof(float)));     // release: publishes ti
+            tma::mbar_expect_tx(bar, (uint32_t)(G::kBoxF * sizeof(float)));     // release: publishes ti
             tma::load_3d(s_src, &mapU, bar, bx0 * C, by0, tl.n);
         }
     }
@@ -220,11 +224,11 @@ warp_fwd_tma_kernel(const __grid_constant__ CUtensorMap mapU, const __grid_const
 #pragma unroll
         for (int k = 0; k < K; ++k) {
             const FastTaps t = make_taps_interior(xn[k], yn[k], cfg.H, cfg.W);
-            const float* pa = s_src + ((t.y0 - by0) * G::SBW + (t.x0 - bx0)) * C;
+            const float* pa = s_src + ((t.y0 - by0) * G::kRowF + (t.x0 - bx0) * C);
             float* o = s_out + ((g * K + k) * TW + tx) * C;
 #pragma unroll
             for (int ch = 0; ch < C; ++ch)
-                o[ch] = blend4(t.ax, t.bx, t.ay, t.by, pa[ch], pa[G::SBW * C + ch], pa[C + ch], pa[G::SBW * C + C + ch]);
+                o[ch] = blend4(t.ax, t.bx, t.ay, t.by, pa[ch], pa[G::kRowF + ch], pa[C + ch], pa[G::kRowF + C + ch]);
         }
     } else {
         const float* Un = U + (size_t)tl.n * cfg.H * cfg.W * C;
@@ -234,10 +238,10 @@ warp_fwd_tma_kernel(const __grid_constant__ CUtensorMap mapU, const __grid_const
             const int sx0 = t.x0 - bx0, sx1 = t.x1 - bx0, sy0 = t.y0 - by0, sy1 = t.y1 - by0;
             float* o = s_out + ((g * K + k) * TW + tx) * C;
             if (sx0 >= 0 && sx1 < G::SBW && sy0 >= 0 && sy1 < G::SBH) {
-                const float* pa = s_src + (sy0 * G::SBW + sx0) * C;
-                const float* pb = s_src + (sy1 * G::SBW + sx0) * C;
-                const float* pc = s_src + (sy0 * G::SBW + sx1) * C;
-                const float* pd = s_src + (sy1 * G::SBW + sx1) * C;
+                const float* pa = s_src + sy0 * G::kRowF + sx0 * C;
+                const float* pb = s_src + sy1 * G::kRowF + sx0 * C;
+                const float* pc = s_src + sy0 * G::kRowF + sx1 * C;
+                const float* pd = s_src + sy1 * G::kRowF + sx1 * C;
 #pragma unroll
                 for (int ch = 0; ch < C; ++ch) o[ch] = blend(t, pa[ch], pb[ch], pc[ch], pd[ch]);
             } else {
@@ -271,20 +275,20 @@ __device__ __forceinline__ void accumulate_dh(float (&dh)[8], float gxn, float g
     dh[6] = fmaf(dzs, xt, dh[6]); dh[7] = fmaf(dzs, yt, dh[7]);
 }
 
-template <int C, int TW, int K>
-__global__ void __launch_bounds__(kThreads, 3)
+template <int C, int TW, int K, int NT>
+__global__ void __launch_bounds__(NT, NT == 256 ? 3 : 2)
 warp_bwd_tma_kernel(const __grid_constant__ CUtensorMap mapU, const __grid_constant__ CUtensorMap mapDU,
                     const float* __restrict__ U, const float* __restrict__ Hs, const float* __restrict__ d_out,
                     const float* __restrict__ d_img, const __grid_constant__ TileCfg cfg, float* __restrict__ dU,
                     float* __restrict__ parts)
 {
-    using G = Geo<C, TW, K>;
+    using G = Geo<C, TW, K, NT>;
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     float* s_src = reinterpret_cast<float*>(smem_raw);
-    float* s_red = s_src + G::kBoxF;                                   // [8 warps][8] dH partials
-    uint64_t* bar = reinterpret_cast<uint64_t*>(s_red + 64);
+    float* s_red = s_src + G::kBoxF;                                   // [warps][8] dH partials (<= 128 floats)
+    uint64_t* bar = reinterpret_cast<uint64_t*>(s_red + 128);
     TileInfo* ti = reinterpret_cast<TileInfo*>(bar + 2);
-    int* s_acc = reinterpret_cast<int*>(s_red + 128);                  // fixed-point dU box (only when dU != nullptr)
+    int* s_acc = reinterpret_cast<int*>(s_red + 256);                  // fixed-point dU box (only when dU != nullptr)
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid == 0) {
@@ -317,15 +321,15 @@ warp_bwd_tma_kernel(const __grid_constant__ CUtensorMap mapU, const __grid_const
     }
     if (dU) {
         int4* a4 = reinterpret_cast<int4*>(s_acc);
-        for (int i = tid; i < G::kBoxF / 4; i += kThreads) a4[i] = make_int4(0, 0, 0, 0);
+        for (int i = tid; i < G::kBoxF / 4; i += NT) a4[i] = make_int4(0, 0, 0, 0);
     }
     __syncthreads();                                  // barrier initialised
     if (tid < 32) {
         int bx0, by0, interior, area_ok;
-        source_box<C, TW, K>(cfg, tl, Hc, stepx, stepy, bx0, by0, interior, area_ok);
+        source_box<C, TW, K, NT>(cfg, tl, Hc, stepx, stepy, bx0, by0, interior, area_ok);
         if (tid == 0) {
             ti->bx0 = bx0; ti->by0 = by0; ti->interior = interior; ti->area_ok = area_ok;
-            tma::mbar_expect_tx(bar, (uint32_t)(G::SBH * G::SBW * C * sizeof(float)));
+            tma::mbar_expect_tx(bar, (uint32_t)(G::kBoxF * sizeof(float)));
             tma::load_3d(s_src, &mapU, bar, bx0 * C, by0, tl.n);
         }
     }
@@ -353,7 +357,7 @@ warp_bwd_tma_kernel(const __grid_constant__ CUtensorMap mapU, const __grid_const
     if (dU) {
         float mm = 0.0f;
 #pragma unroll
-        for (int w = 0; w < kThreads / 32; ++w) mm = fmaxf(mm, ti->wmax[w]);
+        for (int w = 0; w < NT / 32; ++w) mm = fmaxf(mm, ti->wmax[w]);
         const int e = ((__float_as_int(mm) >> 23) & 0xff) - 127;            // floor(log2 mm) for normal mm
         // quantum = 2^-23 of the tile's max|d_out| (tap weights are in [0,1] on this path), 8 bits of headroom = up to
         // 256 coincident full-size taps per word; tiles magnified beyond ~4x4 (area test) take the fp32 path instead
@@ -383,7 +387,7 @@ warp_bwd_tma_kernel(const __grid_constant__ CUtensorMap mapU, const __grid_const
                 zs = __fadd_rn(zs, (zs >= 0.0f) ? 1e-8f : -1e-8f);
                 const float xn = __fdiv_rn(xs, zs), yn = __fdiv_rn(ys, zs);
                 const FastTaps t = make_taps_interior(xn, yn, cfg.H, cfg.W);
-                const int ia = ((t.y0 - by0) * G::SBW + (t.x0 - bx0)) * C;
+                const int ia = ((t.y0 - by0) * G::kRowF + (t.x0 - bx0) * C);
                 const float* pa = s_src + ia;
                 int* qa = s_acc + ia;
                 const float wa = t.ax * t.ay, wb = t.ax * t.by, wc = t.bx * t.ay, wd = t.bx * t.by;
@@ -391,15 +395,15 @@ warp_bwd_tma_kernel(const __grid_constant__ CUtensorMap mapU, const __grid_const
 #pragma unroll
                 for (int ch = 0; ch < C; ++ch) {
                     const float gch = gout[k][ch];
-                    const float Ia = pa[ch], Ib = pa[G::SBW * C + ch], Ic = pa[C + ch], Id = pa[G::SBW * C + C + ch];
+                    const float Ia = pa[ch], Ib = pa[G::kRowF + ch], Ic = pa[C + ch], Id = pa[G::kRowF + C + ch];
                     gx = fmaf(gch, fmaf(Ic - Ia, t.ay, (Id - Ib) * t.by), gx);
                     gy = fmaf(gch, fmaf(Ib - Ia, t.ax, (Id - Ic) * t.bx), gy);
                     if (dU) {
                         const float gs = gch * scale;
                         atomicAdd(qa + ch, __float2int_rn(wa * gs));
-                        atomicAdd(qa + G::SBW * C + ch, __float2int_rn(wb * gs));
+                        atomicAdd(qa + G::kRowF + ch, __float2int_rn(wb * gs));
                         atomicAdd(qa + C + ch, __float2int_rn(wc * gs));
-                        atomicAdd(qa + G::SBW * C + C + ch, __float2int_rn(wd * gs));
+                        atomicAdd(qa + G::kRowF + C + ch, __float2int_rn(wd * gs));
                     }
                 }
                 accumulate_dh(dh, fmaf(gx, halfW, gimg[k][0]), fmaf(gy, halfH, gimg[k][1]), xn, yn, zs, xt, yt);
@@ -426,8 +430,8 @@ warp_bwd_tma_kernel(const __grid_constant__ CUtensorMap mapU, const __grid_const
                 const bool scatter = (dU != nullptr) && taps_scatter(t);
                 const size_t ga = ((size_t)t.y0 * cfg.W + t.x0) * C, gb = ((size_t)t.y1 * cfg.W + t.x0) * C;
                 const size_t gc = ((size_t)t.y0 * cfg.W + t.x1) * C, gd = ((size_t)t.y1 * cfg.W + t.x1) * C;
-                const int ia = (sy0 * G::SBW + sx0) * C, ib = (sy1 * G::SBW + sx0) * C;
-                const int ic = (sy0 * G::SBW + sx1) * C, id = (sy1 * G::SBW + sx1) * C;
+                const int ia = sy0 * G::kRowF + sx0 * C, ib = sy1 * G::kRowF + sx0 * C;
+                const int ic = sy0 * G::kRowF + sx1 * C, id = sy1 * G::kRowF + sx1 * C;
 #pragma unroll
                 for (int ch = 0; ch < C; ++ch) {
                     const float gch = gout[k][ch];
@@ -465,13 +469,13 @@ warp_bwd_tma_kernel(const __grid_constant__ CUtensorMap mapU, const __grid_const
     if (tid < 8) {
         float v = 0.0f;
 #pragma unroll
-        for (int w = 0; w < kThreads / 32; ++w) v += s_red[w * 8 + tid];
+        for (int w = 0; w < NT / 32; ++w) v += s_red[w * 8 + tid];
         parts[((size_t)tl.cell * (cfg.parts_y * cfg.parts_x) + tl.part) * 8 + tid] = v;
     }
     if (fixed) {
         // fixed point -> fp32 in place, then ONE TMA reduce-add of the whole box into dU
         int4* a4 = reinterpret_cast<int4*>(s_acc);
-        for (int i = tid; i < G::kBoxF / 4; i += kThreads) {
+        for (int i = tid; i < G::kBoxF / 4; i += NT) {
             const int4 v = a4[i];
             reinterpret_cast<float4*>(s_acc)[i] = make_float4((float)v.x * inv_scale, (float)v.y * inv_scale,
                                                               (float)v.z * inv_scale, (float)v.w * inv_scale);
@@ -543,11 +547,12 @@ static int fill_axis(AxisTab* tab, int ncell, int cell_px, int total, int T, int
 
 struct Plan {
     TileCfg cfg;
-    int TW, K, TH, nty, ntx;
+    int TW, K, NT, TH, nty, ntx;
 };
 
-// compiled (TW, K) variants: TH = K * 256/TW
-static const int kVariants[][2] = {{64, 6}, {64, 3}, {32, 3}, {32, 2}, {32, 1}};
+// compiled (TW, K, threads) variants: TH = K * threads/TW
+constexpr int kNumVariants = 6;
+static const int kVariants[kNumVariants][3] = {{64, 6, 256}, {64, 3, 512}, {64, 3, 256}, {32, 3, 256}, {32, 2, 256}, {32, 1, 256}};
 
 // Picks the tiling for a shape; false if the TMA path cannot serve it (the generic kernels then do).
 static bool plan(const WarpShape& s, Plan* out)
@@ -561,8 +566,8 @@ static bool plan(const WarpShape& s, Plan* out)
     if (s.W % 4 != 0 || cell_w % 4 != 0) return false;
     double best_eff = 0;
     int best = -1;
-    for (int v = 0; v < 5; ++v) {
-        const int tw = kVariants[v][0], k = kVariants[v][1], th = (kThreads / tw) * k;
+    for (int v = 0; v < kNumVariants; ++v) {
+        const int tw = kVariants[v][0], k = kVariants[v][1], th = (kVariants[v][2] / tw) * k;
         if (tw > cell_w || th > cell_h) continue;
         if (s.C == 4 && tw == 64) continue;                      // 64 px x 4 ch leaves no room for a halo in a 256-element box
         const double ey = (double)cell_h / (((cell_h + th - 1) / th) * th), ex = (double)cell_w / (((cell_w + tw - 1) / tw) * tw);
@@ -570,14 +575,15 @@ static bool plan(const WarpShape& s, Plan* out)
         if (eff > best_eff) { best_eff = eff; best = v; }
     }
     if (const char* force = getenv("MGW_TILE")) {                  // tuning aid: MGW_TILE=64x3 forces a compiled variant if it fits
-        int tw = 0, k = 0;
-        if (sscanf(force, "%dx%d", &tw, &k) == 2)
-            for (int v = 0; v < 5; ++v)
-                if (kVariants[v][0] == tw && kVariants[v][1] == k && tw <= cell_w && (kThreads / tw) * k <= cell_h && !(s.C == 4 && tw == 64)) best = v;
+        int tw = 0, k = 0, nt = 256;
+        if (sscanf(force, "%dx%dx%d", &tw, &k, &nt) >= 2)
+            for (int v = 0; v < kNumVariants; ++v)
+                if (kVariants[v][0] == tw && kVariants[v][1] == k && kVariants[v][2] == nt && tw <= cell_w && (nt / tw) * k <= cell_h &&
+                    !(s.C == 4 && tw == 64)) best = v;
     }
     if (best < 0) return false;
     Plan p;
-    p.TW = kVariants[best][0]; p.K = kVariants[best][1]; p.TH = (kThreads / p.TW) * p.K;
+    p.TW = kVariants[best][0]; p.K = kVariants[best][1]; p.NT = kVariants[best][2]; p.TH = (p.NT / p.TW) * p.K;
     TileCfg& c = p.cfg;
     c.N = s.N; c.H = s.H; c.W = s.W; c.gh = s.gh; c.gw = s.gw;
     p.nty = fill_axis(&c.rows, s.gh, cell_h, s.H, p.TH, &c.parts_y);
@@ -610,46 +616,47 @@ static int allow_smem(KernelT kernel, bool* done_for_device, const char* what)
     return MGW_OK;
 }
 
-template <int C, int TW, int K>
+template <int C, int TW, int K, int NT>
 static int launch_fwd_v(const float* U, const float* Hs, const Plan& p, float* out, float* black, float* img, cudaStream_t st)
 {
-    using G = Geo<C, TW, K>;
+    using G = Geo<C, TW, K, NT>;
     const TileCfg& c = p.cfg;
     CUtensorMap mU, mOut;
-    TRY_RC(make_map(&mU, U, c.W * C, c.H, c.N, G::SBW * C, G::SBH));
+    TRY_RC(make_map(&mU, U, c.W * C, c.H, c.N, G::kRowF, G::SBH));
     TRY_RC(make_map(&mOut, out ? out : U, c.W * C, c.H, c.N, TW * C, G::TH));
     const size_t smem = (size_t)(G::kBoxF + G::kOutF) * 4 + 16 + sizeof(TileInfo) + 64;
     static bool attr[64] = {};
-    TRY_RC(allow_smem(warp_fwd_tma_kernel<C, TW, K>, attr, "warp_fwd_tma"));
-    warp_fwd_tma_kernel<C, TW, K><<<dim3(p.ntx, p.nty, c.N), kThreads, smem, st>>>(mU, mOut, U, Hs, c, out, img, black);
+    TRY_RC(allow_smem(warp_fwd_tma_kernel<C, TW, K, NT>, attr, "warp_fwd_tma"));
+    warp_fwd_tma_kernel<C, TW, K, NT><<<dim3(p.ntx, p.nty, c.N), NT, smem, st>>>(mU, mOut, U, Hs, c, out, img, black);
     return check_launch("warp_fwd_tma");
 }
 
-template <int C, int TW, int K>
+template <int C, int TW, int K, int NT>
 static int launch_bwd_v(const float* U, const float* Hs, const float* d_out, const float* d_img, const Plan& p, float* dU,
                         float* parts, cudaStream_t st)
 {
-    using G = Geo<C, TW, K>;
+    using G = Geo<C, TW, K, NT>;
     const TileCfg& c = p.cfg;
     CUtensorMap mU, mDU;
-    TRY_RC(make_map(&mU, U, c.W * C, c.H, c.N, G::SBW * C, G::SBH));
-    if (dU) TRY_RC(make_map(&mDU, dU, c.W * C, c.H, c.N, G::SBW * C, G::SBH)); else mDU = mU;
-    const size_t smem = (size_t)(G::kBoxF + 128 + (dU ? G::kBoxF : 0)) * 4 + 64;
+    TRY_RC(make_map(&mU, U, c.W * C, c.H, c.N, G::kRowF, G::SBH));
+    if (dU) TRY_RC(make_map(&mDU, dU, c.W * C, c.H, c.N, G::kRowF, G::SBH)); else mDU = mU;
+    const size_t smem = (size_t)(G::kBoxF + 256 + (dU ? G::kBoxF : 0)) * 4 + 64;
     static bool attr[64] = {};
-    TRY_RC(allow_smem(warp_bwd_tma_kernel<C, TW, K>, attr, "warp_bwd_tma"));
-    warp_bwd_tma_kernel<C, TW, K><<<dim3(p.ntx, p.nty, c.N), kThreads, smem, st>>>(mU, mDU, U, Hs, d_out, d_img, c, dU, parts);
+    TRY_RC(allow_smem(warp_bwd_tma_kernel<C, TW, K, NT>, attr, "warp_bwd_tma"));
+    warp_bwd_tma_kernel<C, TW, K, NT><<<dim3(p.ntx, p.nty, c.N), NT, smem, st>>>(mU, mDU, U, Hs, d_out, d_img, c, dU, parts);
     return check_launch("warp_bwd_tma");
 }
 
 template <int C>
 static int launch_fwd_c(const Plan& p, const float* U, const float* Hs, float* out, float* black, float* img, cudaStream_t st)
 {
-    if (p.TW == 32 && p.K == 3) return launch_fwd_v<C, 32, 3>(U, Hs, p, out, black, img, st);
-    if (p.TW == 32 && p.K == 2) return launch_fwd_v<C, 32, 2>(U, Hs, p, out, black, img, st);
-    if (p.TW == 32 && p.K == 1) return launch_fwd_v<C, 32, 1>(U, Hs, p, out, black, img, st);
+    if (p.NT == 256 && p.TW == 32 && p.K == 3) return launch_fwd_v<C, 32, 3, 256>(U, Hs, p, out, black, img, st);
+    if (p.NT == 256 && p.TW == 32 && p.K == 2) return launch_fwd_v<C, 32, 2, 256>(U, Hs, p, out, black, img, st);
+    if (p.NT == 256 && p.TW == 32 && p.K == 1) return launch_fwd_v<C, 32, 1, 256>(U, Hs, p, out, black, img, st);
     if constexpr (C != 4) {
-        if (p.TW == 64 && p.K == 6) return launch_fwd_v<C, 64, 6>(U, Hs, p, out, black, img, st);
-        if (p.TW == 64 && p.K == 3) return launch_fwd_v<C, 64, 3>(U, Hs, p, out, black, img, st);
+        if (p.NT == 256 && p.TW == 64 && p.K == 6) return launch_fwd_v<C, 64, 6, 256>(U, Hs, p, out, black, img, st);
+        if (p.NT == 512 && p.TW == 64 && p.K == 3) return launch_fwd_v<C, 64, 3, 512>(U, Hs, p, out, black, img, st);
+        if (p.NT == 256 && p.TW == 64 && p.K == 3) return launch_fwd_v<C, 64, 3, 256>(U, Hs, p, out, black, img, st);
     }
     return set_error(MGW_ERR_UNSUPPORTED, "warp_fwd_tma: no tile variant");
 }
@@ -658,12 +665,13 @@ template <int C>
 static int launch_bwd_c(const Plan& p, const float* U, const float* Hs, const float* d_out, const float* d_img, float* dU,
                         float* parts, cudaStream_t st)
 {
-    if (p.TW == 32 && p.K == 3) return launch_bwd_v<C, 32, 3>(U, Hs, d_out, d_img, p, dU, parts, st);
-    if (p.TW == 32 && p.K == 2) return launch_bwd_v<C, 32, 2>(U, Hs, d_out, d_img, p, dU, parts, st);
-    if (p.TW == 32 && p.K == 1) return launch_bwd_v<C, 32, 1>(U, Hs, d_out, d_img, p, dU, parts, st);
+    if (p.NT == 256 && p.TW == 32 && p.K == 3) return launch_bwd_v<C, 32, 3, 256>(U, Hs, d_out, d_img, p, dU, parts, st);
+    if (p.NT == 256 && p.TW == 32 && p.K == 2) return launch_bwd_v<C, 32, 2, 256>(U, Hs, d_out, d_img, p, dU, parts, st);
+    if (p.NT == 256 && p.TW == 32 && p.K == 1) return launch_bwd_v<C, 32, 1, 256>(U, Hs, d_out, d_img, p, dU, parts, st);
     if constexpr (C != 4) {
-        if (p.TW == 64 && p.K == 6) return launch_bwd_v<C, 64, 6>(U, Hs, d_out, d_img, p, dU, parts, st);
-        if (p.TW == 64 && p.K == 3) return launch_bwd_v<C, 64, 3>(U, Hs, d_out, d_img, p, dU, parts, st);
+        if (p.NT == 256 && p.TW == 64 && p.K == 6) return launch_bwd_v<C, 64, 6, 256>(U, Hs, d_out, d_img, p, dU, parts, st);
+        if (p.NT == 512 && p.TW == 64 && p.K == 3) return launch_bwd_v<C, 64, 3, 512>(U, Hs, d_out, d_img, p, dU, parts, st);
+        if (p.NT == 256 && p.TW == 64 && p.K == 3) return launch_bwd_v<C, 64, 3, 256>(U, Hs, d_out, d_img, p, dU, parts, st);
     }
     return set_error(MGW_ERR_UNSUPPORTED, "warp_bwd_tma: no tile variant");
 }
