@@ -4,9 +4,9 @@
 //   solve_h_fwd : get_Hs/get_H/pinv, spatial_transformer3.py:144-198  (h = inverse(A + 1e-4 I) . b)
 //   solve_h_bwd : closed-form adjoint of the above, fp64 inside
 //
-// Work is tiny (N*gh*gw cells, 512 for config #2) and latency-bound, so a cell is solved by an 8-lane
-// group (lane = matrix row for the LU, lane = inverse column for the substitutions), four cells per warp,
-// with the LU/inverse exchanged through a few hundred bytes of shared memory.  The operation order is
+// Work is tiny (N*gh*gw cells, 512 for config #2) and latency-bound: one thread per cell, the 8x8 system in
+// registers (no shuffles, no shared memory in the solve itself).  The operation order is
+
 // exactly oracle/mgw_oracle.c's ORC_SOLVE, so Hs is bit-identical to the C oracle's.
 #include "mgw_internal.h"
 
@@ -78,58 +78,68 @@ template <> __device__ __forceinline__ float tfma<float>(float a, float b, float
 template <> __device__ __forceinline__ double tfma<double>(double a, double b, double c) { return fma(a, b, c); }
 template <typename T> __device__ __forceinline__ T tabs(T a) { return a < 0 ? -a : a; }
 
-// In-group (8 lanes) LU with partial pivoting of the row-distributed matrix `row` (lane g holds row g).
-// Mirrors ORC_SOLVE: first-max pivot, reciprocal scaling, fma updates.  piv[] is group-uniform.
+// 8x8 LU with partial pivoting held entirely in one thread's registers (every index is a compile-time constant after
+// unrolling; the data-dependent row swap is a predicated exchange).  Mirrors ORC_SOLVE of oracle/mgw_oracle.c: first
+// maximum wins the pivot search, the column is scaled by the reciprocal of the pivot, updates are fused multiply-adds.
+// One thread per cell beats a shuffle-cooperative 8-lane version by ~3x here: the work is a latency chain, and a
+// register move costs 4 cycles where a shuffle costs ~25.
 template <typename T>
-__device__ __forceinline__ void group_lu(T (&row)[8], int (&piv)[8], int g)
+__device__ __forceinline__ void lu8(T (&M)[8][8], int (&piv)[8])
 {
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
-        T best = (g >= k) ? tabs(row[k]) : (T)-1;
-        int p = g;
+        int p = k;
+        T best = tabs(M[k][k]);
 #pragma unroll
-        for (int o = 4; o > 0; o >>= 1) {
-            const T ob = __shfl_xor_sync(0xffffffffu, best, o, 8);
-            const int op = __shfl_xor_sync(0xffffffffu, p, o, 8);
-            if (ob > best || (ob == best && op < p)) { best = ob; p = op; }
+        for (int r = k + 1; r < 8; ++r) {
+            const T a = tabs(M[r][k]);
+            if (a > best) { best = a; p = r; }
         }
         piv[k] = p;
-        const int src = (g == k) ? p : ((g == p) ? k : g);
-        T pr[8];
 #pragma unroll
-        for (int c = 0; c < 8; ++c) {
-            row[c] = __shfl_sync(0xffffffffu, row[c], src, 8);
-            pr[c] = __shfl_sync(0xffffffffu, row[c], k, 8);
+        for (int r = k + 1; r < 8; ++r) {               // branch-free exchange keeps the matrix in registers
+            const bool sw = (p == r);
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                const T a = M[k][c], b = M[r][c];
+                M[k][c] = sw ? b : a;
+                M[r][c] = sw ? a : b;
+            }
         }
-        const T rp = (T)1 / pr[k];
-        if (g > k) {
-            const T l = row[k] * rp;
-            row[k] = l;
+        const T rp = (T)1 / M[k][k];
 #pragma unroll
-            for (int c = k + 1; c < 8; ++c) row[c] = tfma<T>(-l, pr[c], row[c]);
+        for (int r = k + 1; r < 8; ++r) {
+            const T l = M[r][k] * rp;
+            M[r][k] = l;
+#pragma unroll
+            for (int c = k + 1; c < 8; ++c) M[r][c] = tfma<T>(-l, M[k][c], M[r][c]);
         }
     }
 }
 
-// Solve LU x = P e (getrs): lane g owns one right-hand side `col`; LU is read from shared memory.
+// Solve LU x = P rhs in place (LAPACK getrs): row interchanges, unit-lower forward substitution, back substitution.
 template <typename T>
-__device__ __forceinline__ void group_getrs(const T* __restrict__ LU, const int (&piv)[8], T (&col)[8])
+__device__ __forceinline__ void getrs8(const T (&LU)[8][8], const int (&piv)[8], T (&col)[8])
 {
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
 #pragma unroll
-        for (int r = k + 1; r < 8; ++r)
-            if (piv[k] == r) { const T t = col[k]; col[k] = col[r]; col[r] = t; }
+        for (int r = k + 1; r < 8; ++r) {
+            const bool sw = (piv[k] == r);
+            const T a = col[k], b = col[r];
+            col[k] = sw ? b : a;
+            col[r] = sw ? a : b;
+        }
     }
 #pragma unroll
     for (int r = 1; r < 8; ++r)
 #pragma unroll
-        for (int k = 0; k < r; ++k) col[r] = tfma<T>(-LU[r * 8 + k], col[k], col[r]);
+        for (int k = 0; k < r; ++k) col[r] = tfma<T>(-LU[r][k], col[k], col[r]);
 #pragma unroll
     for (int r = 7; r >= 0; --r) {
 #pragma unroll
-        for (int k = r + 1; k < 8; ++k) col[r] = tfma<T>(-LU[r * 8 + k], col[k], col[r]);
-        col[r] = col[r] / LU[r * 8 + r];
+        for (int k = r + 1; k < 8; ++k) col[r] = tfma<T>(-LU[r][k], col[k], col[r]);
+        col[r] = col[r] / LU[r][r];
     }
 }
 
@@ -152,105 +162,79 @@ __device__ __forceinline__ void dlt_row(const float* __restrict__ theta_n, int i
     b = t;
 }
 
-constexpr int kCellsPerBlock = 16;      // 128 threads
-
-__global__ void __launch_bounds__(kCellsPerBlock * 8)
+__global__ void __launch_bounds__(32)
 solve_h_fwd_kernel(const float* __restrict__ theta, int N, int gh, int gw, float* __restrict__ Hs)
 {
-    __shared__ float sLU[kCellsPerBlock][64];
-    __shared__ float sINV[kCellsPerBlock][64];
-    const int slot = threadIdx.x >> 3, g = threadIdx.x & 7;
-    const int ncell = N * gh * gw;
-    int cell = blockIdx.x * kCellsPerBlock + slot;
-    const bool live = cell < ncell;
-    if (!live) cell = ncell - 1;                       // keep the whole warp converged for the shuffles
+    const int cell = blockIdx.x * blockDim.x + threadIdx.x;
+    if (cell >= N * gh * gw) return;
     const int n = cell / (gh * gw), ij = cell % (gh * gw), i = ij / gw, j = ij % gw;
     const float* theta_n = theta + (size_t)n * (gh + 1) * (gw + 1) * 2;
-
-    float row[8], b; int piv[8];
-    dlt_row<float>(theta_n, i, j, gh, gw, g, row, b);
-    group_lu<float>(row, piv, g);
+    float M[8][8], b[8];
+    int piv[8];
 #pragma unroll
-    for (int c = 0; c < 8; ++c) sLU[slot][g * 8 + c] = row[c];
-    __syncwarp();
-    float col[8];
+    for (int r = 0; r < 8; ++r) dlt_row<float>(theta_n, i, j, gh, gw, r, M[r], b[r]);
+    lu8<float>(M, piv);
+    // h = inverse(M) . b with the inverse formed column by column (getrs on the identity) and consumed at once:
+    // h[r] = inv[r][0]*b[0], then fma(inv[r][k], b[k], h[r]) for k = 1..7 -- the FMA chain of matmul(pinv(A), b)
+    // (spatial_transformer3.py:173), so the explicit inverse never has to be stored
+    float h[8];
 #pragma unroll
-    for (int r = 0; r < 8; ++r) col[r] = (r == g) ? 1.0f : 0.0f;
-    group_getrs<float>(sLU[slot], piv, col);
+    for (int c = 0; c < 8; ++c) {
+        float col[8];
 #pragma unroll
-    for (int r = 0; r < 8; ++r) sINV[slot][r * 8 + g] = col[r];
-    __syncwarp();
-    // matmul(pinv(A), b): FMA chain over k (spatial_transformer3.py:173)
-    float acc = __fmul_rn(sINV[slot][g * 8], __shfl_sync(0xffffffffu, b, 0, 8));
+        for (int r = 0; r < 8; ++r) col[r] = (r == c) ? 1.0f : 0.0f;
+        getrs8<float>(M, piv, col);
 #pragma unroll
-    for (int k = 1; k < 8; ++k) acc = __fmaf_rn(sINV[slot][g * 8 + k], __shfl_sync(0xffffffffu, b, k, 8), acc);
-    if (live) {
-        Hs[(size_t)cell * 9 + g] = acc;
-        if (g == 0) Hs[(size_t)cell * 9 + 8] = 1.0f;
+        for (int r = 0; r < 8; ++r) h[r] = (c == 0) ? __fmul_rn(col[r], b[0]) : __fmaf_rn(col[r], b[c], h[r]);
     }
+#pragma unroll
+    for (int r = 0; r < 8; ++r) Hs[(size_t)cell * 9 + r] = h[r];
+    Hs[(size_t)cell * 9 + 8] = 1.0f;
 }
 
 // ---------------------------------------------------------------- K4: adjoint of the solve
-// dHs_part [N*gh*gw, nparts, 8] tile partials (nparts may be 1) -> dtheta [N,gh+1,gw+1,2].
-// Per cell (8-lane group, fp64): g = sum of partials, lambda = (A+1e-4 I)^-T g,
-// d u_k = lambda_k * s_k, d v_k = lambda_{4+k} * s_k, s_k = 1 + h6 x_k + h7 y_k; then each vertex gathers its
-// (up to) four cells in a fixed order -> deterministic, no atomics.  One block per sample.
+// dHs_part [N*gh*gw, nparts, part_stride] tile partials (nparts may be 1) -> dtheta [N,gh+1,gw+1,2].
+// One thread per cell, fp64: g = sum of the partials, lambda = (A+1e-4 I)^-T g by a fresh pivoted LU of the transposed
+// system, d u_k = lambda_k * s_k, d v_k = lambda_{4+k} * s_k with s_k = 1 + h6 x_k + h7 y_k; then
+// each vertex gathers its (up to) four cells in a fixed order -> deterministic, no atomics.  One block per sample.
 __global__ void solve_h_bwd_kernel(const float* __restrict__ theta, const float* __restrict__ Hs,
                                    const float* __restrict__ dHs_part, int nparts, int part_stride,
                                    int N, int gh, int gw, float* __restrict__ dtheta)
 {
-    extern __shared__ double sm[];
+    extern __shared__ double sDuv[];                   // [gh*gw][8]  (du0..3, dv0..3)
     const int ncell_s = gh * gw;
-    double* sLU = sm;                                  // [ncell_s][64]
-    double* sDuv = sm + (size_t)ncell_s * 64;          // [ncell_s][8]  (du0..3, dv0..3)
     const int n = blockIdx.x;
-    const int g = threadIdx.x & 7;
     const float* theta_n = theta + (size_t)n * (gh + 1) * (gw + 1) * 2;
-
-    for (int base = 0; base < ncell_s; base += blockDim.x >> 3) {
-        int ij = base + (threadIdx.x >> 3);
-        const bool live = ij < ncell_s;
-        if (!live) ij = ncell_s - 1;
+    for (int ij = threadIdx.x; ij < ncell_s; ij += blockDim.x) {
         const int i = ij / gw, j = ij % gw;
         const size_t cell = (size_t)n * ncell_s + ij;
-        // transpose system: lane g holds row g of M^T = column g of M
-        double mrow[8], bdummy, trow[8];
-#pragma unroll
-        for (int r = 0; r < 8; ++r) {
-            double tmp[8];
-            dlt_row<double>(theta_n, i, j, gh, gw, r, tmp, bdummy);
-            double pick = 0;
-#pragma unroll
-            for (int c = 0; c < 8; ++c) if (c == g) pick = tmp[c];
-            trow[r] = pick;
-        }
-#pragma unroll
-        for (int c = 0; c < 8; ++c) mrow[c] = trow[c];
+        double Mt[8][8], rhs[8];
         int piv[8];
-        group_lu<double>(mrow, piv, g);
-        double* LU = sLU + (size_t)ij * 64;
-        if (live) {
-#pragma unroll
-            for (int c = 0; c < 8; ++c) LU[g * 8 + c] = mrow[c];
-        }
-        __syncwarp();
-        // right-hand side: the summed dH[0:8] of this cell (every lane builds the full vector)
-        double rhs[8];
 #pragma unroll
         for (int r = 0; r < 8; ++r) {
-            double s = 0;
-            for (int p = 0; p < nparts; ++p) s += (double)dHs_part[(cell * nparts + p) * part_stride + r];
-            rhs[r] = s;
-        }
-        if (live) group_getrs<double>(LU, piv, rhs);    // rhs -> lambda (all lanes compute the same thing)
-        const double h6 = Hs[cell * 9 + 6], h7 = Hs[cell * 9 + 7];
-        float xf, yf; int vid;
-        cell_corner(i, j, gh, gw, g & 3, xf, yf, vid);
-        const double s = 1.0 + h6 * (double)xf + h7 * (double)yf;
-        double lam = 0;
+            double row[8], bdummy;
+            dlt_row<double>(theta_n, i, j, gh, gw, r, row, bdummy);
 #pragma unroll
-        for (int r = 0; r < 8; ++r) if (r == g) lam = rhs[r];
-        if (live) sDuv[(size_t)ij * 8 + g] = lam * s;
+            for (int c = 0; c < 8; ++c) Mt[c][r] = row[c];
+        }
+#pragma unroll
+        for (int r = 0; r < 8; ++r) rhs[r] = 0;
+        for (int p = 0; p < nparts; ++p) {
+            const float* src = dHs_part + (cell * nparts + p) * part_stride;
+#pragma unroll
+            for (int r = 0; r < 8; ++r) rhs[r] += (double)__ldg(src + r);
+        }
+        lu8<double>(Mt, piv);
+        getrs8<double>(Mt, piv, rhs);                  // rhs -> lambda
+        const double h6 = Hs[cell * 9 + 6], h7 = Hs[cell * 9 + 7];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            float xf, yf; int vid;
+            cell_corner(i, j, gh, gw, k, xf, yf, vid);
+            const double s = 1.0 + h6 * (double)xf + h7 * (double)yf;
+            sDuv[(size_t)ij * 8 + k] = rhs[k] * s;
+            sDuv[(size_t)ij * 8 + 4 + k] = rhs[4 + k] * s;
+        }
     }
     __syncthreads();
     const int nv2 = (gh + 1) * (gw + 1) * 2;
@@ -286,7 +270,7 @@ int launch_vertices_bwd(const float* head, const float* d_pts2, const float* d_p
 int launch_solve_h_fwd(const float* theta, int N, int gh, int gw, float* Hs, cudaStream_t st)
 {
     const int ncell = N * gh * gw;
-    solve_h_fwd_kernel<<<(ncell + kCellsPerBlock - 1) / kCellsPerBlock, kCellsPerBlock * 8, 0, st>>>(theta, N, gh, gw, Hs);
+    solve_h_fwd_kernel<<<(ncell + 31) / 32, 32, 0, st>>>(theta, N, gh, gw, Hs);
     return check_launch("solve_h_fwd");
 }
 
@@ -294,10 +278,10 @@ int launch_solve_h_bwd(const float* theta, const float* Hs, const float* dHs_par
                        int N, int gh, int gw, float* dtheta, cudaStream_t st)
 {
     const int ncell_s = gh * gw;
-    int threads = ((ncell_s * 8 + 31) / 32) * 32;
-    if (threads > 256) threads = 256;
-    const size_t smem = (size_t)ncell_s * (64 + 8) * sizeof(double);
-    if (smem > 48 * 1024) return set_error(MGW_ERR_UNSUPPORTED, "solve_h_bwd: grid too large (gh*gw > 85)");
+    int threads = ((ncell_s > (gh + 1) * (gw + 1) * 2 ? ncell_s : (gh + 1) * (gw + 1) * 2) + 31) / 32 * 32;
+    if (threads > 128) threads = 128;
+    const size_t smem = (size_t)ncell_s * 8 * sizeof(double);
+    if (smem > 48 * 1024) return set_error(MGW_ERR_UNSUPPORTED, "solve_h_bwd: grid too large (gh*gw > 768)");
     solve_h_bwd_kernel<<<N, threads, smem, st>>>(theta, Hs, dHs_part, nparts, part_stride, N, gh, gw, dtheta);
     return check_launch("solve_h_bwd");
 }

@@ -11,7 +11,7 @@
 //             shared-memory box in FIXED POINT with native integer shared atomics (ATOMS.ADD, ~1 cycle per warp
 //             instruction measured on B200, against ~4-6 cycles and a serialising ~300-cycle round trip for the CAS
 //             loop behind atomicAdd(float*)); the scale is a power of two chosen per tile from max|d_out| so the
-//             quantum is 2^-23 of that maximum (fp32-grade) with 8 bits of headroom for coincident taps.  The box is
+//             quantum is 2^-22 of that maximum (fp32-grade) with 9 bits of headroom for coincident taps.  The box is
 //             converted back to fp32 and leaves by ONE TMA reduce-add (cp.reduce.async.bulk.tensor, UTMAREDG: L2
 //             atomics at line granularity).  The 8 dH terms are reduced warp-shuffle -> shared -> one deterministic
 //             partial per tile (no global atomics).
@@ -264,6 +264,17 @@ warp_fwd_tma_kernel(const __grid_constant__ CUtensorMap mapU, const __grid_const
 }
 
 // ------------------------------------------------------------------------------------------------ backward
+// float <-> fixed point without the conversion unit (F2I / I2F issue at a quarter rate on the XU pipe and there are 12
+// per pixel): adding 1.5*2^23 leaves round-to-nearest-even(v) in the low mantissa bits for |v| <= 2^22.
+constexpr float kMagic = 12582912.0f;          // 1.5 * 2^23
+constexpr int kMagicBits = 0x4B400000;
+__device__ __forceinline__ int fixed_of(float w, float gs) { return __float_as_int(__fmaf_rn(w, gs, kMagic)) - kMagicBits; }
+__device__ __forceinline__ float float_of_fixed(int v)
+{
+    // exact for |v| < 2^22; larger sums (many coincident taps) take the conversion instruction
+    return (abs(v) < (1 << 22)) ? __fsub_rn(__int_as_float(v + kMagicBits), kMagic) : (float)v;
+}
+
 // dH terms of one pixel accumulated into the thread's 8 partial sums
 __device__ __forceinline__ void accumulate_dh(float (&dh)[8], float gxn, float gyn, float xn, float yn, float zs, float xt, float yt)
 {
@@ -359,11 +370,12 @@ warp_bwd_tma_kernel(const __grid_constant__ CUtensorMap mapU, const __grid_const
 #pragma unroll
         for (int w = 0; w < NT / 32; ++w) mm = fmaxf(mm, ti->wmax[w]);
         const int e = ((__float_as_int(mm) >> 23) & 0xff) - 127;            // floor(log2 mm) for normal mm
-        // quantum = 2^-23 of the tile's max|d_out| (tap weights are in [0,1] on this path), 8 bits of headroom = up to
-        // 256 coincident full-size taps per word; tiles magnified beyond ~4x4 (area test) take the fp32 path instead
+        // quantum = 2^-22 of the tile's max|d_out| (tap weights are in [0,1] on this path, so |w*g*scale| < 2^22), 9 bits
+        // of headroom = up to 512 coincident full-size taps per word; tiles magnified beyond ~4x4 (area test) take the
+        // fp32 path instead
         fixed = (mm > 0.0f) && (e > -100) && (e < 100) && ti->area_ok;
-        scale = __int_as_float((22 - e + 127) << 23);
-        inv_scale = __int_as_float((e - 22 + 127) << 23);
+        scale = __int_as_float((21 - e + 127) << 23);
+        inv_scale = __int_as_float((e - 21 + 127) << 23);
     }
 
     const float xt = lin_at(col, stepx);
@@ -400,10 +412,10 @@ warp_bwd_tma_kernel(const __grid_constant__ CUtensorMap mapU, const __grid_const
                     gy = fmaf(gch, fmaf(Ib - Ia, t.ax, (Id - Ic) * t.bx), gy);
                     if (dU) {
                         const float gs = gch * scale;
-                        atomicAdd(qa + ch, __float2int_rn(wa * gs));
-                        atomicAdd(qa + G::kRowF + ch, __float2int_rn(wb * gs));
-                        atomicAdd(qa + C + ch, __float2int_rn(wc * gs));
-                        atomicAdd(qa + G::kRowF + C + ch, __float2int_rn(wd * gs));
+                        atomicAdd(qa + ch, fixed_of(wa, gs));
+                        atomicAdd(qa + G::kRowF + ch, fixed_of(wb, gs));
+                        atomicAdd(qa + C + ch, fixed_of(wc, gs));
+                        atomicAdd(qa + G::kRowF + C + ch, fixed_of(wd, gs));
                     }
                 }
                 accumulate_dh(dh, fmaf(gx, halfW, gimg[k][0]), fmaf(gy, halfH, gimg[k][1]), xn, yn, zs, xt, yt);
@@ -443,10 +455,10 @@ warp_bwd_tma_kernel(const __grid_constant__ CUtensorMap mapU, const __grid_const
                     if (scatter) {
                         if (inbox && fixed) {      // unclipped taps have weights in [0,1], so |w*g| <= max|d_out|
                             const float gs = gch * scale;
-                            atomicAdd(s_acc + ia + ch, __float2int_rn(wa * gs));
-                            atomicAdd(s_acc + ib + ch, __float2int_rn(wb * gs));
-                            atomicAdd(s_acc + ic + ch, __float2int_rn(wc * gs));
-                            atomicAdd(s_acc + id + ch, __float2int_rn(wd * gs));
+                            atomicAdd(s_acc + ia + ch, fixed_of(wa, gs));
+                            atomicAdd(s_acc + ib + ch, fixed_of(wb, gs));
+                            atomicAdd(s_acc + ic + ch, fixed_of(wc, gs));
+                            atomicAdd(s_acc + id + ch, fixed_of(wd, gs));
                         } else {
                             atomicAdd(dUn + ga + ch, wa * gch);
                             atomicAdd(dUn + gb + ch, wb * gch);
@@ -477,8 +489,8 @@ warp_bwd_tma_kernel(const __grid_constant__ CUtensorMap mapU, const __grid_const
         int4* a4 = reinterpret_cast<int4*>(s_acc);
         for (int i = tid; i < G::kBoxF / 4; i += NT) {
             const int4 v = a4[i];
-            reinterpret_cast<float4*>(s_acc)[i] = make_float4((float)v.x * inv_scale, (float)v.y * inv_scale,
-                                                              (float)v.z * inv_scale, (float)v.w * inv_scale);
+            reinterpret_cast<float4*>(s_acc)[i] = make_float4(float_of_fixed(v.x) * inv_scale, float_of_fixed(v.y) * inv_scale,
+                                                              float_of_fixed(v.z) * inv_scale, float_of_fixed(v.w) * inv_scale);
         }
         tma::fence_proxy_async();
         __syncthreads();
