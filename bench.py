@@ -133,6 +133,7 @@ def main():
     ap.add_argument('--cpu-sample', type=int, default=4, help='frames per CPU-baseline step')
     ap.add_argument('--no-cpu-baseline', action='store_true', help='skip the CPU leg (profiling runs)')
     ap.add_argument('--kernel-impl', default='auto', choices=['auto', 'generic', 'tma'])
+    ap.add_argument('--no-graph', action='store_true', help='launch the step eagerly instead of replaying CUDA graphs')
     args = ap.parse_args()
     if args.impl == 'reference':
         return run_reference(args)
@@ -158,7 +159,7 @@ def main():
     feats = torch.randn(n, 512, device=dev)
     reducer = mgw.parallel.MeshHeadGradReducer(512, 2 * (GH + 1) * (GW + 1), dev)
 
-    def step(i):
+    def step_eager(i):
         s = sets[i % R]
         out, black, img, Hs = ops.mesh_warp_fwd(s['U'], s['theta'])
         dU, dtheta = ops.mesh_warp_bwd(s['U'], s['theta'], Hs, s['d_out'], s['d_img'])
@@ -167,6 +168,37 @@ def main():
             reducer.head_grad(feats, dtheta)
             reducer.launch()
         return dtheta
+
+    # The step is launch-bound on the host once NCCL is in it (a dozen launches for ~160 us of GPU work): capture one
+    # CUDA graph per rotating input set and replay.  Same kernels, same work; falls back to eager launches if capture
+    # is not possible.
+    graphs = None
+    if not args.no_graph:
+        try:
+            for i in range(R):
+                step_eager(i)
+            if world > 1:
+                reducer.wait()
+            torch.cuda.synchronize()
+            graphs = []
+            for i in range(R):
+                gph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(gph):
+                    step_eager(i)
+                    if world > 1:
+                        reducer.wait()
+                graphs.append(gph)
+            torch.cuda.synchronize()
+        except Exception as e:      # noqa: BLE001
+            sys.stderr.write('CUDA graph capture failed (%s); running eager\n' % e)
+            graphs = None
+            torch.cuda.synchronize()
+
+    def step(i):
+        if graphs is not None:
+            graphs[i % R].replay()
+        else:
+            step_eager(i)
 
     def timed(fn, steps, warm):
         for i in range(warm):
@@ -194,9 +226,12 @@ def main():
         sampler.start()
         time.sleep(0.3)
     l0 = mgw.launch_count()
+    step_eager(0)
+    if world > 1:
+        reducer.wait()
+    launches_per_step = mgw.launch_count() - l0          # kernels of OUR library per step (replayed as-is under the graph)
     ms_total = timed(step, K, Wm)
-    launches = (mgw.launch_count() - l0 - 0) * 1.0
-    launches_timed = int(round(launches * K / (K + Wm)))
+    launches_timed = launches_per_step * K
     clocks = sampler.stop() if rank == 0 else None
 
     # --- per-kernel timings (same rotation, CUDA events around the single C-ABI call)
@@ -227,6 +262,8 @@ def main():
     ms_e2e = timed(e2e_step, Ke, 3)
 
     if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
         return
     peak, peak_src = peaks()
     pix_per_step = P * world
@@ -256,6 +293,7 @@ def main():
         'data': 'synthetic',
         'config': {'workload': 'configs[1]: %d x %dx%dx%d fp32 frames per GPU, %dx%d mesh warp forward+backward (dU + dtheta)' % (n, H, W, C, GH, GW),
                    'l2': 'inputs rotate over %d sets of 151 MB (> 126 MB L2)' % R, 'kernel_impl': args.kernel_impl,
+                   'launch': 'cuda graph replay' if graphs is not None else 'eager',
                    'parallelism': 'dp%d (batch-sharded, 100 KB mesh-head grad all-reduce)' % world if world > 1 else 'single GPU'},
         'fwd_mpix_per_s': pix_per_step * K / (ms_fwd_full * 1e-3) / 1e6,
         'step_hbm_gbs': gbs_step, 'step_hbm_frac_of_measured': gbs_step / peak, 'step_hbm_frac_of_8tbs': gbs_step / 8000.0,
@@ -275,6 +313,8 @@ def main():
                                 'kind': 'port', 'sample': '%d of %d frames of the same workload, fwd+bwd, mean of %d runs (%.1f s of CPU work)'
                                 % (ns, n, len(ts), sum(ts))}
     print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
 
 
 if __name__ == '__main__':

@@ -162,34 +162,99 @@ __device__ __forceinline__ void dlt_row(const float* __restrict__ theta_n, int i
     b = t;
 }
 
-__global__ void __launch_bounds__(32)
-solve_h_fwd_kernel(const float* __restrict__ theta, int N, int gh, int gw, float* __restrict__ Hs)
+// K1 runs the same LU cooperatively on 8 lanes per cell (lane = matrix row for the factorisation, lane = inverse column
+// for the substitutions; measured 6.5 us against 10 us for the one-thread-per-cell form: its chain is the longest,
+// 8 right-hand sides).  In-group (8 lanes) LU with partial pivoting of the row-distributed matrix `row` (lane g holds row g).
+// Mirrors ORC_SOLVE: first-max pivot, reciprocal scaling, fma updates.  piv[] is group-uniform.
+template <typename T>
+__device__ __forceinline__ void group_lu(T (&row)[8], int (&piv)[8], int g)
 {
-    const int cell = blockIdx.x * blockDim.x + threadIdx.x;
-    if (cell >= N * gh * gw) return;
-    const int n = cell / (gh * gw), ij = cell % (gh * gw), i = ij / gw, j = ij % gw;
-    const float* theta_n = theta + (size_t)n * (gh + 1) * (gw + 1) * 2;
-    float M[8][8], b[8];
-    int piv[8];
 #pragma unroll
-    for (int r = 0; r < 8; ++r) dlt_row<float>(theta_n, i, j, gh, gw, r, M[r], b[r]);
-    lu8<float>(M, piv);
-    // h = inverse(M) . b with the inverse formed column by column (getrs on the identity) and consumed at once:
-    // h[r] = inv[r][0]*b[0], then fma(inv[r][k], b[k], h[r]) for k = 1..7 -- the FMA chain of matmul(pinv(A), b)
-    // (spatial_transformer3.py:173), so the explicit inverse never has to be stored
-    float h[8];
+    for (int k = 0; k < 8; ++k) {
+        T best = (g >= k) ? tabs(row[k]) : (T)-1;
+        int p = g;
 #pragma unroll
-    for (int c = 0; c < 8; ++c) {
-        float col[8];
+        for (int o = 4; o > 0; o >>= 1) {
+            const T ob = __shfl_xor_sync(0xffffffffu, best, o, 8);
+            const int op = __shfl_xor_sync(0xffffffffu, p, o, 8);
+            if (ob > best || (ob == best && op < p)) { best = ob; p = op; }
+        }
+        piv[k] = p;
+        const int src = (g == k) ? p : ((g == p) ? k : g);
+        T pr[8];
 #pragma unroll
-        for (int r = 0; r < 8; ++r) col[r] = (r == c) ? 1.0f : 0.0f;
-        getrs8<float>(M, piv, col);
+        for (int c = 0; c < 8; ++c) {
+            row[c] = __shfl_sync(0xffffffffu, row[c], src, 8);
+            pr[c] = __shfl_sync(0xffffffffu, row[c], k, 8);
+        }
+        const T rp = (T)1 / pr[k];
+        if (g > k) {
+            const T l = row[k] * rp;
+            row[k] = l;
 #pragma unroll
-        for (int r = 0; r < 8; ++r) h[r] = (c == 0) ? __fmul_rn(col[r], b[0]) : __fmaf_rn(col[r], b[c], h[r]);
+            for (int c = k + 1; c < 8; ++c) row[c] = tfma<T>(-l, pr[c], row[c]);
+        }
+    }
+}
+
+// Solve LU x = P e (getrs): lane g owns one right-hand side `col`; LU is read from shared memory.
+template <typename T>
+__device__ __forceinline__ void group_getrs(const T* __restrict__ LU, const int (&piv)[8], T (&col)[8])
+{
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+#pragma unroll
+        for (int r = k + 1; r < 8; ++r)
+            if (piv[k] == r) { const T t = col[k]; col[k] = col[r]; col[r] = t; }
     }
 #pragma unroll
-    for (int r = 0; r < 8; ++r) Hs[(size_t)cell * 9 + r] = h[r];
-    Hs[(size_t)cell * 9 + 8] = 1.0f;
+    for (int r = 1; r < 8; ++r)
+#pragma unroll
+        for (int k = 0; k < r; ++k) col[r] = tfma<T>(-LU[r * 8 + k], col[k], col[r]);
+#pragma unroll
+    for (int r = 7; r >= 0; --r) {
+#pragma unroll
+        for (int k = r + 1; k < 8; ++k) col[r] = tfma<T>(-LU[r * 8 + k], col[k], col[r]);
+        col[r] = col[r] / LU[r * 8 + r];
+    }
+}
+
+constexpr int kCellsPerBlock = 16;      // 128 threads
+
+__global__ void __launch_bounds__(kCellsPerBlock * 8)
+solve_h_fwd_kernel(const float* __restrict__ theta, int N, int gh, int gw, float* __restrict__ Hs)
+{
+    __shared__ float sLU[kCellsPerBlock][64];
+    __shared__ float sINV[kCellsPerBlock][64];
+    const int slot = threadIdx.x >> 3, g = threadIdx.x & 7;
+    const int ncell = N * gh * gw;
+    int cell = blockIdx.x * kCellsPerBlock + slot;
+    const bool live = cell < ncell;
+    if (!live) cell = ncell - 1;                       // keep the whole warp converged for the shuffles
+    const int n = cell / (gh * gw), ij = cell % (gh * gw), i = ij / gw, j = ij % gw;
+    const float* theta_n = theta + (size_t)n * (gh + 1) * (gw + 1) * 2;
+
+    float row[8], b; int piv[8];
+    dlt_row<float>(theta_n, i, j, gh, gw, g, row, b);
+    group_lu<float>(row, piv, g);
+#pragma unroll
+    for (int c = 0; c < 8; ++c) sLU[slot][g * 8 + c] = row[c];
+    __syncwarp();
+    float col[8];
+#pragma unroll
+    for (int r = 0; r < 8; ++r) col[r] = (r == g) ? 1.0f : 0.0f;
+    group_getrs<float>(sLU[slot], piv, col);
+#pragma unroll
+    for (int r = 0; r < 8; ++r) sINV[slot][r * 8 + g] = col[r];
+    __syncwarp();
+    // matmul(pinv(A), b): FMA chain over k (spatial_transformer3.py:173)
+    float acc = __fmul_rn(sINV[slot][g * 8], __shfl_sync(0xffffffffu, b, 0, 8));
+#pragma unroll
+    for (int k = 1; k < 8; ++k) acc = __fmaf_rn(sINV[slot][g * 8 + k], __shfl_sync(0xffffffffu, b, k, 8), acc);
+    if (live) {
+        Hs[(size_t)cell * 9 + g] = acc;
+        if (g == 0) Hs[(size_t)cell * 9 + 8] = 1.0f;
+    }
 }
 
 // ---------------------------------------------------------------- K4: adjoint of the solve
@@ -270,7 +335,7 @@ int launch_vertices_bwd(const float* head, const float* d_pts2, const float* d_p
 int launch_solve_h_fwd(const float* theta, int N, int gh, int gw, float* Hs, cudaStream_t st)
 {
     const int ncell = N * gh * gw;
-    solve_h_fwd_kernel<<<(ncell + 31) / 32, 32, 0, st>>>(theta, N, gh, gw, Hs);
+    solve_h_fwd_kernel<<<(ncell + kCellsPerBlock - 1) / kCellsPerBlock, kCellsPerBlock * 8, 0, st>>>(theta, N, gh, gw, Hs);
     return check_launch("solve_h_fwd");
 }
 
