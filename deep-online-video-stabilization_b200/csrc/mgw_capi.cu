@@ -134,7 +134,7 @@ int mgw_warp_fwd(const float* U, const float* Hs, int N, int H, int W, int C, in
     const WarpShape s{N, H, W, C, H, W, gh, gw};
     cudaStream_t st = (cudaStream_t)stream;
     int rc;
-    if (!cell_idx && use_tma_fwd(s, U, out, black, img, &rc)) return launch_warp_fwd_tma(U, Hs, s, out, black, img, st);
+    if (!cell_idx && use_tma_fwd(s, U, out, black, img, &rc)) return launch_warp_fwd_tma(U, Hs, s, out, black, img, nullptr, nullptr, st);
     if (rc != MGW_OK) return rc;
     return launch_warp_fwd_generic(U, Hs, s, false, out, black, img, cell_idx, st);
 }
@@ -148,22 +148,27 @@ size_t mgw_warp_bwd_workspace_bytes(int N, int H, int W, int C, int gh, int gw)
 // shared by mgw_warp_bwd and mgw_mesh_warp_bwd: produces dH partials; returns their layout
 static int warp_bwd_core(const float* U, const float* Hs, const float* d_out, const float* d_img, const WarpShape& s,
                          float* dU, float* dHs_acc /*[cells,9]*/, void* workspace, const float** parts, int* nparts,
-                         int* part_stride, cudaStream_t st)
+                         int* part_stride, cudaStream_t st, const FusedImgLoss* fl = nullptr, float* d_out_scratch = nullptr)
 {
     const size_t ncell = (size_t)s.N * s.gh * s.gw;
     if (dU) TRY(check_memset(cudaMemsetAsync(dU, 0, sizeof(float) * (size_t)s.N * s.H * s.W * s.C, st), "memset dU"));
     const int mode = impl_mode();
-    const bool tma_ok = mode != 1 && workspace && tma_bwd_supported(s) && aligned(U, 16) && aligned(d_out, 16) &&
-                        (!dU || aligned(dU, 16)) && (!d_img || aligned(d_img, 16));
+    const bool tma_ok = mode != 1 && workspace && tma_bwd_supported(s) && aligned(U, 16) && (!dU || aligned(dU, 16)) &&
+                        (!d_img || aligned(d_img, 8));
     if (!tma_ok && mode == 2)
         return set_error(MGW_ERR_UNSUPPORTED, "TMA path required (mgw_set_impl(2)) but shape/alignment/workspace does not allow it");
     if (tma_ok) {
         int np = 0;
-        TRY(launch_warp_bwd_tma(U, Hs, d_out, d_img, s, dU, (float*)workspace, &np, st));
+        TRY(launch_warp_bwd_tma(U, Hs, d_out, d_img, s, dU, (float*)workspace, &np, fl, st));
         *parts = (const float*)workspace; *nparts = np; *part_stride = 8;
         return MGW_OK;
     }
     TRY(check_memset(cudaMemsetAsync(dHs_acc, 0, sizeof(float) * ncell * 9, st), "memset dHs"));
+    if (fl) {       // generic path: materialise d_out of the fused loss first
+        if (!d_out_scratch) return set_error(MGW_ERR_INVALID, "fused img_loss backward: workspace too small for the generic path");
+        TRY(launch_img_loss_bwd(fl->out, fl->y, fl->black, fl->sums, fl->kscale * 0.5f * (float)s.N, s.N, s.H, s.W, s.C, d_out_scratch, st));
+        d_out = d_out_scratch;
+    }
     TRY(launch_warp_bwd_generic(U, Hs, d_out, d_img, s, false, dU, dHs_acc, st));
     *parts = dHs_acc; *nparts = 1; *part_stride = 9;
     return MGW_OK;
@@ -214,6 +219,53 @@ int mgw_mesh_warp_bwd(const float* U, const float* theta, const float* Hs, const
     void* tma_ws = mgw_warp_bwd_workspace_bytes(N, H, W, C, gh, gw) ? (void*)((char*)workspace + off) : nullptr;
     const float* parts; int np, ps;
     TRY(warp_bwd_core(U, Hs, d_out, d_img, s, dU, dHs_acc, tma_ws, &parts, &np, &ps, st));
+    return launch_solve_h_bwd(theta, Hs, parts, np, ps, N, gh, gw, dtheta, st);
+}
+
+int mgw_mesh_warp_img_loss_fwd(const float* U, const float* theta, const float* y, int N, int H, int W, int C, int gh, int gw,
+                               float* Hs, float* out, float* black, float* img, float* sums, void* stream)
+{
+    REQUIRE(U && theta && y && Hs && out && black && sums, "mgw_mesh_warp_img_loss_fwd: null pointer");
+    TRY(validate_mesh_shape("mgw_mesh_warp_img_loss_fwd", N, H, W, C, gh, gw));
+    REQUIRE(!img || aligned(img, 8), "mgw_mesh_warp_img_loss_fwd: img must be 8-byte aligned");
+    cudaStream_t st = (cudaStream_t)stream;
+    const WarpShape s{N, H, W, C, H, W, gh, gw};
+    TRY(launch_solve_h_fwd(theta, N, gh, gw, Hs, st));
+    int rc;
+    if (use_tma_fwd(s, U, out, black, img, &rc)) {
+        TRY(check_memset(cudaMemsetAsync(sums, 0, sizeof(float) * 2 * N, st), "memset sums"));
+        return launch_warp_fwd_tma(U, Hs, s, out, black, img, y, sums, st);
+    }
+    if (rc != MGW_OK) return rc;
+    TRY(launch_warp_fwd_generic(U, Hs, s, false, out, black, img, nullptr, st));
+    return launch_img_loss_fwd(out, y, black, N, H, W, C, sums, st);
+}
+
+size_t mgw_mesh_warp_img_loss_bwd_workspace_bytes(int N, int H, int W, int C, int gh, int gw)
+{
+    const WarpShape s{N, H, W, C, H, W, gh, gw};
+    const size_t base = mgw_mesh_warp_bwd_workspace_bytes(N, H, W, C, gh, gw);
+    return align_up(base, 256) + (tma_bwd_supported(s) && impl_mode() != 1 ? 0 : sizeof(float) * (size_t)N * H * W * C);
+}
+
+int mgw_mesh_warp_img_loss_bwd(const float* U, const float* theta, const float* Hs, const float* out, const float* y,
+                               const float* black, const float* sums, float upstream, float batch, const float* d_img, int N,
+                               int H, int W, int C, int gh, int gw, float* dU, float* dtheta, void* workspace, void* stream)
+{
+    REQUIRE(U && theta && Hs && out && y && black && sums && dtheta && workspace, "mgw_mesh_warp_img_loss_bwd: null pointer");
+    TRY(validate_mesh_shape("mgw_mesh_warp_img_loss_bwd", N, H, W, C, gh, gw));
+    REQUIRE(aligned(workspace, 256) && batch > 0.0f, "mgw_mesh_warp_img_loss_bwd: workspace must be 256-byte aligned, batch > 0");
+    const WarpShape s{N, H, W, C, H, W, gh, gw};
+    cudaStream_t st = (cudaStream_t)stream;
+    float* dHs_acc = (float*)workspace;
+    const size_t off = align_up(sizeof(float) * (size_t)N * gh * gw * 9, 256);
+    const size_t tma_bytes = mgw_warp_bwd_workspace_bytes(N, H, W, C, gh, gw);
+    void* tma_ws = tma_bytes ? (void*)((char*)workspace + off) : nullptr;
+    const size_t base = align_up(mgw_mesh_warp_bwd_workspace_bytes(N, H, W, C, gh, gw), 256);
+    float* scratch = (mgw_mesh_warp_img_loss_bwd_workspace_bytes(N, H, W, C, gh, gw) > base) ? (float*)((char*)workspace + base) : nullptr;
+    const FusedImgLoss fl{out, y, black, sums, upstream * 2.0f / batch};
+    const float* parts; int np, ps;
+    TRY(warp_bwd_core(U, Hs, nullptr, d_img, s, dU, dHs_acc, tma_ws, &parts, &np, &ps, st, &fl, scratch));
     return launch_solve_h_bwd(theta, Hs, parts, np, ps, N, gh, gw, dtheta, st);
 }
 

@@ -58,12 +58,21 @@ int launch_temp_loss_bwd(const float* out1, const float* black1, const float* ou
                          float* d_out1, float* d_out2, cudaStream_t st);
 
 // mgw_warp_tma.cu : TMA-staged tiles (fast path)
+struct FusedImgLoss {            // img_loss fused onto the warp (s_net_bundle_nobm.py:347-352)
+    const float* out;            // backward: the forward's output_img
+    const float* y;              // target frames [N,H,W,C]
+    const float* black;          // backward: the forward's black_pix
+    const float* sums;           // backward: [N,2] per-sample (sum e^2, sum (1-black)) from the fused forward
+    float kscale;                // backward: upstream * 2 / batch
+};
 bool tma_fwd_supported(const WarpShape& s);
+// y_tgt / sums nullable: when given, the img_loss partial sums are accumulated into sums[N,2] (must be zeroed)
 int launch_warp_fwd_tma(const float* U, const float* Hs, const WarpShape& s, float* out, float* black, float* img,
-                        cudaStream_t st);
+                        const float* y_tgt, float* sums, cudaStream_t st);
 bool tma_bwd_supported(const WarpShape& s);
 size_t tma_bwd_workspace_bytes(const WarpShape& s);
+// fl nullable: when given, d_out is ignored and the upstream gradient is the fused img_loss's
 int launch_warp_bwd_tma(const float* U, const float* Hs, const float* d_out, const float* d_img, const WarpShape& s,
-                        float* dU, float* dHs_part, int* nparts, cudaStream_t st);
+                        float* dU, float* dHs_part, int* nparts, const FusedImgLoss* fl, cudaStream_t st);
 
 }  // namespace mgw

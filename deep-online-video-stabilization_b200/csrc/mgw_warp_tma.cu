@@ -163,11 +163,14 @@ __device__ __forceinline__ float blend4(float ax, float bx, float ay, float by, 
 }
 
 // ------------------------------------------------------------------------------------------------ forward
-template <int C, int TW, int K, int NT>
-__global__ void __launch_bounds__(NT, NT == 256 ? 4 : 2)
+// LOSS = true fuses the img_loss epilogue (s_net_bundle_nobm.py:347-352) onto the warped tile: per-sample
+// sums[n] += (sum over owned pixels of ((out - y)*(1-black))^2, sum of (1-black)).
+template <int C, int TW, int K, int NT, bool LOSS>
+__global__ void __launch_bounds__(NT, NT == 256 ? (LOSS ? 3 : 4) : 2)
 warp_fwd_tma_kernel(const __grid_constant__ CUtensorMap mapU, const __grid_constant__ CUtensorMap mapOut,
                     const float* __restrict__ U, const float* __restrict__ Hs, const __grid_constant__ TileCfg cfg,
-                    float* __restrict__ out, float* __restrict__ img, float* __restrict__ black)
+                    float* __restrict__ out, float* __restrict__ img, float* __restrict__ black,
+                    const float* __restrict__ y_tgt, float* __restrict__ sums)
 {
     using G = Geo<C, TW, K, NT>;
     extern __shared__ __align__(1024) unsigned char smem_raw[];
@@ -201,10 +204,15 @@ warp_fwd_tma_kernel(const __grid_constant__ CUtensorMap mapU, const __grid_const
     const float xt = lin_at(tl.c0 + tx, stepx);
     const float hx0 = __fmul_rn(Hc[0], xt), hx3 = __fmul_rn(Hc[3], xt), hx6 = __fmul_rn(Hc[6], xt);   // first term of hrow()
     float xn[K], yn[K];
+    float yv[LOSS ? K : 1][C], nbv[LOSS ? K : 1];          // fused loss: target pixels and (1 - black) of the owned pixels
     {
         size_t p = ((size_t)tl.n * cfg.H + tl.r0 + g * K) * cfg.W + tl.c0 + tx;
 #pragma unroll
         for (int k = 0; k < K; ++k, p += cfg.W) {
+            if (LOSS) {
+#pragma unroll
+                for (int ch = 0; ch < C; ++ch) yv[k][ch] = __ldg(y_tgt + p * C + ch);
+            }
             const float yt = lin_at(tl.r0 + g * K + k, stepy);
             const float xs = __fadd_rn(__fmaf_rn(Hc[1], yt, hx0), Hc[2]);
             const float ys = __fadd_rn(__fmaf_rn(Hc[4], yt, hx3), Hc[5]);
@@ -213,11 +221,14 @@ warp_fwd_tma_kernel(const __grid_constant__ CUtensorMap mapU, const __grid_const
             xn[k] = __fdiv_rn(xs, zs);
             yn[k] = __fdiv_rn(ys, zs);
             // x_map,y_map and black_pix are 8 / 4 contiguous bytes per lane: plain coalesced stores, no staging
+            const float bk = black_of(xn[k], yn[k]);
             if (img) reinterpret_cast<float2*>(img)[p] = make_float2(xn[k], yn[k]);
-            if (black) black[p] = black_of(xn[k], yn[k]);
+            if (black) black[p] = bk;
+            if (LOSS) nbv[k] = (tl.r0 + g * K + k >= tl.vr0 && tl.c0 + tx >= tl.vc0) ? 1.0f - bk : -1.0f;    // -1: not owned
         }
     }
     if (!out) return;
+    float se = 0.0f, sm = 0.0f;
     tma::mbar_wait(bar, 0);                           // acquire: the source box has landed and ti is visible
     const int bx0 = ti->bx0, by0 = ti->by0;
     if (ti->interior) {
@@ -227,8 +238,12 @@ warp_fwd_tma_kernel(const __grid_constant__ CUtensorMap mapU, const __grid_const
             const float* pa = s_src + ((t.y0 - by0) * G::kRowF + (t.x0 - bx0) * C);
             float* o = s_out + ((g * K + k) * TW + tx) * C;
 #pragma unroll
-            for (int ch = 0; ch < C; ++ch)
-                o[ch] = blend4(t.ax, t.bx, t.ay, t.by, pa[ch], pa[G::kRowF + ch], pa[C + ch], pa[G::kRowF + C + ch]);
+            for (int ch = 0; ch < C; ++ch) {
+                const float v = blend4(t.ax, t.bx, t.ay, t.by, pa[ch], pa[G::kRowF + ch], pa[C + ch], pa[G::kRowF + C + ch]);
+                o[ch] = v;
+                if (LOSS && nbv[k] >= 0.0f) { const float e = (v - yv[k][ch]) * nbv[k]; se = fmaf(e, e, se); }
+            }
+            if (LOSS && nbv[k] >= 0.0f) sm += nbv[k];
         }
     } else {
         const float* Un = U + (size_t)tl.n * cfg.H * cfg.W * C;
@@ -252,13 +267,31 @@ warp_fwd_tma_kernel(const __grid_constant__ CUtensorMap mapU, const __grid_const
 #pragma unroll
                 for (int ch = 0; ch < C; ++ch) o[ch] = blend(t, __ldg(pa + ch), __ldg(pb + ch), __ldg(pc + ch), __ldg(pd + ch));
             }
+            if (LOSS && nbv[k] >= 0.0f) {
+#pragma unroll
+                for (int ch = 0; ch < C; ++ch) { const float e = (o[ch] - yv[k][ch]) * nbv[k]; se = fmaf(e, e, se); }
+                sm += nbv[k];
+            }
         }
+    }
+    if (LOSS) {
+        se = warp_sum(se); sm = warp_sum(sm);
+        float* s_loss = reinterpret_cast<float*>(ti + 1);             // [warps][2]
+        if ((tid & 31) == 0) { s_loss[(tid >> 5) * 2] = se; s_loss[(tid >> 5) * 2 + 1] = sm; }
     }
     tma::fence_proxy_async();
     __syncthreads();
     if (tid == 0) {
         tma::store_3d(&mapOut, s_out, tl.c0 * C, tl.r0, tl.n);
         tma::commit_group();
+        if (LOSS) {
+            const float* s_loss = reinterpret_cast<const float*>(ti + 1);
+            float a = 0.0f, b = 0.0f;
+#pragma unroll
+            for (int w = 0; w < NT / 32; ++w) { a += s_loss[2 * w]; b += s_loss[2 * w + 1]; }
+            atomicAdd(sums + 2 * tl.n, a);
+            atomicAdd(sums + 2 * tl.n + 1, b);
+        }
         tma::wait_group_read0();
     }
 }
@@ -286,12 +319,22 @@ __device__ __forceinline__ void accumulate_dh(float (&dh)[8], float gxn, float g
     dh[6] = fmaf(dzs, xt, dh[6]); dh[7] = fmaf(dzs, yt, dh[7]);
 }
 
-template <int C, int TW, int K, int NT>
+// LOSS = true takes the upstream gradient from the fused img_loss instead of a d_out tensor:
+// d_out = kscale/(sums[n][1]+1e-8) * (out - y) * (1-black)^2, computed in registers from the forward's out / black.
+struct LossBwd {
+    const float* out;       // forward output_img
+    const float* y;         // target
+    const float* black;     // forward black_pix
+    const float* sums;      // [N,2] from the fused forward
+    float kscale;           // upstream * 2 / batch
+};
+
+template <int C, int TW, int K, int NT, bool LOSS>
 __global__ void __launch_bounds__(NT, NT == 256 ? 3 : 2)
 warp_bwd_tma_kernel(const __grid_constant__ CUtensorMap mapU, const __grid_constant__ CUtensorMap mapDU,
                     const float* __restrict__ U, const float* __restrict__ Hs, const float* __restrict__ d_out,
                     const float* __restrict__ d_img, const __grid_constant__ TileCfg cfg, float* __restrict__ dU,
-                    float* __restrict__ parts)
+                    float* __restrict__ parts, const LossBwd loss)
 {
     using G = Geo<C, TW, K, NT>;
     extern __shared__ __align__(1024) unsigned char smem_raw[];
@@ -318,10 +361,18 @@ warp_bwd_tma_kernel(const __grid_constant__ CUtensorMap mapU, const __grid_const
     float gout[K][C], gimg[K][2];
     {
         size_t p = ((size_t)tl.n * cfg.H + tl.r0 + g * K) * cfg.W + col;
+        const float kn = LOSS ? loss.kscale / (__ldg(loss.sums + 2 * tl.n + 1) + 1e-8f) : 0.0f;
 #pragma unroll
         for (int k = 0; k < K; ++k, p += cfg.W) {
+            if (LOSS) {
+                const float nb = 1.0f - __ldg(loss.black + p);
+                const float kk = kn * nb * nb;
 #pragma unroll
-            for (int ch = 0; ch < C; ++ch) gout[k][ch] = __ldg(d_out + p * C + ch);
+                for (int ch = 0; ch < C; ++ch) gout[k][ch] = kk * (__ldg(loss.out + p * C + ch) - __ldg(loss.y + p * C + ch));
+            } else {
+#pragma unroll
+                for (int ch = 0; ch < C; ++ch) gout[k][ch] = __ldg(d_out + p * C + ch);
+            }
             if (d_img) {
                 const float2 di = __ldg(reinterpret_cast<const float2*>(d_img) + p);
                 gimg[k][0] = di.x; gimg[k][1] = di.y;
@@ -629,23 +680,30 @@ static int allow_smem(KernelT kernel, bool* done_for_device, const char* what)
 }
 
 template <int C, int TW, int K, int NT>
-static int launch_fwd_v(const float* U, const float* Hs, const Plan& p, float* out, float* black, float* img, cudaStream_t st)
+static int launch_fwd_v(const float* U, const float* Hs, const Plan& p, float* out, float* black, float* img, const float* y_tgt,
+                        float* sums, cudaStream_t st)
 {
     using G = Geo<C, TW, K, NT>;
     const TileCfg& c = p.cfg;
     CUtensorMap mU, mOut;
     TRY_RC(make_map(&mU, U, c.W * C, c.H, c.N, G::kRowF, G::SBH));
     TRY_RC(make_map(&mOut, out ? out : U, c.W * C, c.H, c.N, TW * C, G::TH));
-    const size_t smem = (size_t)(G::kBoxF + G::kOutF) * 4 + 16 + sizeof(TileInfo) + 64;
+    const size_t smem = (size_t)(G::kBoxF + G::kOutF) * 4 + 16 + sizeof(TileInfo) + 2 * kMaxWarps * 4 + 64;
+    if (y_tgt) {
+        static bool attr_l[64] = {};
+        TRY_RC(allow_smem(warp_fwd_tma_kernel<C, TW, K, NT, true>, attr_l, "warp_fwd_tma(loss)"));
+        warp_fwd_tma_kernel<C, TW, K, NT, true><<<dim3(p.ntx, p.nty, c.N), NT, smem, st>>>(mU, mOut, U, Hs, c, out, img, black, y_tgt, sums);
+        return check_launch("warp_fwd_tma(loss)");
+    }
     static bool attr[64] = {};
-    TRY_RC(allow_smem(warp_fwd_tma_kernel<C, TW, K, NT>, attr, "warp_fwd_tma"));
-    warp_fwd_tma_kernel<C, TW, K, NT><<<dim3(p.ntx, p.nty, c.N), NT, smem, st>>>(mU, mOut, U, Hs, c, out, img, black);
+    TRY_RC(allow_smem(warp_fwd_tma_kernel<C, TW, K, NT, false>, attr, "warp_fwd_tma"));
+    warp_fwd_tma_kernel<C, TW, K, NT, false><<<dim3(p.ntx, p.nty, c.N), NT, smem, st>>>(mU, mOut, U, Hs, c, out, img, black, nullptr, nullptr);
     return check_launch("warp_fwd_tma");
 }
 
 template <int C, int TW, int K, int NT>
 static int launch_bwd_v(const float* U, const float* Hs, const float* d_out, const float* d_img, const Plan& p, float* dU,
-                        float* parts, cudaStream_t st)
+                        float* parts, const LossBwd* loss, cudaStream_t st)
 {
     using G = Geo<C, TW, K, NT>;
     const TileCfg& c = p.cfg;
@@ -653,62 +711,73 @@ static int launch_bwd_v(const float* U, const float* Hs, const float* d_out, con
     TRY_RC(make_map(&mU, U, c.W * C, c.H, c.N, G::kRowF, G::SBH));
     if (dU) TRY_RC(make_map(&mDU, dU, c.W * C, c.H, c.N, G::kRowF, G::SBH)); else mDU = mU;
     const size_t smem = (size_t)(G::kBoxF + 256 + (dU ? G::kBoxF : 0)) * 4 + 64;
+    if (loss) {
+        static bool attr_l[64] = {};
+        TRY_RC(allow_smem(warp_bwd_tma_kernel<C, TW, K, NT, true>, attr_l, "warp_bwd_tma(loss)"));
+        warp_bwd_tma_kernel<C, TW, K, NT, true><<<dim3(p.ntx, p.nty, c.N), NT, smem, st>>>(mU, mDU, U, Hs, nullptr, d_img, c, dU, parts, *loss);
+        return check_launch("warp_bwd_tma(loss)");
+    }
     static bool attr[64] = {};
-    TRY_RC(allow_smem(warp_bwd_tma_kernel<C, TW, K, NT>, attr, "warp_bwd_tma"));
-    warp_bwd_tma_kernel<C, TW, K, NT><<<dim3(p.ntx, p.nty, c.N), NT, smem, st>>>(mU, mDU, U, Hs, d_out, d_img, c, dU, parts);
+    TRY_RC(allow_smem(warp_bwd_tma_kernel<C, TW, K, NT, false>, attr, "warp_bwd_tma"));
+    warp_bwd_tma_kernel<C, TW, K, NT, false><<<dim3(p.ntx, p.nty, c.N), NT, smem, st>>>(mU, mDU, U, Hs, d_out, d_img, c, dU, parts, LossBwd{});
     return check_launch("warp_bwd_tma");
 }
 
 template <int C>
-static int launch_fwd_c(const Plan& p, const float* U, const float* Hs, float* out, float* black, float* img, cudaStream_t st)
+static int launch_fwd_c(const Plan& p, const float* U, const float* Hs, float* out, float* black, float* img, const float* y_tgt,
+                        float* sums, cudaStream_t st)
 {
-    if (p.NT == 256 && p.TW == 32 && p.K == 3) return launch_fwd_v<C, 32, 3, 256>(U, Hs, p, out, black, img, st);
-    if (p.NT == 256 && p.TW == 32 && p.K == 2) return launch_fwd_v<C, 32, 2, 256>(U, Hs, p, out, black, img, st);
-    if (p.NT == 256 && p.TW == 32 && p.K == 1) return launch_fwd_v<C, 32, 1, 256>(U, Hs, p, out, black, img, st);
+    if (p.NT == 256 && p.TW == 32 && p.K == 3) return launch_fwd_v<C, 32, 3, 256>(U, Hs, p, out, black, img, y_tgt, sums, st);
+    if (p.NT == 256 && p.TW == 32 && p.K == 2) return launch_fwd_v<C, 32, 2, 256>(U, Hs, p, out, black, img, y_tgt, sums, st);
+    if (p.NT == 256 && p.TW == 32 && p.K == 1) return launch_fwd_v<C, 32, 1, 256>(U, Hs, p, out, black, img, y_tgt, sums, st);
     if constexpr (C != 4) {
-        if (p.NT == 256 && p.TW == 64 && p.K == 6) return launch_fwd_v<C, 64, 6, 256>(U, Hs, p, out, black, img, st);
-        if (p.NT == 512 && p.TW == 64 && p.K == 3) return launch_fwd_v<C, 64, 3, 512>(U, Hs, p, out, black, img, st);
-        if (p.NT == 256 && p.TW == 64 && p.K == 3) return launch_fwd_v<C, 64, 3, 256>(U, Hs, p, out, black, img, st);
+        if (p.NT == 256 && p.TW == 64 && p.K == 6) return launch_fwd_v<C, 64, 6, 256>(U, Hs, p, out, black, img, y_tgt, sums, st);
+        if (p.NT == 512 && p.TW == 64 && p.K == 3) return launch_fwd_v<C, 64, 3, 512>(U, Hs, p, out, black, img, y_tgt, sums, st);
+        if (p.NT == 256 && p.TW == 64 && p.K == 3) return launch_fwd_v<C, 64, 3, 256>(U, Hs, p, out, black, img, y_tgt, sums, st);
     }
     return set_error(MGW_ERR_UNSUPPORTED, "warp_fwd_tma: no tile variant");
 }
 
 template <int C>
 static int launch_bwd_c(const Plan& p, const float* U, const float* Hs, const float* d_out, const float* d_img, float* dU,
-                        float* parts, cudaStream_t st)
+                        float* parts, const LossBwd* loss, cudaStream_t st)
 {
-    if (p.NT == 256 && p.TW == 32 && p.K == 3) return launch_bwd_v<C, 32, 3, 256>(U, Hs, d_out, d_img, p, dU, parts, st);
-    if (p.NT == 256 && p.TW == 32 && p.K == 2) return launch_bwd_v<C, 32, 2, 256>(U, Hs, d_out, d_img, p, dU, parts, st);
-    if (p.NT == 256 && p.TW == 32 && p.K == 1) return launch_bwd_v<C, 32, 1, 256>(U, Hs, d_out, d_img, p, dU, parts, st);
+    if (p.NT == 256 && p.TW == 32 && p.K == 3) return launch_bwd_v<C, 32, 3, 256>(U, Hs, d_out, d_img, p, dU, parts, loss, st);
+    if (p.NT == 256 && p.TW == 32 && p.K == 2) return launch_bwd_v<C, 32, 2, 256>(U, Hs, d_out, d_img, p, dU, parts, loss, st);
+    if (p.NT == 256 && p.TW == 32 && p.K == 1) return launch_bwd_v<C, 32, 1, 256>(U, Hs, d_out, d_img, p, dU, parts, loss, st);
     if constexpr (C != 4) {
-        if (p.NT == 256 && p.TW == 64 && p.K == 6) return launch_bwd_v<C, 64, 6, 256>(U, Hs, d_out, d_img, p, dU, parts, st);
-        if (p.NT == 512 && p.TW == 64 && p.K == 3) return launch_bwd_v<C, 64, 3, 512>(U, Hs, d_out, d_img, p, dU, parts, st);
-        if (p.NT == 256 && p.TW == 64 && p.K == 3) return launch_bwd_v<C, 64, 3, 256>(U, Hs, d_out, d_img, p, dU, parts, st);
+        if (p.NT == 256 && p.TW == 64 && p.K == 6) return launch_bwd_v<C, 64, 6, 256>(U, Hs, d_out, d_img, p, dU, parts, loss, st);
+        if (p.NT == 512 && p.TW == 64 && p.K == 3) return launch_bwd_v<C, 64, 3, 512>(U, Hs, d_out, d_img, p, dU, parts, loss, st);
+        if (p.NT == 256 && p.TW == 64 && p.K == 3) return launch_bwd_v<C, 64, 3, 256>(U, Hs, d_out, d_img, p, dU, parts, loss, st);
     }
     return set_error(MGW_ERR_UNSUPPORTED, "warp_bwd_tma: no tile variant");
 }
 
-int launch_warp_fwd_tma(const float* U, const float* Hs, const WarpShape& s, float* out, float* black, float* img, cudaStream_t st)
+int launch_warp_fwd_tma(const float* U, const float* Hs, const WarpShape& s, float* out, float* black, float* img,
+                        const float* y_tgt, float* sums, cudaStream_t st)
 {
     Plan p;
     if (!plan(s, &p)) return set_error(MGW_ERR_UNSUPPORTED, "warp_fwd_tma: unsupported shape");
-    if (s.C == 1) return launch_fwd_c<1>(p, U, Hs, out, black, img, st);
-    if (s.C == 3) return launch_fwd_c<3>(p, U, Hs, out, black, img, st);
-    return launch_fwd_c<4>(p, U, Hs, out, black, img, st);
+    if (s.C == 1) return launch_fwd_c<1>(p, U, Hs, out, black, img, y_tgt, sums, st);
+    if (s.C == 3) return launch_fwd_c<3>(p, U, Hs, out, black, img, y_tgt, sums, st);
+    return launch_fwd_c<4>(p, U, Hs, out, black, img, y_tgt, sums, st);
 }
 
 int launch_warp_bwd_tma(const float* U, const float* Hs, const float* d_out, const float* d_img, const WarpShape& s, float* dU,
-                        float* parts, int* nparts, cudaStream_t st)
+                        float* parts, int* nparts, const FusedImgLoss* fl, cudaStream_t st)
 {
+    LossBwd lb{};
+    const LossBwd* loss = nullptr;
+    if (fl) { lb.out = fl->out; lb.y = fl->y; lb.black = fl->black; lb.sums = fl->sums; lb.kscale = fl->kscale; loss = &lb; }
     Plan p;
     if (!plan(s, &p)) return set_error(MGW_ERR_UNSUPPORTED, "warp_bwd_tma: unsupported shape");
     *nparts = p.cfg.parts_y * p.cfg.parts_x;
     // cells with fewer tiles than parts_y*parts_x leave slots untouched: zero them (a few hundred KB at most)
     if (cudaMemsetAsync(parts, 0, tma_bwd_workspace_bytes(s), st) != cudaSuccess)
         return set_error(MGW_ERR_CUDA, "memset parts: %s", cudaGetErrorString(cudaGetLastError()));
-    if (s.C == 1) return launch_bwd_c<1>(p, U, Hs, d_out, d_img, dU, parts, st);
-    if (s.C == 3) return launch_bwd_c<3>(p, U, Hs, d_out, d_img, dU, parts, st);
-    return launch_bwd_c<4>(p, U, Hs, d_out, d_img, dU, parts, st);
+    if (s.C == 1) return launch_bwd_c<1>(p, U, Hs, d_out, d_img, dU, parts, loss, st);
+    if (s.C == 3) return launch_bwd_c<3>(p, U, Hs, d_out, d_img, dU, parts, loss, st);
+    return launch_bwd_c<4>(p, U, Hs, d_out, d_img, dU, parts, loss, st);
 }
 
 }  // namespace mgw

@@ -24,6 +24,34 @@ class MeshWarp(torch.autograd.Function):
         return dU, dtheta
 
 
+class MeshWarpImgLoss(torch.autograd.Function):
+    """transformer(U, theta) + img_loss(h_trans, y, black_pix) in one forward kernel and one backward kernel
+    (reference s_net_bundle_nobm.py:332 and :347-352).  Returns (loss, output, black_pix, img).  The fused backward is
+    taken when no other gradient reaches `output`; otherwise the loss gradient is materialised and added."""
+
+    @staticmethod
+    def forward(ctx, U, theta, y, batch):
+        out, black, img, Hs, sums = ops.mesh_warp_img_loss_fwd(U, theta, y)
+        ctx.save_for_backward(U, theta, Hs, out, y, black, sums)
+        ctx.batch = batch
+        ctx.mark_non_differentiable(black)
+        loss = (sums[:, 0] / (sums[:, 1] + 1e-8)).sum() / batch
+        return loss, out, black, img
+
+    @staticmethod
+    def backward(ctx, g_loss, g_out, _g_black, g_img):
+        U, theta, Hs, out, y, black, sums = ctx.saved_tensors
+        g_img = None if g_img is None else g_img.contiguous()
+        up = 0.0 if g_loss is None else float(g_loss)
+        if g_out is None:
+            dU, dtheta = ops.mesh_warp_img_loss_bwd(U, theta, Hs, out, y, black, sums, up, ctx.batch, g_img,
+                                                    want_dU=ctx.needs_input_grad[0])
+        else:
+            d_out = g_out.contiguous() + ops.img_loss_bwd(out, y, black, sums, up * out.shape[0] / ctx.batch)
+            dU, dtheta = ops.mesh_warp_bwd(U, theta, Hs, d_out, g_img, want_dU=ctx.needs_input_grad[0])
+        return dU, dtheta, None, None
+
+
 class HomographyWarp(torch.autograd.Function):
     """spatial_transformer.transformer(U, theta[N,9], out_size) (reference spatial_transformer.py:18-197)."""
 

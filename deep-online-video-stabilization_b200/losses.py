@@ -17,6 +17,12 @@ def img_loss(h_trans, y, black_pix, batch_size=None):
     return F.ImgLoss.apply(h_trans, y, black_pix.reshape(n, h, w), float(batch_size or n))
 
 
+def transformer_img_loss(U, theta, y, batch_size=None):
+    """transformer(U, theta) and img_loss(h_trans, y, black_pix) fused into the warp kernels (north_star part 4):
+    -> (img_loss, h_trans, black_pix, flow).  Equivalent to reference s_net_bundle_nobm.py:332 + :347-352."""
+    return F.MeshWarpImgLoss.apply(U, theta, y, float(batch_size or U.shape[0]))
+
+
 def feature_loss(matches, mask, flow, batch_size=None):
     """reference s_net_bundle_nobm.py:335-343 -> (loss, stable_warpped [N,M,2])."""
     return F.FeatureLoss.apply(matches, mask, flow, float(batch_size or flow.shape[0]))

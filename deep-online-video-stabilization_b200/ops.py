@@ -138,6 +138,41 @@ def mesh_warp_bwd(U, theta, Hs, d_out, d_img=None, want_dU=True):
     return dU, dtheta
 
 
+def mesh_warp_img_loss_fwd(U, theta, y, want_img=True):
+    """transformer(U, theta) with the img_loss partial sums accumulated inside the warp kernel -> (out, black, img, Hs, sums[N,2])."""
+    U, theta, y = _chk(U, 'U'), _chk(theta, 'theta'), _chk(y, 'y')
+    n, h, w, c = _mesh_dims(U, theta, 'theta')
+    if tuple(y.shape) != (n, h, w, c):
+        raise ValueError('y must have the shape of U')
+    gh, gw = theta.shape[1] - 1, theta.shape[2] - 1
+    dev = U.device
+    Hs = torch.empty((n, gh, gw, 9), device=dev, dtype=torch.float32)
+    out = torch.empty((n, h, w, c), device=dev, dtype=torch.float32)
+    black = torch.empty((n, h, w), device=dev, dtype=torch.float32)
+    img = torch.empty((n, h, w, 2), device=dev, dtype=torch.float32) if want_img else None
+    sums = torch.empty((n, 2), device=dev, dtype=torch.float32)
+    with torch.cuda.device(dev):
+        check(lib.mgw_mesh_warp_img_loss_fwd(_p(U), _p(theta), _p(y), n, h, w, c, gh, gw, _p(Hs), _p(out), _p(black), _p(img),
+                                             _p(sums), _st()), 'mgw_mesh_warp_img_loss_fwd')
+    return out, black, img, Hs, sums
+
+
+def mesh_warp_img_loss_bwd(U, theta, Hs, out, y, black, sums, upstream, batch, d_img=None, want_dU=True):
+    U, theta, Hs, out, y, black, sums = (_chk(t, nm) for t, nm in ((U, 'U'), (theta, 'theta'), (Hs, 'Hs'), (out, 'out'), (y, 'y'),
+                                                                   (black, 'black'), (sums, 'sums')))
+    d_img = None if d_img is None else _chk(d_img, 'd_img')
+    n, h, w, c = _mesh_dims(U, theta, 'theta')
+    gh, gw = Hs.shape[1:3]
+    dU = torch.empty_like(U) if want_dU else None
+    dtheta = torch.empty_like(theta)
+    ws = _workspace(lib.mgw_mesh_warp_img_loss_bwd_workspace_bytes(n, h, w, c, gh, gw), U.device)
+    with torch.cuda.device(U.device):
+        check(lib.mgw_mesh_warp_img_loss_bwd(_p(U), _p(theta), _p(Hs), _p(out), _p(y), _p(black), _p(sums), float(upstream),
+                                             float(batch), _p(d_img), n, h, w, c, gh, gw, _p(dU), _p(dtheta), _p(ws), _st()),
+              'mgw_mesh_warp_img_loss_bwd')
+    return dU, dtheta
+
+
 def interp_fwd(im, x, y, out_size):
     im, x, y = _chk(im, 'im'), _chk(x, 'x'), _chk(y, 'y')
     n, ih, iw, c = im.shape

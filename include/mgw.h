@@ -89,6 +89,20 @@ MGW_API int mgw_mesh_warp_bwd(const float* U, const float* theta, const float* H
                       int N, int H, int W, int C, int gh, int gw, float* dU, float* dtheta, void* workspace,
                       void* stream);
 
+/* ---- fused a1-a5 + a8: transformer(U, theta) with the img_loss epilogue (s_net_bundle_nobm.py:332,347-352) ----------
+ * Forward: as mgw_mesh_warp_fwd (out, black required) plus sums [N,2] = per-sample (sum ((out-y)(1-black))^2,
+ * sum (1-black)) accumulated inside the warp kernel -- no second pass over out / y / black.
+ * Backward: the upstream gradient of out is the loss's, d_out = upstream*2/batch * (out-y)(1-black)^2/(sums[n][1]+1e-8),
+ * formed in registers inside the backward kernel (no d_out tensor is written or read); d_img nullable as before.
+ * loss = sum_n sums[n][0]/(sums[n][1]+1e-8)/batch is N scalars of arithmetic left to the caller. */
+MGW_API int mgw_mesh_warp_img_loss_fwd(const float* U, const float* theta, const float* y, int N, int H, int W, int C, int gh,
+                               int gw, float* Hs, float* out, float* black, float* img, float* sums, void* stream);
+MGW_API size_t mgw_mesh_warp_img_loss_bwd_workspace_bytes(int N, int H, int W, int C, int gh, int gw);
+MGW_API int mgw_mesh_warp_img_loss_bwd(const float* U, const float* theta, const float* Hs, const float* out, const float* y,
+                               const float* black, const float* sums, float upstream, float batch, const float* d_img,
+                               int N, int H, int W, int C, int gh, int gw, float* dU, float* dtheta, void* workspace,
+                               void* stream);
+
 /* ---- a6: interpolate(im, x, y, out_size), spatial_transformer.py:200-281 ------------------------------
  * im [N,IH,IW,C]; x,y [N,OH,OW] normalised coords -> out [N,OH,OW,C]. */
 MGW_API int mgw_interp_fwd(const float* im, const float* x, const float* y, int N, int IH, int IW, int C, int OH, int OW,

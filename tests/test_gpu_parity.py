@@ -275,6 +275,43 @@ def test_vertices_and_losses(mgw):
                 assert ok, '%s %s rel err %.3g' % (nm, k, e)
 
 
+@pytest.mark.parametrize('impl', IMPLS)
+@pytest.mark.parametrize('shape', [(2, 96, 160, 3), (2, 48, 64, 1)])
+def test_fused_img_loss_equals_unfused(mgw, impl, shape):
+    """transformer_img_loss (loss sums inside the warp kernel, d_out formed in registers) == transformer + img_loss, and
+    == the oracle port's fp64 autograd at the same inputs."""
+    import mesh_warp_ref as ref
+    import synth
+    mgw.set_impl(impl)
+    n, h, w, c = shape
+    U, y = synth.smooth_image(n, h, w, c, 700), synth.smooth_image(n, h, w, c, 701)
+    theta = synth.random_mesh(n, 4, 4, 0.05, 702)
+    d_img = synth.randn((n, h, w, 2), 703, 1e-4)
+    Ua, ta = dev(U).requires_grad_(True), dev(theta).requires_grad_(True)
+    loss_f, out_f, black_f, img_f = mgw.transformer_img_loss(Ua, ta, dev(y))
+    (loss_f * 3.0 + (img_f * dev(d_img)).sum()).backward()
+    Ub, tb = dev(U).requires_grad_(True), dev(theta).requires_grad_(True)
+    out_u, black_u, img_u = mgw.transformer(Ub, tb)
+    loss_u = mgw.img_loss(out_u, dev(y), black_u)
+    (loss_u * 3.0 + (img_u * dev(d_img)).sum()).backward()
+    assert torch.equal(out_f, out_u) and torch.equal(black_f, black_u) and torch.equal(img_f, img_u)
+    assert abs(float(loss_f) - float(loss_u)) <= 1e-5 * abs(float(loss_u))
+    assert relmax(ta.grad.cpu().numpy(), tb.grad.cpu().numpy()) < 1e-4
+    assert relmax(Ua.grad.cpu().numpy(), Ub.grad.cpu().numpy()) < 1e-4
+    # fused loss with ANOTHER gradient on the output takes the unfused backward and must still be right
+    Uc, tc = dev(U).requires_grad_(True), dev(theta).requires_grad_(True)
+    loss_c, out_c, _, _ = mgw.transformer_img_loss(Uc, tc, dev(y))
+    (loss_c * 3.0 + (out_c * dev(d_img[..., :1]).expand_as(out_c)).sum()).backward()
+    Ud, td = dev(U).requires_grad_(True), dev(theta).requires_grad_(True)
+    out_d, black_d, _ = mgw.transformer(Ud, td)
+    (mgw.img_loss(out_d, dev(y), black_d) * 3.0 + (out_d * dev(d_img[..., :1]).expand_as(out_d)).sum()).backward()
+    assert relmax(tc.grad.cpu().numpy(), td.grad.cpu().numpy()) < 1e-4
+    # and against the oracle (fp64 port) for the loss value
+    o64, b64, _, _ = ref.transformer(torch.tensor(U, dtype=torch.float64), torch.tensor(theta, dtype=torch.float64))
+    l64 = float(ref.img_loss(o64, torch.tensor(y, dtype=torch.float64), b64))
+    assert abs(float(loss_f) - l64) <= 2e-5 * abs(l64)
+
+
 # ------------------------------------------------------------------ full-size properties (config #2: 32 x 288 x 512 x 3)
 @pytest.fixture(scope='module')
 def full():

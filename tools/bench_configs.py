@@ -1,0 +1,137 @@
+"""Numbers for the BASELINE.json configs that are not the bench.py line (they are parity cases there):
+  #1 single 288x512x3 frame forward, #3 StabNet-v2_93-shaped forward (torch ResNet-50 as carrier, random init, batch 16)
+  with the multi-grid warp stage on our kernels, #4 1080p batch-1 streaming warp latency (p50 over 1000 frames).
+Writes one JSON object to stdout.  Not part of the bench.py contract."""
+import json, os, sys, time
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, 'oracle'))
+import numpy as np, torch, torch.nn as nn
+import synth, dovs_b200 as mgw
+from dovs_b200 import ops
+from dovs_b200._lib import lib, check
+dev = 'cuda'
+res = {}
+flush = torch.empty(40 * 1024 * 1024, device=dev)
+
+
+def dev_time(fn, reps=50, flush_l2=True):
+    for _ in range(5):
+        fn()
+    ts = []
+    for _ in range(reps):
+        if flush_l2:
+            flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); fn(); e1.record(); torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1) * 1e3)
+    return float(np.median(ts))
+
+
+# ---- config #1: single frame forward
+U = torch.tensor(synth.noise_image(1, 288, 512, 3, 1), device=dev)
+th = torch.tensor(synth.random_mesh(1, 4, 4, 0.05, 2), device=dev)
+t = dev_time(lambda: ops.mesh_warp_fwd(U, th))
+res['config1_single_frame_fwd'] = {'us_device': t, 'mpix_per_s': 288 * 512 / t}
+
+# ---- config #4: 1080p streaming, batch 1: preallocated buffers, one CUDA graph (K1 + K2), pinned host frames
+Hh, Ww = 1080, 1920
+frame_h = torch.tensor(synth.noise_image(1, Hh, Ww, 3, 3)).pin_memory()
+th = torch.tensor(synth.random_mesh(1, 4, 4, 0.03, 4), device=dev)
+frame_d = torch.empty((1, Hh, Ww, 3), device=dev)
+out_d = torch.empty_like(frame_d); black_d = torch.empty((1, Hh, Ww), device=dev); img_d = torch.empty((1, Hh, Ww, 2), device=dev)
+Hs_d = torch.empty((1, 4, 4, 9), device=dev)
+out_h = torch.empty((1, Hh, Ww, 3)).pin_memory()
+P = lambda x: x.data_ptr()
+s = torch.cuda.Stream()
+with torch.cuda.stream(s):
+    call = lambda: check(lib.mgw_mesh_warp_fwd(P(frame_d), P(th), 1, Hh, Ww, 3, 4, 4, P(Hs_d), P(out_d), P(black_d), P(img_d),
+                                                torch.cuda.current_stream().cuda_stream), 'fwd')
+    frame_d.copy_(frame_h, non_blocking=True)
+    for _ in range(3):
+        call()
+    s.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g, stream=s):
+        call()
+    dev_eager = dev_time(call, 200, flush_l2=False)
+    dev_graph = dev_time(g.replay, 200, flush_l2=False)
+    lat = []
+    for i in range(1000):
+        t0 = time.perf_counter()
+        frame_d.copy_(frame_h, non_blocking=True)
+        g.replay()
+        out_h.copy_(out_d, non_blocking=True)
+        s.synchronize()
+        lat.append((time.perf_counter() - t0) * 1e6)
+    lat2 = []
+    for i in range(1000):
+        t0 = time.perf_counter()
+        g.replay()
+        s.synchronize()
+        lat2.append((time.perf_counter() - t0) * 1e6)
+res['config4_1080p_stream'] = {
+    'us_device_eager_call': dev_eager, 'us_device_graph_replay': dev_graph,
+    'us_p50_host_to_host_fp32_frames': float(np.percentile(lat, 50)), 'us_p99_host_to_host': float(np.percentile(lat, 99)),
+    'us_p50_launch_to_done_resident': float(np.percentile(lat2, 50)),
+    'bytes_h2d_per_frame': frame_h.numel() * 4, 'bytes_d2h_per_frame': out_h.numel() * 4,
+    'note': 'host-to-host is PCIe-bound: 24.9 MB each way per fp32 1080p frame'}
+
+
+# ---- config #3: StabNet-shaped forward, batch 16, 13-channel 288x512 input (configs/v2_93.py:19-22,40)
+def bottleneck(cin, mid, stride):
+    return nn.ModuleDict(dict(
+        pre=nn.Sequential(nn.BatchNorm2d(cin), nn.ReLU(inplace=True)),
+        short=nn.Conv2d(cin, mid * 4, 1, stride) if (stride != 1 or cin != mid * 4) else nn.Identity(),
+        body=nn.Sequential(nn.Conv2d(cin, mid, 1), nn.BatchNorm2d(mid), nn.ReLU(inplace=True),
+                           nn.Conv2d(mid, mid, 3, stride, 1), nn.BatchNorm2d(mid), nn.ReLU(inplace=True),
+                           nn.Conv2d(mid, mid * 4, 1))))
+
+
+class ResNet50v2Head(nn.Module):
+    """resnet_v2_50(global_pool=False, output_stride=32) -> mean pool -> fc 2048/1024/512/50 (s_net_bundle_nobm.py:250-264)."""
+
+    def __init__(self, cin=13, nout=50):
+        super().__init__()
+        self.stem = nn.Sequential(nn.Conv2d(cin, 64, 7, 2, 3), nn.MaxPool2d(3, 2, 1))
+        blocks, c = [], 64
+        for mid, n, stride in ((64, 3, 2), (128, 4, 2), (256, 6, 2), (512, 3, 1)):
+            for i in range(n):
+                blocks.append(bottleneck(c, mid, stride if i == n - 1 else 1))
+                c = mid * 4
+        self.blocks = nn.ModuleList(blocks)
+        self.post = nn.Sequential(nn.BatchNorm2d(c), nn.ReLU(inplace=True))
+        self.fc = nn.Sequential(nn.Linear(2048, 2048), nn.ReLU(), nn.Linear(2048, 1024), nn.ReLU(), nn.Linear(1024, 512), nn.ReLU(),
+                                nn.Linear(512, nout))
+        nn.init.zeros_(self.fc[-1].weight); nn.init.zeros_(self.fc[-1].bias)
+
+    def forward(self, x):
+        x = self.stem(x)
+        for b in self.blocks:
+            y = b['pre'](x)
+            x = b['short'](y if not isinstance(b['short'], nn.Identity) else x) + b['body'](y)
+        return self.fc(self.post(x).mean((2, 3)))
+
+
+torch.backends.cudnn.benchmark = True
+net = ResNet50v2Head().to(dev).eval().to(memory_format=torch.channels_last)
+n = 16
+x_nhwc = torch.tensor(synth.noise_image(n, 288, 512, 13, 5), device=dev)
+with torch.no_grad():
+    def backbone():
+        return net(x_nhwc.permute(0, 3, 1, 2))          # NHWC storage viewed as channels_last NCHW: no copy
+
+    def warp_stage(head):
+        head = head + 0.01 * torch.randn_like(head)       # random-init head outputs zeros: jitter so the mesh is not the identity
+        _, pts2 = mgw.get_4_pts(head, n, (4, 4))
+        cur = x_nhwc[..., 12:13].contiguous()             # the current frame, channel 12 (s_net_bundle_nobm.py:281)
+        return mgw.transformer(cur, pts2)
+
+    head = backbone()
+    t_backbone = dev_time(backbone, 20)
+    t_warp = dev_time(lambda: warp_stage(head), 50)
+    t_total = dev_time(lambda: warp_stage(backbone()), 20)
+res['config3_stabnet_fwd_b16'] = {'us_backbone_torch_fp32': t_backbone, 'us_warp_stage_C1': t_warp, 'us_total': t_total,
+                                  'warp_share_pct': 100 * t_warp / t_total,
+                                  'note': 'backbone = torch/cuDNN ResNet-50-v2-shaped carrier at random init (not a kernel-writing target); '
+                                          'warp stage = get_4_pts + slice + K1 + K2 on the 1-channel current frame'}
+print(json.dumps(res, indent=1))
