@@ -133,7 +133,7 @@ int mgw_warp_fwd(const float* U, const float* Hs, int N, int H, int W, int C, in
     REQUIRE(!img || aligned(img, 8), "mgw_warp_fwd: img must be 8-byte aligned");
     const WarpShape s{N, H, W, C, H, W, gh, gw};
     cudaStream_t st = (cudaStream_t)stream;
-    int rc;
+    int rc = MGW_OK;
     if (!cell_idx && use_tma_fwd(s, U, out, black, img, &rc)) return launch_warp_fwd_tma(U, Hs, s, out, black, img, nullptr, nullptr, st);
     if (rc != MGW_OK) return rc;
     return launch_warp_fwd_generic(U, Hs, s, false, out, black, img, cell_idx, st);
@@ -231,7 +231,7 @@ int mgw_mesh_warp_img_loss_fwd(const float* U, const float* theta, const float* 
     cudaStream_t st = (cudaStream_t)stream;
     const WarpShape s{N, H, W, C, H, W, gh, gw};
     TRY(launch_solve_h_fwd(theta, N, gh, gw, Hs, st));
-    int rc;
+    int rc = MGW_OK;
     if (use_tma_fwd(s, U, out, black, img, &rc)) {
         TRY(check_memset(cudaMemsetAsync(sums, 0, sizeof(float) * 2 * N, st), "memset sums"));
         return launch_warp_fwd_tma(U, Hs, s, out, black, img, y, sums, st);
