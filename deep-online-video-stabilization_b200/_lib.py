@@ -7,7 +7,7 @@ import ctypes
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-SO = os.path.join(HERE, 'libmgw_b200.so')
+SO = os.path.join(HERE, os.environ.get('MGW_SO_NAME', 'libmgw_b200.so'))      # MGW_SO_NAME selects an A/B build (tuning only)
 
 c_f = ctypes.c_void_p      # device pointers travel as raw addresses
 c_i = ctypes.c_int

@@ -13,7 +13,7 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
-SO = os.path.join(HERE, 'libmgw_b200.so')
+SO = os.path.join(HERE, os.environ.get('MGW_SO_NAME', 'libmgw_b200.so'))       # MGW_SO_NAME / MGW_EXTRA_FLAGS: A/B builds for tuning
 SOURCES = ['mgw_capi.cu', 'mgw_solve.cu', 'mgw_warp_generic.cu', 'mgw_warp_tma.cu', 'mgw_interp.cu', 'mgw_loss.cu']
 FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17', '-fmad=false',
          '--expt-relaxed-constexpr', '-Xcompiler', '-fPIC,-O2,-fvisibility=hidden', '-cudart', 'static']
@@ -31,13 +31,13 @@ def build(force=False, verbose=False):
         return SO
     nvcc = os.environ.get('NVCC', '/usr/local/cuda/bin/nvcc')
     objs = []
-    bdir = os.path.join(HERE, 'build')
+    bdir = os.path.join(HERE, 'build', os.path.basename(SO))
     os.makedirs(bdir, exist_ok=True)
     procs = []
     for src in SOURCES:
         obj = os.path.join(bdir, src.replace('.cu', '.o'))
         objs.append(obj)
-        cmd = [nvcc] + FLAGS + (['-Xptxas', '-v'] if verbose else []) + ['-c', os.path.join(CSRC, src), '-o', obj]
+        cmd = [nvcc] + FLAGS + os.environ.get('MGW_EXTRA_FLAGS', '').split() + (['-Xptxas', '-v'] if verbose else []) + ['-c', os.path.join(CSRC, src), '-o', obj]
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
     failed = False
     for src, p in procs:

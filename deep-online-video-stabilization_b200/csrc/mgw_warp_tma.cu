@@ -163,10 +163,13 @@ __device__ __forceinline__ float blend4(float ax, float bx, float ay, float by, 
 }
 
 // ------------------------------------------------------------------------------------------------ forward
+#ifndef MGW_FWD_MINB
+#define MGW_FWD_MINB (NT == 256 ? (LOSS ? 3 : 4) : 2)
+#endif
 // LOSS = true fuses the img_loss epilogue (s_net_bundle_nobm.py:347-352) onto the warped tile: per-sample
 // sums[n] += (sum over owned pixels of ((out - y)*(1-black))^2, sum of (1-black)).
 template <int C, int TW, int K, int NT, bool LOSS>
-__global__ void __launch_bounds__(NT, NT == 256 ? (LOSS ? 3 : 4) : 2)
+__global__ void __launch_bounds__(NT, MGW_FWD_MINB)
 warp_fwd_tma_kernel(const __grid_constant__ CUtensorMap mapU, const __grid_constant__ CUtensorMap mapOut,
                     const float* __restrict__ U, const float* __restrict__ Hs, const __grid_constant__ TileCfg cfg,
                     float* __restrict__ out, float* __restrict__ img, float* __restrict__ black,
@@ -302,11 +305,7 @@ warp_fwd_tma_kernel(const __grid_constant__ CUtensorMap mapU, const __grid_const
 constexpr float kMagic = 12582912.0f;          // 1.5 * 2^23
 constexpr int kMagicBits = 0x4B400000;
 __device__ __forceinline__ int fixed_of(float w, float gs) { return __float_as_int(__fmaf_rn(w, gs, kMagic)) - kMagicBits; }
-__device__ __forceinline__ float float_of_fixed(int v)
-{
-    // exact for |v| < 2^22; larger sums (many coincident taps) take the conversion instruction
-    return (abs(v) < (1 << 22)) ? __fsub_rn(__int_as_float(v + kMagicBits), kMagic) : (float)v;
-}
+__device__ __forceinline__ float float_of_fixed(int v) { return (float)v; }      // sums of coincident taps may exceed 2^22: plain I2F
 
 // dH terms of one pixel accumulated into the thread's 8 partial sums
 __device__ __forceinline__ void accumulate_dh(float (&dh)[8], float gxn, float gyn, float xn, float yn, float zs, float xt, float yt)
@@ -329,8 +328,11 @@ struct LossBwd {
     float kscale;           // upstream * 2 / batch
 };
 
+#ifndef MGW_BWD_MINB
+#define MGW_BWD_MINB (NT == 256 ? (K <= 3 ? 4 : 3) : 2)
+#endif
 template <int C, int TW, int K, int NT, bool LOSS>
-__global__ void __launch_bounds__(NT, NT == 256 ? 3 : 2)
+__global__ void __launch_bounds__(NT, MGW_BWD_MINB)
 warp_bwd_tma_kernel(const __grid_constant__ CUtensorMap mapU, const __grid_constant__ CUtensorMap mapDU,
                     const float* __restrict__ U, const float* __restrict__ Hs, const float* __restrict__ d_out,
                     const float* __restrict__ d_img, const __grid_constant__ TileCfg cfg, float* __restrict__ dU,
@@ -383,7 +385,9 @@ warp_bwd_tma_kernel(const __grid_constant__ CUtensorMap mapU, const __grid_const
     }
     if (dU) {
         int4* a4 = reinterpret_cast<int4*>(s_acc);
-        for (int i = tid; i < G::kBoxF / 4; i += NT) a4[i] = make_int4(0, 0, 0, 0);
+#pragma unroll
+        for (int i = 0; i < (G::kBoxF / 4 + NT - 1) / NT; ++i)
+            if (i * NT + tid < G::kBoxF / 4) a4[i * NT + tid] = make_int4(0, 0, 0, 0);
     }
     __syncthreads();                                  // barrier initialised
     if (tid < 32) {
@@ -397,30 +401,25 @@ warp_bwd_tma_kernel(const __grid_constant__ CUtensorMap mapU, const __grid_const
     }
     // ---- per-tile fixed-point scale from max|d_out| (Inf/NaN anywhere in the tile disables the fixed-point path)
     if (dU) {
-        float m = 0.0f;
-        bool bad = false;
+        // max over |d_out| as unsigned bit patterns: Inf/NaN (>= 0x7f800000) win the max, one REDUX per warp
+        unsigned m = 0u;
 #pragma unroll
         for (int k = 0; k < K; ++k)
 #pragma unroll
-            for (int ch = 0; ch < C; ++ch) {
-                const float v = fabsf(gout[k][ch]);
-                m = fmaxf(m, v);
-                bad = bad || !(v <= 3.0e38f);
-            }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-        bad = __any_sync(0xffffffffu, bad);
-        if (lane == 0) ti->wmax[warp] = bad ? __int_as_float(0x7f800000) : m;
+            for (int ch = 0; ch < C; ++ch) m = max(m, (unsigned)__float_as_int(gout[k][ch]) & 0x7fffffffu);
+        m = __reduce_max_sync(0xffffffffu, m);
+        if (lane == 0) ti->wmax[warp] = __int_as_float((int)m);
     }
     __syncthreads();                                  // wmax, box and the zeroed accumulator are visible
     const int bx0 = ti->bx0, by0 = ti->by0;
     int fixed = 0;
     float scale = 0.0f, inv_scale = 0.0f;
     if (dU) {
-        float mm = 0.0f;
+        unsigned mb = 0u;
 #pragma unroll
-        for (int w = 0; w < NT / 32; ++w) mm = fmaxf(mm, ti->wmax[w]);
-        const int e = ((__float_as_int(mm) >> 23) & 0xff) - 127;            // floor(log2 mm) for normal mm
+        for (int w = 0; w < NT / 32; ++w) mb = max(mb, (unsigned)__float_as_int(ti->wmax[w]));
+        const float mm = __int_as_float((int)mb);
+        const int e = (int)(mb >> 23) - 127;                                // floor(log2 mm) for normal mm; 128 for Inf/NaN
         // quantum = 2^-22 of the tile's max|d_out| (tap weights are in [0,1] on this path, so |w*g*scale| < 2^22), 9 bits
         // of headroom = up to 512 coincident full-size taps per word; tiles magnified beyond ~4x4 (area test) take the
         // fp32 path instead
@@ -522,11 +521,30 @@ warp_bwd_tma_kernel(const __grid_constant__ CUtensorMap mapU, const __grid_const
             }
         }
     }
-    // dH: warp shuffle -> shared -> one partial per tile
+    // dH: halving butterfly (9 shuffles for the 8 sums instead of 40) -> shared -> one partial per tile.
+    // After the three halving steps lane l holds term (l>>2)&7 summed over the lanes that share l's low two bits ... the
+    // last two steps finish the sum, so lanes 0,4,..,28 hold terms 0..7.
+    {
+        float v4[4], v2[2], v1;
+        const bool hi16 = lane & 16, hi8 = lane & 8, hi4 = lane & 4;
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-        const float v = warp_sum(dh[k]);
-        if (lane == 0) s_red[warp * 8 + k] = v;
+        for (int i = 0; i < 4; ++i) {
+            const float send = hi16 ? dh[i] : dh[i + 4], keep = hi16 ? dh[i + 4] : dh[i];
+            v4[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+        }
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            const float send = hi8 ? v4[i] : v4[i + 2], keep = hi8 ? v4[i + 2] : v4[i];
+            v2[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+        }
+        {
+            const float send = hi4 ? v2[0] : v2[1], keep = hi4 ? v2[1] : v2[0];
+            v1 = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+        }
+        v1 += __shfl_xor_sync(0xffffffffu, v1, 2);
+        v1 += __shfl_xor_sync(0xffffffffu, v1, 1);
+        // lane l now holds term  4*bit4(l) + 2*bit3(l) + bit2(l)
+        if ((lane & 3) == 0) s_red[warp * 8 + ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1)] = v1;
     }
     __syncthreads();                                  // also orders every shared atomic before the conversion below
     if (tid < 8) {
@@ -538,10 +556,14 @@ warp_bwd_tma_kernel(const __grid_constant__ CUtensorMap mapU, const __grid_const
     if (fixed) {
         // fixed point -> fp32 in place, then ONE TMA reduce-add of the whole box into dU
         int4* a4 = reinterpret_cast<int4*>(s_acc);
-        for (int i = tid; i < G::kBoxF / 4; i += NT) {
-            const int4 v = a4[i];
-            reinterpret_cast<float4*>(s_acc)[i] = make_float4(float_of_fixed(v.x) * inv_scale, float_of_fixed(v.y) * inv_scale,
-                                                              float_of_fixed(v.z) * inv_scale, float_of_fixed(v.w) * inv_scale);
+#pragma unroll
+        for (int i = 0; i < (G::kBoxF / 4 + NT - 1) / NT; ++i) {
+            const int j = i * NT + tid;
+            if (j < G::kBoxF / 4) {
+                const int4 v = a4[j];
+                reinterpret_cast<float4*>(s_acc)[j] = make_float4(float_of_fixed(v.x) * inv_scale, float_of_fixed(v.y) * inv_scale,
+                                                                  float_of_fixed(v.z) * inv_scale, float_of_fixed(v.w) * inv_scale);
+            }
         }
         tma::fence_proxy_async();
         __syncthreads();
