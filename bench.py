@@ -132,7 +132,7 @@ def main():
     ap.add_argument('--batch', type=int, default=32, help='frames per GPU')
     ap.add_argument('--cpu-sample', type=int, default=4, help='frames per CPU-baseline step')
     ap.add_argument('--no-cpu-baseline', action='store_true', help='skip the CPU leg (profiling runs)')
-    ap.add_argument('--kernel-impl', default='auto', choices=['auto', 'generic', 'tma'])
+    ap.add_argument('--kernel-impl', default='auto', choices=['auto', 'generic', 'tma', 'pipe'])
     ap.add_argument('--no-graph', action='store_true', help='launch the step eagerly instead of replaying CUDA graphs')
     args = ap.parse_args()
     if args.impl == 'reference':

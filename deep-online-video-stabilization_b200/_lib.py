@@ -80,4 +80,4 @@ def launch_count():
 
 def set_impl(mode):
     """'auto' | 'generic' | 'tma'"""
-    check(lib.mgw_set_impl({'auto': 0, 'generic': 1, 'tma': 2}[mode]), 'mgw_set_impl')
+    check(lib.mgw_set_impl({'auto': 0, 'generic': 1, 'tma': 2, 'pipe': 3}[mode]), 'mgw_set_impl')

@@ -80,7 +80,7 @@ uint64_t mgw_launch_count(void) { return g_launches.load(std::memory_order_relax
 
 int mgw_set_impl(int impl)
 {
-    REQUIRE(impl >= 0 && impl <= 2, "mgw_set_impl: impl must be 0 (auto), 1 (generic) or 2 (tma)");
+    REQUIRE(impl >= 0 && impl <= 3, "mgw_set_impl: impl must be 0 (auto), 1 (generic), 2 (tma tiles) or 3 (tma pipeline)");
     g_impl.store(impl);
     return MGW_OK;
 }
@@ -118,10 +118,22 @@ static bool use_tma_fwd(const WarpShape& s, const float* U, const float* out, co
 {
     *rc = MGW_OK;
     const int mode = impl_mode();
-    if (mode == 1) return false;
+    if (mode == 1 || mode == 3) return false;
     const bool ok = tma_fwd_supported(s) && aligned(U, 16) && (!out || aligned(out, 16)) && (!black || aligned(black, 16)) &&
                     (!img || aligned(img, 16));
     if (!ok && mode == 2) *rc = set_error(MGW_ERR_UNSUPPORTED, "TMA path required (mgw_set_impl(2)) but shape/alignment does not allow it");
+    return ok;
+}
+
+// the persistent pipeline serves the full call (warped image + maps + mask); partial calls take the one-tile-per-CTA kernels
+static bool use_pipe_fwd(const WarpShape& s, const float* U, const float* out, const float* black, const float* img, int* rc)
+{
+    *rc = MGW_OK;
+    const int mode = impl_mode();
+    if (mode == 1 || mode == 2) return false;
+    const bool ok = out && black && img && pipe_fwd_supported(s) && aligned(U, 16) && aligned(out, 16) && aligned(black, 16) &&
+                    aligned(img, 16);
+    if (!ok && mode == 3) *rc = set_error(MGW_ERR_UNSUPPORTED, "pipeline path required (mgw_set_impl(3)) but shape/alignment does not allow it");
     return ok;
 }
 
@@ -134,6 +146,8 @@ int mgw_warp_fwd(const float* U, const float* Hs, int N, int H, int W, int C, in
     const WarpShape s{N, H, W, C, H, W, gh, gw};
     cudaStream_t st = (cudaStream_t)stream;
     int rc = MGW_OK;
+    if (!cell_idx && use_pipe_fwd(s, U, out, black, img, &rc)) return launch_warp_fwd_pipe(U, Hs, s, out, black, img, st);
+    if (rc != MGW_OK) return rc;
     if (!cell_idx && use_tma_fwd(s, U, out, black, img, &rc)) return launch_warp_fwd_tma(U, Hs, s, out, black, img, nullptr, nullptr, st);
     if (rc != MGW_OK) return rc;
     return launch_warp_fwd_generic(U, Hs, s, false, out, black, img, cell_idx, st);
@@ -155,8 +169,8 @@ static int warp_bwd_core(const float* U, const float* Hs, const float* d_out, co
     const int mode = impl_mode();
     const bool tma_ok = mode != 1 && workspace && tma_bwd_supported(s) && aligned(U, 16) && (!dU || aligned(dU, 16)) &&
                         (!d_img || aligned(d_img, 8));
-    if (!tma_ok && mode == 2)
-        return set_error(MGW_ERR_UNSUPPORTED, "TMA path required (mgw_set_impl(2)) but shape/alignment/workspace does not allow it");
+    if (!tma_ok && mode >= 2)      // the backward has one TMA family (tiles); mode 3 only differs in the forward
+        return set_error(MGW_ERR_UNSUPPORTED, "TMA path required (mgw_set_impl(2|3)) but shape/alignment/workspace does not allow it");
     if (tma_ok) {
         int np = 0;
         TRY(launch_warp_bwd_tma(U, Hs, d_out, d_img, s, dU, (float*)workspace, &np, fl, st));

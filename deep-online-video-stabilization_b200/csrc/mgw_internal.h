@@ -75,4 +75,9 @@ size_t tma_bwd_workspace_bytes(const WarpShape& s);
 int launch_warp_bwd_tma(const float* U, const float* Hs, const float* d_out, const float* d_img, const WarpShape& s,
                         float* dU, float* dHs_part, int* nparts, const FusedImgLoss* fl, cudaStream_t st);
 
+// mgw_warp_pipe.cu : forward as a persistent warp-specialised pipeline over TMA-staged tiles (serves the full call:
+// out + black + img)
+bool pipe_fwd_supported(const WarpShape& s);
+int launch_warp_fwd_pipe(const float* U, const float* Hs, const WarpShape& s, float* out, float* black, float* img, cudaStream_t st);
+
 }  // namespace mgw

@@ -28,6 +28,19 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes)
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
 
+// plain arrival (release): a consumer warp hands a pipeline stage back to the producer
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// named barrier among the first `count` threads' warps of a role (barrier 0 is __syncthreads)
+template <int ID, int COUNT>
+__device__ __forceinline__ void named_bar_sync()
+{
+    asm volatile("bar.sync %0, %1;" ::"n"(ID), "n"(COUNT) : "memory");
+}
+
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
 {
     asm volatile(
@@ -62,6 +75,12 @@ __device__ __forceinline__ void reduce_add_3d(const CUtensorMap* map, const void
 __device__ __forceinline__ void commit_group() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 // smem sources may be reused / the CTA may exit once the bulk operations have READ them
 __device__ __forceinline__ void wait_group_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+
+// coalesced 16-byte fp32 reduction into global memory (SASS RED.E.ADD.F32x4 ... no return value)
+__device__ __forceinline__ void red_add_v4(float* dst, float a, float b, float c, float d)
+{
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
 
 __device__ __forceinline__ void prefetch_map(const CUtensorMap* map)
 {

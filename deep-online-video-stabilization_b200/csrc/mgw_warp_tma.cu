@@ -18,35 +18,11 @@
 // Every tap is checked against the staged box; taps outside it (folded cells, extreme magnification, far
 // out-of-range pixels) and weights outside [-1,1] fall back to global loads / global fp32 atomics, so results never
 // depend on the box heuristic.  Arithmetic is mgw_device.cuh's, bit-identical to the generic kernels and the C oracle.
-#include <cuda.h>
-#include <cstdio>
-#include <cstdlib>
-
-#include "mgw_internal.h"
-#include "mgw_tma.cuh"
+#include "mgw_tile.cuh"
 
 namespace mgw {
 
-#define TRY_RC(expr) do { const int rc_ = (expr); if (rc_ != MGW_OK) return rc_; } while (0)
-
 constexpr int kMaxWarps = 16;
-
-constexpr int kMaxTilesPerAxis = 128;
-
-// One tile row (or column) of the image: which cell it lies in, where it starts, and from where it OWNS pixels
-// (edge tiles are shifted inward so that every tile is full; the overlap is owned by the earlier tile).
-struct AxisTab {
-    unsigned short start[kMaxTilesPerAxis];
-    unsigned short vstart[kMaxTilesPerAxis];
-    unsigned char cell[kMaxTilesPerAxis];
-    unsigned char part[kMaxTilesPerAxis];
-};
-
-struct TileCfg {
-    int N, H, W, gh, gw;
-    int parts_y, parts_x;           // max tiles per cell (backward partial layout)
-    AxisTab rows, cols;             // grid = (cols, rows, N): blockIdx is the tile, no index arithmetic on the device
-};
 
 template <int C, int TW, int K, int NT>
 struct Geo {
@@ -221,8 +197,7 @@ warp_fwd_tma_kernel(const __grid_constant__ CUtensorMap mapU, const __grid_const
             const float ys = __fadd_rn(__fmaf_rn(Hc[4], yt, hx3), Hc[5]);
             float zs = __fadd_rn(__fmaf_rn(Hc[7], yt, hx6), Hc[8]);
             zs = __fadd_rn(zs, (zs >= 0.0f) ? 1e-8f : -1e-8f);
-            xn[k] = __fdiv_rn(xs, zs);
-            yn[k] = __fdiv_rn(ys, zs);
+            div2_rn(xs, ys, zs, xn[k], yn[k]);
             // x_map,y_map and black_pix are 8 / 4 contiguous bytes per lane: plain coalesced stores, no staging
             const float bk = black_of(xn[k], yn[k]);
             if (img) reinterpret_cast<float2*>(img)[p] = make_float2(xn[k], yn[k]);
@@ -311,6 +286,16 @@ __device__ __forceinline__ float float_of_fixed(int v) { return (float)v; }     
 __device__ __forceinline__ void accumulate_dh(float (&dh)[8], float gxn, float gyn, float xn, float yn, float zs, float xt, float yt)
 {
     const float rz = __frcp_rn(zs);
+    const float dxs = gxn * rz, dys = gyn * rz;
+    const float dzs = -(gxn * xn + gyn * yn) * rz;
+    dh[0] = fmaf(dxs, xt, dh[0]); dh[1] = fmaf(dxs, yt, dh[1]); dh[2] += dxs;
+    dh[3] = fmaf(dys, xt, dh[3]); dh[4] = fmaf(dys, yt, dh[4]); dh[5] += dys;
+    dh[6] = fmaf(dzs, xt, dh[6]); dh[7] = fmaf(dzs, yt, dh[7]);
+}
+
+// the same with the reciprocal of zs already at hand (the shared-reciprocal division of the fast path)
+__device__ __forceinline__ void accumulate_dh_r(float (&dh)[8], float gxn, float gyn, float xn, float yn, float rz, float xt, float yt)
+{
     const float dxs = gxn * rz, dys = gyn * rz;
     const float dzs = -(gxn * xn + gyn * yn) * rz;
     dh[0] = fmaf(dxs, xt, dh[0]); dh[1] = fmaf(dxs, yt, dh[1]); dh[2] += dxs;
@@ -447,19 +432,21 @@ warp_bwd_tma_kernel(const __grid_constant__ CUtensorMap mapU, const __grid_const
                 const float ys = __fadd_rn(__fmaf_rn(Hc[4], yt, hx3), Hc[5]);
                 float zs = __fadd_rn(__fmaf_rn(Hc[7], yt, hx6), Hc[8]);
                 zs = __fadd_rn(zs, (zs >= 0.0f) ? 1e-8f : -1e-8f);
-                const float xn = __fdiv_rn(xs, zs), yn = __fdiv_rn(ys, zs);
+                float xn, yn;
+                const float rz = div2_rn(xs, ys, zs, xn, yn);
                 const FastTaps t = make_taps_interior(xn, yn, cfg.H, cfg.W);
                 const int ia = ((t.y0 - by0) * G::kRowF + (t.x0 - bx0) * C);
                 const float* pa = s_src + ia;
                 int* qa = s_acc + ia;
                 const float wa = t.ax * t.ay, wb = t.ax * t.by, wc = t.bx * t.ay, wd = t.bx * t.by;
-                float gx = 0.0f, gy = 0.0f;
+                // gx = sum_c g_c [(Ic-Ia) ay + (Id-Ib) by], gy = sum_c g_c [(Ib-Ia) ax + (Id-Ic) bx], with the channel sums taken
+                // per tap first (4 FMAs per channel instead of 10 operations)
+                float sa = 0.0f, sb = 0.0f, sc = 0.0f, sd = 0.0f;
 #pragma unroll
                 for (int ch = 0; ch < C; ++ch) {
                     const float gch = gout[k][ch];
-                    const float Ia = pa[ch], Ib = pa[G::kRowF + ch], Ic = pa[C + ch], Id = pa[G::kRowF + C + ch];
-                    gx = fmaf(gch, fmaf(Ic - Ia, t.ay, (Id - Ib) * t.by), gx);
-                    gy = fmaf(gch, fmaf(Ib - Ia, t.ax, (Id - Ic) * t.bx), gy);
+                    sa = fmaf(gch, pa[ch], sa); sb = fmaf(gch, pa[G::kRowF + ch], sb);
+                    sc = fmaf(gch, pa[C + ch], sc); sd = fmaf(gch, pa[G::kRowF + C + ch], sd);
                     if (dU) {
                         const float gs = gch * scale;
                         atomicAdd(qa + ch, fixed_of(wa, gs));
@@ -468,7 +455,8 @@ warp_bwd_tma_kernel(const __grid_constant__ CUtensorMap mapU, const __grid_const
                         atomicAdd(qa + G::kRowF + C + ch, fixed_of(wd, gs));
                     }
                 }
-                accumulate_dh(dh, fmaf(gx, halfW, gimg[k][0]), fmaf(gy, halfH, gimg[k][1]), xn, yn, zs, xt, yt);
+                const float gx = fmaf(sc - sa, t.ay, (sd - sb) * t.by), gy = fmaf(sb - sa, t.ax, (sd - sc) * t.bx);
+                accumulate_dh_r(dh, fmaf(gx, halfW, gimg[k][0]), fmaf(gy, halfH, gimg[k][1]), xn, yn, rz, xt, yt);
             }
         }
     } else {
@@ -575,61 +563,6 @@ warp_bwd_tma_kernel(const __grid_constant__ CUtensorMap mapU, const __grid_const
     }
 }
 
-// ------------------------------------------------------------------------------------------------ host side
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-static EncodeTiledFn encode_fn()
-{
-    static EncodeTiledFn fn = nullptr;
-    if (!fn) {
-        void* p = nullptr;
-        cudaDriverEntryPointQueryResult q;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
-            q == cudaDriverEntryPointSuccess)
-            fn = reinterpret_cast<EncodeTiledFn>(p);
-    }
-    return fn;
-}
-
-// 3-D view [N][rows][inner floats] of an NHWC tensor, box = [1][box_rows][box_inner]
-static int make_map(CUtensorMap* m, const void* base, int inner, int rows, int N, int box_inner, int box_rows)
-{
-    EncodeTiledFn enc = encode_fn();
-    if (!enc) return set_error(MGW_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
-    const cuuint64_t dims[3] = {(cuuint64_t)inner, (cuuint64_t)rows, (cuuint64_t)N};
-    const cuuint64_t strides[2] = {(cuuint64_t)inner * 4, (cuuint64_t)inner * 4 * rows};
-    const cuuint32_t box[3] = {(cuuint32_t)box_inner, (cuuint32_t)box_rows, 1};
-    const cuuint32_t es[3] = {1, 1, 1};
-    const CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void*>(base), dims, strides, box, es,
-                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) return set_error(MGW_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) inner=%d rows=%d box=%dx%d", (int)r, inner, rows, box_inner, box_rows);
-    return MGW_OK;
-}
-
-// fills the axis table; returns the tile count (or -1 if it does not fit) and the max tiles per cell
-static int fill_axis(AxisTab* tab, int ncell, int cell_px, int total, int T, int* max_per_cell)
-{
-    int n = 0, mx = 0;
-    for (int c = 0; c < ncell; ++c) {
-        const int s = c * cell_px, len = (c == ncell - 1) ? total - s : cell_px;      // the last cell absorbs the remainder
-        const int nt = (len + T - 1) / T;
-        for (int t = 0; t < nt; ++t) {
-            if (n >= kMaxTilesPerAxis) return -1;
-            const int vstart = s + t * T;                          // first row/col the tile OWNS
-            const int start = vstart < s + len - T ? vstart : s + len - T;      // edge tiles are shifted inward
-            tab->start[n] = (unsigned short)start; tab->vstart[n] = (unsigned short)vstart;
-            tab->cell[n] = (unsigned char)c; tab->part[n] = (unsigned char)t;
-            ++n;
-        }
-        mx = nt > mx ? nt : mx;
-    }
-    *max_per_cell = mx;
-    return n;
-}
-
 struct Plan {
     TileCfg cfg;
     int TW, K, NT, TH, nty, ntx;
@@ -686,19 +619,6 @@ size_t tma_bwd_workspace_bytes(const WarpShape& s)
     Plan p;
     if (!plan(s, &p)) return 0;
     return (size_t)s.N * s.gh * s.gw * p.cfg.parts_y * p.cfg.parts_x * 8 * sizeof(float);
-}
-
-template <typename KernelT>
-static int allow_smem(KernelT kernel, bool* done_for_device, const char* what)
-{
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (!done_for_device[dev & 63]) {
-        if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess)
-            return set_error(MGW_ERR_CUDA, "cudaFuncSetAttribute(%s): %s", what, cudaGetErrorString(cudaGetLastError()));
-        done_for_device[dev & 63] = true;
-    }
-    return MGW_OK;
 }
 
 template <int C, int TW, int K, int NT>

@@ -174,6 +174,25 @@ def test_tma_path_is_taken_and_matches_generic(mgw, name):
     mgw.set_impl('auto')
 
 
+@pytest.mark.parametrize('name', TMA_MESH_CASES + FULL_MESH_CASES)
+def test_pipe_path_is_taken_and_matches_generic(mgw, name):
+    """set_impl('pipe') (forward as a persistent warp-specialised pipeline) errors out instead of falling back; == generic bit for bit."""
+    g = load_golden(name)
+    U, d_out, d_img = golden_inputs(name, g)
+    Ud, Hd = dev(U), dev(g['ref_Hs'])
+    mgw.set_impl('generic')
+    o_g, b_g, i_g, _ = mgw.ops.warp_fwd(Ud, Hd)
+    mgw.set_impl('pipe')
+    o_t, b_t, i_t, _ = mgw.ops.warp_fwd(Ud, Hd)
+    assert torch.equal(o_g.view(torch.int32), o_t.view(torch.int32)) and torch.equal(b_g, b_t)
+    assert torch.equal(i_g.view(torch.int32), i_t.view(torch.int32))
+    with pytest.raises(mgw.MgwError):                                          # the pipeline serves the full call only
+        mgw.ops.warp_fwd(Ud, Hd, want_black=False, want_img=False)
+    o_r = mgw.ops.warp_fwd(Ud, Hd)[0]                                          # run to run
+    assert torch.equal(o_r.view(torch.int32), o_t.view(torch.int32))
+    mgw.set_impl('auto')
+
+
 def test_tma_rejects_shapes_it_cannot_serve(mgw):
     g = load_golden('mesh_ragged_c1')            # 50 x 70: row pitch not a multiple of 16 bytes
     U, _, _ = golden_inputs('mesh_ragged_c1', g)
