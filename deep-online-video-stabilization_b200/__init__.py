@@ -2,11 +2,12 @@
 
 Layout: csrc/ (CUDA kernels + C ABI, built into libmgw_b200.so), _lib.py (ctypes), ops.py (tensor carriers),
 functional.py (autograd), spatial_transformer3.py / spatial_transformer.py (reference-named operator modules),
-losses.py (vertex builder + fused loss epilogue), parallel.py (batch sharding + NCCL all-reduce).
+losses.py (vertex builder + fused loss epilogue), deploy.py (deploy-side colour-frame warp), parallel.py (batch sharding + NCCL all-reduce).
 """
-from . import _lib, functional, losses, ops, parallel, spatial_transformer, spatial_transformer3  # noqa: F401
+from . import _lib, deploy, functional, losses, ops, parallel, spatial_transformer, spatial_transformer3  # noqa: F401
 from ._lib import MgwError, launch_count, set_impl  # noqa: F401
 from .losses import feature_loss, get_4_pts, img_loss, temp_loss, transformer_img_loss  # noqa: F401
+from .deploy import warpRevBundle2  # noqa: F401
 from .spatial_transformer import interpolate  # noqa: F401
 from .spatial_transformer3 import transformer  # noqa: F401
 

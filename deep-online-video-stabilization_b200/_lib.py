@@ -27,12 +27,16 @@ SIGNATURES = {
     'mgw_warp_fwd': (c_i, [c_f, c_f] + [c_i] * 6 + [c_f, c_f, c_f, c_f, c_st]),
     'mgw_warp_bwd_workspace_bytes': (ctypes.c_size_t, [c_i] * 6),
     'mgw_warp_bwd': (c_i, [c_f, c_f, c_f, c_f] + [c_i] * 6 + [c_f, c_f, c_f, c_st]),
+    'mgw_warp_bwd_acc': (c_i, [c_f, c_f, c_f, c_f] + [c_i] * 6 + [c_f, c_f, c_f, c_st]),
     'mgw_mesh_warp_fwd': (c_i, [c_f, c_f] + [c_i] * 6 + [c_f, c_f, c_f, c_f, c_st]),
     'mgw_mesh_warp_bwd_workspace_bytes': (ctypes.c_size_t, [c_i] * 6),
     'mgw_mesh_warp_bwd': (c_i, [c_f, c_f, c_f, c_f, c_f] + [c_i] * 6 + [c_f, c_f, c_f, c_st]),
+    'mgw_mesh_warp_bwd_acc': (c_i, [c_f, c_f, c_f, c_f, c_f] + [c_i] * 6 + [c_f, c_f, c_f, c_st]),
     'mgw_mesh_warp_img_loss_fwd': (c_i, [c_f, c_f, c_f] + [c_i] * 6 + [c_f, c_f, c_f, c_f, c_f, c_st]),
     'mgw_mesh_warp_img_loss_bwd_workspace_bytes': (ctypes.c_size_t, [c_i] * 6),
     'mgw_mesh_warp_img_loss_bwd': (c_i, [c_f] * 7 + [c_fl, c_fl, c_f] + [c_i] * 6 + [c_f, c_f, c_f, c_st]),
+    'mgw_remap_bundle_u8_workspace_bytes': (ctypes.c_size_t, [c_i, c_i, c_i]),
+    'mgw_remap_bundle_u8': (c_i, [c_f, c_f, c_i, c_i, c_i, c_i, c_f, c_f, c_st]),
     'mgw_interp_fwd': (c_i, [c_f, c_f, c_f] + [c_i] * 6 + [c_f, c_st]),
     'mgw_interp_bwd': (c_i, [c_f, c_f, c_f, c_f] + [c_i] * 6 + [c_f, c_f, c_f, c_st]),
     'mgw_homography_warp_fwd': (c_i, [c_f, c_f] + [c_i] * 6 + [c_f, c_f, c_f, c_st]),

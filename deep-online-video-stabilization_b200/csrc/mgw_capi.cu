@@ -162,10 +162,11 @@ size_t mgw_warp_bwd_workspace_bytes(int N, int H, int W, int C, int gh, int gw)
 // shared by mgw_warp_bwd and mgw_mesh_warp_bwd: produces dH partials; returns their layout
 static int warp_bwd_core(const float* U, const float* Hs, const float* d_out, const float* d_img, const WarpShape& s,
                          float* dU, float* dHs_acc /*[cells,9]*/, void* workspace, const float** parts, int* nparts,
-                         int* part_stride, cudaStream_t st, const FusedImgLoss* fl = nullptr, float* d_out_scratch = nullptr)
+                         int* part_stride, cudaStream_t st, const FusedImgLoss* fl = nullptr, float* d_out_scratch = nullptr,
+                         bool zero_dU = true)
 {
     const size_t ncell = (size_t)s.N * s.gh * s.gw;
-    if (dU) TRY(check_memset(cudaMemsetAsync(dU, 0, sizeof(float) * (size_t)s.N * s.H * s.W * s.C, st), "memset dU"));
+    if (dU && zero_dU) TRY(check_memset(cudaMemsetAsync(dU, 0, sizeof(float) * (size_t)s.N * s.H * s.W * s.C, st), "memset dU"));
     const int mode = impl_mode();
     const bool tma_ok = mode != 1 && workspace && tma_bwd_supported(s) && aligned(U, 16) && (!dU || aligned(dU, 16)) &&
                         (!d_img || aligned(d_img, 8));
@@ -188,8 +189,8 @@ static int warp_bwd_core(const float* U, const float* Hs, const float* d_out, co
     return MGW_OK;
 }
 
-int mgw_warp_bwd(const float* U, const float* Hs, const float* d_out, const float* d_img, int N, int H, int W, int C,
-                 int gh, int gw, float* dU, float* dHs, void* workspace, void* stream)
+static int warp_bwd_impl(const float* U, const float* Hs, const float* d_out, const float* d_img, int N, int H, int W, int C,
+                         int gh, int gw, float* dU, float* dHs, void* workspace, void* stream, bool zero_dU)
 {
     REQUIRE(U && Hs && d_out && dHs, "mgw_warp_bwd: null pointer");
     TRY(validate_mesh_shape("mgw_warp_bwd", N, H, W, C, gh, gw));
@@ -197,13 +198,25 @@ int mgw_warp_bwd(const float* U, const float* Hs, const float* d_out, const floa
     const WarpShape s{N, H, W, C, H, W, gh, gw};
     cudaStream_t st = (cudaStream_t)stream;
     const float* parts; int np, ps;
-    TRY(warp_bwd_core(U, Hs, d_out, d_img, s, dU, dHs, workspace, &parts, &np, &ps, st));
+    TRY(warp_bwd_core(U, Hs, d_out, d_img, s, dU, dHs, workspace, &parts, &np, &ps, st, nullptr, nullptr, zero_dU));
     if (parts != dHs) {
         const int ncell = N * gh * gw;
         reduce_parts_kernel<<<(ncell * 9 + 127) / 128, 128, 0, st>>>(parts, np, ncell, dHs);
         TRY(check_launch("reduce_parts"));
     }
     return MGW_OK;
+}
+
+int mgw_warp_bwd(const float* U, const float* Hs, const float* d_out, const float* d_img, int N, int H, int W, int C,
+                 int gh, int gw, float* dU, float* dHs, void* workspace, void* stream)
+{
+    return warp_bwd_impl(U, Hs, d_out, d_img, N, H, W, C, gh, gw, dU, dHs, workspace, stream, true);
+}
+
+int mgw_warp_bwd_acc(const float* U, const float* Hs, const float* d_out, const float* d_img, int N, int H, int W, int C,
+                     int gh, int gw, float* dU, float* dHs, void* workspace, void* stream)
+{
+    return warp_bwd_impl(U, Hs, d_out, d_img, N, H, W, C, gh, gw, dU, dHs, workspace, stream, false);
 }
 
 int mgw_mesh_warp_fwd(const float* U, const float* theta, int N, int H, int W, int C, int gh, int gw, float* Hs,
@@ -220,8 +233,9 @@ size_t mgw_mesh_warp_bwd_workspace_bytes(int N, int H, int W, int C, int gh, int
     return align_up(sizeof(float) * (size_t)N * gh * gw * 9, 256) + mgw_warp_bwd_workspace_bytes(N, H, W, C, gh, gw);
 }
 
-int mgw_mesh_warp_bwd(const float* U, const float* theta, const float* Hs, const float* d_out, const float* d_img,
-                      int N, int H, int W, int C, int gh, int gw, float* dU, float* dtheta, void* workspace, void* stream)
+static int mesh_warp_bwd_impl(const float* U, const float* theta, const float* Hs, const float* d_out, const float* d_img,
+                              int N, int H, int W, int C, int gh, int gw, float* dU, float* dtheta, void* workspace, void* stream,
+                              bool zero_dU)
 {
     REQUIRE(U && theta && Hs && d_out && dtheta && workspace, "mgw_mesh_warp_bwd: null pointer");
     TRY(validate_mesh_shape("mgw_mesh_warp_bwd", N, H, W, C, gh, gw));
@@ -232,8 +246,20 @@ int mgw_mesh_warp_bwd(const float* U, const float* theta, const float* Hs, const
     const size_t off = align_up(sizeof(float) * (size_t)N * gh * gw * 9, 256);
     void* tma_ws = mgw_warp_bwd_workspace_bytes(N, H, W, C, gh, gw) ? (void*)((char*)workspace + off) : nullptr;
     const float* parts; int np, ps;
-    TRY(warp_bwd_core(U, Hs, d_out, d_img, s, dU, dHs_acc, tma_ws, &parts, &np, &ps, st));
+    TRY(warp_bwd_core(U, Hs, d_out, d_img, s, dU, dHs_acc, tma_ws, &parts, &np, &ps, st, nullptr, nullptr, zero_dU));
     return launch_solve_h_bwd(theta, Hs, parts, np, ps, N, gh, gw, dtheta, st);
+}
+
+int mgw_mesh_warp_bwd(const float* U, const float* theta, const float* Hs, const float* d_out, const float* d_img,
+                      int N, int H, int W, int C, int gh, int gw, float* dU, float* dtheta, void* workspace, void* stream)
+{
+    return mesh_warp_bwd_impl(U, theta, Hs, d_out, d_img, N, H, W, C, gh, gw, dU, dtheta, workspace, stream, true);
+}
+
+int mgw_mesh_warp_bwd_acc(const float* U, const float* theta, const float* Hs, const float* d_out, const float* d_img,
+                          int N, int H, int W, int C, int gh, int gw, float* dU, float* dtheta, void* workspace, void* stream)
+{
+    return mesh_warp_bwd_impl(U, theta, Hs, d_out, d_img, N, H, W, C, gh, gw, dU, dtheta, workspace, stream, false);
 }
 
 int mgw_mesh_warp_img_loss_fwd(const float* U, const float* theta, const float* y, int N, int H, int W, int C, int gh, int gw,
@@ -323,6 +349,20 @@ int mgw_homography_warp_bwd(const float* U, const float* theta, const float* d_o
     TRY(check_memset(cudaMemsetAsync(dtheta, 0, sizeof(float) * (size_t)N * 9, st), "memset dtheta"));
     TRY(launch_warp_bwd_generic(U, theta, d_out, nullptr, s, true, dU, dtheta, st));
     return launch_homography_finish_bwd(theta, dtheta, N, dtheta, st);
+}
+
+size_t mgw_remap_bundle_u8_workspace_bytes(int N, int H, int W)
+{
+    return (N > 0 && H >= 4 && W >= 4) ? remap_bundle_workspace_bytes(N, H, W) : 0;
+}
+
+int mgw_remap_bundle_u8(const uint8_t* img, const float* xy, int N, int H, int W, int C, uint8_t* dst, void* workspace, void* stream)
+{
+    REQUIRE(img && xy && dst && workspace, "mgw_remap_bundle_u8: null pointer");
+    REQUIRE(N > 0 && H >= 8 && W >= 8, "mgw_remap_bundle_u8: need N > 0, H >= 8, W >= 8 (got N=%d H=%d W=%d)", N, H, W);
+    REQUIRE(H <= 32767 && W <= 32767 && (long long)N * H * W < (1LL << 31), "mgw_remap_bundle_u8: image too large");
+    REQUIRE(aligned(xy, 8) && aligned(workspace, 8), "mgw_remap_bundle_u8: xy and workspace must be 8-byte aligned");
+    return launch_remap_bundle_u8(img, xy, N, H, W, C, dst, workspace, (cudaStream_t)stream);
 }
 
 int mgw_img_loss_fwd(const float* out, const float* y, const float* black, int N, int H, int W, int C, float* sums, void* stream)

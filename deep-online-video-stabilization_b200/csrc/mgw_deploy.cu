@@ -1,0 +1,145 @@
+// Deploy-side colour-frame warp: warpRevBundle2 of deploy_bundle.py:136-146.
+//   x_map, y_map (the operator's outputs, [N,H,W,2] interleaved)  --cv2.resize /4-->  small maps  --cv2.resize x4-->
+//   smoothed maps  --((m+1)/2*size)-->  pixel coordinates  --cv2.remap(INTER_LINEAR, constant border 0)-->  uint8 frame
+// Two launches: K5a writes the /4 maps (a 74 KB scratch at 288x512, L2 resident), K5b upsamples them per output pixel,
+// converts to OpenCV's 1/32-pixel fixed point and blends the uint8 taps with OpenCV's 15-bit integer weights.  The
+// arithmetic restates OpenCV's published algorithm (resize.cpp resizeGeneric_/HResizeLinear/VResizeLinear, plain C++
+// path; imgwarp.cpp remapBilinear) operation by operation: deploy_ref.py (test infrastructure) is the numpy statement of the same thing
+// and is pinned bit-exact against cv2 (tests/golden/deploy_remap.npz).  HBM-bound byte work: no tensor cores.
+#include "mgw_internal.h"
+
+namespace mgw {
+
+namespace {
+
+struct Lin { int i0, i1; float a0, a1; };
+
+// resize.cpp: inv_scale = dsize / (double)ssize, scale = 1. / inv_scale, fx = (float)((d + 0.5) * scale - 0.5)
+__device__ __forceinline__ float src_pos(int d, int n_out, int n_in)
+{
+    const double scale = 1.0 / ((double)n_out / (double)n_in);
+    return (float)(((double)d + 0.5) * scale - 0.5);
+}
+
+// horizontal taps: a tap outside the row is folded onto the border with weight 0
+__device__ __forceinline__ Lin hcoef(int d, int n_out, int n_in)
+{
+    float fx = src_pos(d, n_out, n_in);
+    int sx = (int)floorf(fx);
+    fx = __fsub_rn(fx, (float)sx);
+    if (sx < 0) { sx = 0; fx = 0.0f; }
+    if (sx >= n_in - 1) { sx = n_in - 1; fx = 0.0f; }
+    Lin l;
+    l.i0 = sx; l.i1 = min(sx + 1, n_in - 1); l.a0 = __fsub_rn(1.0f, fx); l.a1 = fx;
+    return l;
+}
+
+// vertical taps: row indices clamped, weights kept
+__device__ __forceinline__ Lin vcoef(int d, int n_out, int n_in)
+{
+    float fy = src_pos(d, n_out, n_in);
+    const int sy = (int)floorf(fy);
+    fy = __fsub_rn(fy, (float)sy);
+    Lin l;
+    l.i0 = min(max(sy, 0), n_in - 1); l.i1 = min(max(sy + 1, 0), n_in - 1); l.a0 = __fsub_rn(1.0f, fy); l.a1 = fy;
+    return l;
+}
+
+// one bilinear resize sample of an interleaved (x,y) map: rows first horizontally, then vertically, fp32 mul / add
+__device__ __forceinline__ float2 resize_sample(const float2* __restrict__ s, int sw, const Lin& h, const Lin& v)
+{
+    const float2 p00 = __ldg(s + (size_t)v.i0 * sw + h.i0), p01 = __ldg(s + (size_t)v.i0 * sw + h.i1);
+    const float2 p10 = __ldg(s + (size_t)v.i1 * sw + h.i0), p11 = __ldg(s + (size_t)v.i1 * sw + h.i1);
+    const float r0x = __fadd_rn(__fmul_rn(p00.x, h.a0), __fmul_rn(p01.x, h.a1));
+    const float r1x = __fadd_rn(__fmul_rn(p10.x, h.a0), __fmul_rn(p11.x, h.a1));
+    const float r0y = __fadd_rn(__fmul_rn(p00.y, h.a0), __fmul_rn(p01.y, h.a1));
+    const float r1y = __fadd_rn(__fmul_rn(p10.y, h.a0), __fmul_rn(p11.y, h.a1));
+    return make_float2(__fadd_rn(__fmul_rn(r0x, v.a0), __fmul_rn(r1x, v.a1)), __fadd_rn(__fmul_rn(r0y, v.a0), __fmul_rn(r1y, v.a1)));
+}
+
+__global__ void __launch_bounds__(256)
+maps_down_kernel(const float2* __restrict__ xy, int N, int H, int W, int h4, int w4, float2* __restrict__ small)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= N * h4 * w4) return;
+    const int c = t % w4, r = (t / w4) % h4, n = t / (w4 * h4);
+    const Lin h = hcoef(c, w4, W), v = vcoef(r, h4, H);
+    small[t] = resize_sample(xy + (size_t)n * H * W, W, h, v);
+}
+
+// cvRound(v) as x86 does it (cvtss2si: round half to even; out of range / NaN -> INT_MIN)
+__device__ __forceinline__ int cv_round(float v)
+{
+    return (fabsf(v) < 2147483648.0f) ? __float2int_rn(v) : (int)0x80000000;
+}
+
+template <int C>
+__global__ void __launch_bounds__(256)
+remap_up_kernel(const uint8_t* __restrict__ img, const float2* __restrict__ small, int N, int H, int W, int h4, int w4,
+                uint8_t* __restrict__ dst)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= N * H * W) return;
+    const int c = t % W, r = (t / W) % H, n = t / (W * H);
+    const Lin h = hcoef(c, W, w4), v = vcoef(r, H, h4);
+    const float2 m = resize_sample(small + (size_t)n * h4 * w4, w4, h, v);
+    // (map + 1) / 2 * size in fp32 (deploy_bundle.py:142-143)
+    const float xp = __fmul_rn(__fmul_rn(__fadd_rn(m.x, 1.0f), 0.5f), (float)W);
+    const float yp = __fmul_rn(__fmul_rn(__fadd_rn(m.y, 1.0f), 0.5f), (float)H);
+    // remapBilinear: 1/32-pixel fixed point, taps clamped to int16, 15-bit weights, constant border 0
+    const int sx = cv_round(__fmul_rn(xp, 32.0f)), sy = cv_round(__fmul_rn(yp, 32.0f));
+    const int ix = min(max(sx >> 5, -32768), 32767), iy = min(max(sy >> 5, -32768), 32767);
+    const int fx = sx & 31, fy = sy & 31;
+    const int w00 = (32 - fx) * (32 - fy) * 32, w01 = fx * (32 - fy) * 32, w10 = (32 - fx) * fy * 32, w11 = fx * fy * 32;
+    const bool x0 = (unsigned)ix < (unsigned)W, x1 = (unsigned)(ix + 1) < (unsigned)W;
+    const bool y0 = (unsigned)iy < (unsigned)H, y1 = (unsigned)(iy + 1) < (unsigned)H;
+    const uint8_t* base = img + (size_t)n * H * W * C;
+    const uint8_t* p00 = base + ((size_t)iy * W + ix) * C;
+    int acc[C];
+#pragma unroll
+    for (int ch = 0; ch < C; ++ch) acc[ch] = 1 << 14;
+    if (y0 && x0) {
+#pragma unroll
+        for (int ch = 0; ch < C; ++ch) acc[ch] += w00 * (int)__ldg(p00 + ch);
+    }
+    if (y0 && x1) {
+#pragma unroll
+        for (int ch = 0; ch < C; ++ch) acc[ch] += w01 * (int)__ldg(p00 + C + ch);
+    }
+    if (y1 && x0) {
+#pragma unroll
+        for (int ch = 0; ch < C; ++ch) acc[ch] += w10 * (int)__ldg(p00 + (size_t)W * C + ch);
+    }
+    if (y1 && x1) {
+#pragma unroll
+        for (int ch = 0; ch < C; ++ch) acc[ch] += w11 * (int)__ldg(p00 + (size_t)W * C + C + ch);
+    }
+    uint8_t* o = dst + (size_t)t * C;
+#pragma unroll
+    for (int ch = 0; ch < C; ++ch) o[ch] = (uint8_t)min(max(acc[ch] >> 15, 0), 255);
+}
+
+}  // namespace
+
+size_t remap_bundle_workspace_bytes(int N, int H, int W) { return sizeof(float) * 2 * (size_t)N * (H / 4) * (W / 4); }
+
+int launch_remap_bundle_u8(const uint8_t* img, const float* xy, int N, int H, int W, int C, uint8_t* dst, void* workspace,
+                           cudaStream_t st)
+{
+    const int h4 = H / 4, w4 = W / 4;       // int(height / rate), int(width / rate)
+    float2* small = reinterpret_cast<float2*>(workspace);
+    const int t1 = N * h4 * w4, t2 = N * H * W;
+    maps_down_kernel<<<(t1 + 255) / 256, 256, 0, st>>>(reinterpret_cast<const float2*>(xy), N, H, W, h4, w4, small);
+    int rc = check_launch("maps_down");
+    if (rc != MGW_OK) return rc;
+    const int grid = (t2 + 255) / 256;
+    switch (C) {
+    case 1: remap_up_kernel<1><<<grid, 256, 0, st>>>(img, small, N, H, W, h4, w4, dst); break;
+    case 3: remap_up_kernel<3><<<grid, 256, 0, st>>>(img, small, N, H, W, h4, w4, dst); break;
+    case 4: remap_up_kernel<4><<<grid, 256, 0, st>>>(img, small, N, H, W, h4, w4, dst); break;
+    default: return set_error(MGW_ERR_UNSUPPORTED, "remap_bundle_u8: C must be 1, 3 or 4 (got %d)", C);
+    }
+    return check_launch("remap_up");
+}
+
+}  // namespace mgw

@@ -80,4 +80,9 @@ int launch_warp_bwd_tma(const float* U, const float* Hs, const float* d_out, con
 bool pipe_fwd_supported(const WarpShape& s);
 int launch_warp_fwd_pipe(const float* U, const float* Hs, const WarpShape& s, float* out, float* black, float* img, cudaStream_t st);
 
+// mgw_deploy.cu : deploy-side colour-frame warp (deploy_bundle.py:136-146)
+size_t remap_bundle_workspace_bytes(int N, int H, int W);
+int launch_remap_bundle_u8(const uint8_t* img, const float* xy, int N, int H, int W, int C, uint8_t* dst, void* workspace,
+                           cudaStream_t st);
+
 }  // namespace mgw

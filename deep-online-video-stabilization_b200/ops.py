@@ -93,17 +93,27 @@ def _workspace(nbytes, dev):
     return torch.empty((max(nbytes, 256) + 255) // 256 * 64, device=dev, dtype=torch.float32) if nbytes else None
 
 
-def warp_bwd(U, Hs, d_out, d_img=None, want_dU=True):
+def _acc_target(U, accumulate_into):
+    """dU buffer of the accumulate variants: the caller's tensor, added to in place (never zero-filled by the library)."""
+    dU = _chk(accumulate_into, 'accumulate_into')
+    if dU.shape != U.shape or dU.device != U.device:
+        raise ValueError('accumulate_into must have the shape and device of U')
+    return dU
+
+
+def warp_bwd(U, Hs, d_out, d_img=None, want_dU=True, accumulate_into=None):
+    """accumulate_into: a [N,H,W,C] tensor that receives dU += gradient (mgw_warp_bwd_acc); otherwise dU is a fresh tensor."""
     U, Hs, d_out = _chk(U, 'U'), _chk(Hs, 'Hs'), _chk(d_out, 'd_out')
     d_img = None if d_img is None else _chk(d_img, 'd_img')
     n, h, w, c = _mesh_dims(U, Hs, 'Hs')
     gh, gw = Hs.shape[1:3]
-    dU = torch.empty_like(U) if want_dU else None
+    acc = accumulate_into is not None
+    dU = _acc_target(U, accumulate_into) if acc else (torch.empty_like(U) if want_dU else None)
     dHs = torch.empty_like(Hs)
     ws = _workspace(lib.mgw_warp_bwd_workspace_bytes(n, h, w, c, gh, gw), U.device)
+    fn = lib.mgw_warp_bwd_acc if acc else lib.mgw_warp_bwd
     with torch.cuda.device(U.device):
-        check(lib.mgw_warp_bwd(_p(U), _p(Hs), _p(d_out), _p(d_img), n, h, w, c, gh, gw, _p(dU), _p(dHs), _p(ws), _st()),
-              'mgw_warp_bwd')
+        check(fn(_p(U), _p(Hs), _p(d_out), _p(d_img), n, h, w, c, gh, gw, _p(dU), _p(dHs), _p(ws), _st()), 'mgw_warp_bwd')
     return dU, dHs
 
 
@@ -124,17 +134,19 @@ def mesh_warp_fwd(U, theta, want_out=True, want_black=True, want_img=True):
     return out, black, img, Hs
 
 
-def mesh_warp_bwd(U, theta, Hs, d_out, d_img=None, want_dU=True):
+def mesh_warp_bwd(U, theta, Hs, d_out, d_img=None, want_dU=True, accumulate_into=None):
     U, theta, Hs, d_out = _chk(U, 'U'), _chk(theta, 'theta'), _chk(Hs, 'Hs'), _chk(d_out, 'd_out')
     d_img = None if d_img is None else _chk(d_img, 'd_img')
     n, h, w, c = _mesh_dims(U, theta, 'theta')
     gh, gw = Hs.shape[1:3]
-    dU = torch.empty_like(U) if want_dU else None
+    acc = accumulate_into is not None
+    dU = _acc_target(U, accumulate_into) if acc else (torch.empty_like(U) if want_dU else None)
     dtheta = torch.empty_like(theta)
     ws = _workspace(lib.mgw_mesh_warp_bwd_workspace_bytes(n, h, w, c, gh, gw), U.device)
+    fn = lib.mgw_mesh_warp_bwd_acc if acc else lib.mgw_mesh_warp_bwd
     with torch.cuda.device(U.device):
-        check(lib.mgw_mesh_warp_bwd(_p(U), _p(theta), _p(Hs), _p(d_out), _p(d_img), n, h, w, c, gh, gw, _p(dU), _p(dtheta),
-                                    _p(ws), _st()), 'mgw_mesh_warp_bwd')
+        check(fn(_p(U), _p(theta), _p(Hs), _p(d_out), _p(d_img), n, h, w, c, gh, gw, _p(dU), _p(dtheta), _p(ws), _st()),
+              'mgw_mesh_warp_bwd')
     return dU, dtheta
 
 
@@ -288,3 +300,17 @@ def temp_loss_bwd(out1, black1, out2, black2, flow, sums, upstream):
         check(lib.mgw_temp_loss_bwd(_p(out1), _p(black1), _p(out2), _p(black2), _p(flow), _p(sums), float(upstream), n, h, w, c,
                                     _p(d1), _p(d2), _st()), 'mgw_temp_loss_bwd')
     return d1, d2
+
+
+def remap_bundle_u8(img, xy):
+    """deploy_bundle.py:136-146 on the device: img [N,H,W,C] uint8, xy [N,H,W,2] fp32 (x_map,y_map interleaved, the `img`
+    output of warp_fwd) -> [N,H,W,C] uint8.  One C-ABI call (two launches)."""
+    img, xy = _chk(img, 'img', torch.uint8), _chk(xy, 'xy')
+    if img.dim() != 4 or xy.dim() != 4 or xy.shape[3] != 2 or xy.shape[:3] != img.shape[:3]:
+        raise ValueError('img must be [N,H,W,C] uint8 and xy [N,H,W,2] (got %s, %s)' % (tuple(img.shape), tuple(xy.shape)))
+    n, h, w, c = img.shape
+    dst = torch.empty_like(img)
+    ws = torch.empty(max(lib.mgw_remap_bundle_u8_workspace_bytes(n, h, w) // 4, 2), device=img.device, dtype=torch.float32)
+    with torch.cuda.device(img.device):
+        check(lib.mgw_remap_bundle_u8(_p(img), _p(xy), n, h, w, c, _p(dst), _p(ws), _st()), 'mgw_remap_bundle_u8')
+    return dst

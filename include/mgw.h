@@ -77,6 +77,11 @@ MGW_API int mgw_warp_fwd(const float* U, const float* Hs, int N, int H, int W, i
 MGW_API size_t mgw_warp_bwd_workspace_bytes(int N, int H, int W, int C, int gh, int gw);
 MGW_API int mgw_warp_bwd(const float* U, const float* Hs, const float* d_out, const float* d_img, int N, int H, int W,
                  int C, int gh, int gw, float* dU, float* dHs, void* workspace, void* stream);
+/* The same, but dU is ACCUMULATED INTO (dU += gradient) and never zero-filled by the library: the caller owns its initial
+ * contents -- gradient accumulation across micro-batches, or a zero-fill issued earlier on another stream so that it
+ * overlaps the forward pass (what bench.py does).  dHs is still overwritten. */
+MGW_API int mgw_warp_bwd_acc(const float* U, const float* Hs, const float* d_out, const float* d_img, int N, int H, int W,
+                     int C, int gh, int gw, float* dU, float* dHs, void* workspace, void* stream);
 
 /* ---- fused a1-a5: spatial_transformer3.transformer(U, theta), :19-365 ---------------------------------
  * theta [N,gh+1,gw+1,2] mesh vertices.  Hs is an output too (deploy_bundle.py:54 fetches it). */
@@ -88,6 +93,10 @@ MGW_API size_t mgw_mesh_warp_bwd_workspace_bytes(int N, int H, int W, int C, int
 MGW_API int mgw_mesh_warp_bwd(const float* U, const float* theta, const float* Hs, const float* d_out, const float* d_img,
                       int N, int H, int W, int C, int gh, int gw, float* dU, float* dtheta, void* workspace,
                       void* stream);
+/* dU += gradient (see mgw_warp_bwd_acc); dtheta overwritten */
+MGW_API int mgw_mesh_warp_bwd_acc(const float* U, const float* theta, const float* Hs, const float* d_out, const float* d_img,
+                          int N, int H, int W, int C, int gh, int gw, float* dU, float* dtheta, void* workspace,
+                          void* stream);
 
 /* ---- fused a1-a5 + a8: transformer(U, theta) with the img_loss epilogue (s_net_bundle_nobm.py:332,347-352) ----------
  * Forward: as mgw_mesh_warp_fwd (out, black required) plus sums [N,2] = per-sample (sum ((out-y)(1-black))^2,
@@ -102,6 +111,15 @@ MGW_API int mgw_mesh_warp_img_loss_bwd(const float* U, const float* theta, const
                                const float* black, const float* sums, float upstream, float batch, const float* d_img,
                                int N, int H, int W, int C, int gh, int gw, float* dU, float* dtheta, void* workspace,
                                void* stream);
+
+/* ---- f1 (deploy side): warpRevBundle2(img, x_map, y_map), deploy_bundle.py:136-146 ---------------------------------
+ * img [N,H,W,C] uint8 (the unstable frame at network size), xy [N,H,W,2] = the operator's x_map,y_map (the `img` output of
+ * mgw_warp_fwd / mgw_mesh_warp_fwd) -> dst [N,H,W,C] uint8: maps smoothed by cv2.resize /4 then x4, converted to pixel
+ * coordinates, cv2.remap(INTER_LINEAR, constant border 0).  Bit-exact with OpenCV's plain C++ path.  C in {1,3,4}.
+ * workspace: device scratch of mgw_remap_bundle_u8_workspace_bytes() (the /4 maps). */
+MGW_API size_t mgw_remap_bundle_u8_workspace_bytes(int N, int H, int W);
+MGW_API int mgw_remap_bundle_u8(const uint8_t* img, const float* xy, int N, int H, int W, int C, uint8_t* dst, void* workspace,
+                        void* stream);
 
 /* ---- a6: interpolate(im, x, y, out_size), spatial_transformer.py:200-281 ------------------------------
  * im [N,IH,IW,C]; x,y [N,OH,OW] normalised coords -> out [N,OH,OW,C]. */

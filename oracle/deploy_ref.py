@@ -1,0 +1,109 @@
+"""TEST INFRASTRUCTURE -- numpy restatement of the deploy-side colour-frame warp, deploy_bundle.py:136-146
+(`warpRevBundle2`): the network's x_map / y_map are smoothed by a /4 then x4 cv2.resize, turned into pixel coordinates
+and used to cv2.remap the uint8 frame.  The arithmetic lives in a third-party dependency that is not under
+/root/reference (OpenCV, version not pinned by the reference; 4.13.0 in this container); restated here from its
+published algorithm and pinned against cv2 itself (tests/golden/deploy_remap.npz, oracle/make_golden.py):
+
+  cv2.resize(float32, INTER_LINEAR)   modules/imgproc/src/resize.cpp, resizeGeneric_ + HResizeLinear / VResizeLinear:
+      fx = (float)((dx + 0.5) * scale - 0.5), sx = floor(fx), fx -= sx; horizontally a tap that falls outside is
+      folded onto the border with weight 0 (sx < 0 -> sx = 0, fx = 0; sx >= w-1 -> sx = w-1, fx = 0); vertically the ROW
+      INDICES are clamped and the weights kept.  D = S[sx]*(1-fx) + S[sx+1]*fx per row, then rows*(1-fy) + rows'*fy, all in
+      fp32 with separate multiplies and adds.  That is OpenCV's plain C++ path (cv2.setUseOptimized(False)): its
+      SIMD-dispatched path (FMA) differs from it by 1 ulp on about a third of the map values, i.e. the reference's own
+      result depends on the OpenCV build; parity is pinned to the plain path and the effect of the other one on the
+      uint8 output is recorded in the fixture (fraction of differing bytes, max difference).
+  cv2.remap(uint8, float32 maps, INTER_LINEAR, BORDER_CONSTANT 0)   modules/imgproc/src/imgwarp.cpp, remapBilinear:
+      sx = cvRound(x*32), sy = cvRound(y*32) (round half to even), taps at (sx>>5, sy>>5) clamped to int16, 5-bit
+      fractions, integer weights (32-fx)(32-fy)*32 ... summing to 2^15, out = (sum + 2^14) >> 15; taps outside the image
+      read 0.  Identical in both OpenCV paths.
+Only tests/, __graft_entry__.smoke() and bench.py's CPU legs may import this module.
+"""
+import numpy as np
+
+f32 = np.float32
+
+
+def _scale(n_out, n_in):
+    """resize.cpp: inv_scale = dsize / (double)ssize; scale = 1. / inv_scale"""
+    return 1.0 / (n_out / float(n_in))
+
+
+def _hcoef(n_out, n_in):
+    scale = _scale(n_out, n_in)
+    i0 = np.zeros(n_out, np.int64)
+    a = np.zeros((n_out, 2), np.float32)
+    for d in range(n_out):
+        fx = f32((d + 0.5) * scale - 0.5)
+        sx = int(np.floor(fx))
+        fx = f32(fx - f32(sx))
+        if sx < 0:
+            sx, fx = 0, f32(0)
+        if sx >= n_in - 1:
+            sx, fx = n_in - 1, f32(0)
+        i0[d] = sx
+        a[d] = (f32(1) - fx, fx)
+    return i0, np.minimum(i0 + 1, n_in - 1), a
+
+
+def _vcoef(n_out, n_in):
+    scale = _scale(n_out, n_in)
+    i0 = np.zeros(n_out, np.int64)
+    i1 = np.zeros(n_out, np.int64)
+    a = np.zeros((n_out, 2), np.float32)
+    for d in range(n_out):
+        fy = f32((d + 0.5) * scale - 0.5)
+        sy = int(np.floor(fy))
+        fy = f32(fy - f32(sy))
+        i0[d] = min(max(sy, 0), n_in - 1)
+        i1[d] = min(max(sy + 1, 0), n_in - 1)
+        a[d] = (f32(1) - fy, fy)
+    return i0, i1, a
+
+
+def resize_linear(s, out_w, out_h):
+    """cv2.resize(s, (out_w, out_h)) for a float32 [H,W] array, plain C++ path."""
+    s = np.asarray(s, np.float32)
+    sh, sw = s.shape
+    ix0, ix1, ax = _hcoef(out_w, sw)
+    iy0, iy1, ay = _vcoef(out_h, sh)
+    h = s[:, ix0] * ax[:, 0] + s[:, ix1] * ax[:, 1]
+    return (h[iy0, :] * ay[:, 0:1] + h[iy1, :] * ay[:, 1:2]).astype(np.float32)
+
+
+def remap_linear_u8(img, x, y):
+    """cv2.remap(img, x, y, cv2.INTER_LINEAR) for uint8 [H,W,C] and float32 maps [OH,OW]; constant border 0."""
+    H, W = img.shape[:2]
+    def cv_round(v):            # cvtss2si: round half to even; out of range / NaN -> INT_MIN
+        r = np.rint(v)
+        bad = ~(np.abs(r) < 2147483648.0)
+        return np.where(bad, -2147483648.0, r).astype(np.int64)
+
+    sx = cv_round(np.asarray(x, np.float32) * f32(32))
+    sy = cv_round(np.asarray(y, np.float32) * f32(32))
+    ix = np.clip(sx >> 5, -32768, 32767)
+    iy = np.clip(sy >> 5, -32768, 32767)
+    fx, fy = sx & 31, sy & 31
+    w = [(32 - fx) * (32 - fy) * 32, fx * (32 - fy) * 32, (32 - fx) * fy * 32, fx * fy * 32]
+
+    def tap(yy, xx):
+        ok = (xx >= 0) & (xx < W) & (yy >= 0) & (yy < H)
+        v = img[np.clip(yy, 0, H - 1), np.clip(xx, 0, W - 1)].astype(np.int64)
+        return v * ok[..., None]
+
+    s = (tap(iy, ix) * w[0][..., None] + tap(iy, ix + 1) * w[1][..., None] + tap(iy + 1, ix) * w[2][..., None] +
+         tap(iy + 1, ix + 1) * w[3][..., None])
+    return np.clip((s + (1 << 14)) >> 15, 0, 255).astype(np.uint8)
+
+
+def smooth_maps(x_map, y_map, rate=4):
+    """deploy_bundle.py:139-143: /rate then x rate resize, then to pixel coordinates ((m + 1) / 2 * size in fp32)."""
+    H, W = x_map.shape
+    xs = resize_linear(resize_linear(x_map, int(W / rate), int(H / rate)), W, H)
+    ys = resize_linear(resize_linear(y_map, int(W / rate), int(H / rate)), W, H)
+    return ((xs + f32(1)) / f32(2) * f32(W)).astype(np.float32), ((ys + f32(1)) / f32(2) * f32(H)).astype(np.float32)
+
+
+def warp_rev_bundle2(img, x_map, y_map):
+    """deploy_bundle.py:136-146 for one uint8 frame [H,W,3] and the network's x_map / y_map [H,W]."""
+    xp, yp = smooth_maps(np.asarray(x_map, np.float32), np.asarray(y_map, np.float32))
+    return remap_linear_u8(img, xp, yp)

@@ -137,3 +137,14 @@ def train_temp_loss(height, width, batch_size, ret1, ret2, flow, use_temp_loss=1
     finally:
         t.placeholder = saved
     return ns['temp_loss']
+
+
+def deploy_warp_rev_bundle2(height, width):
+    """warpRevBundle2 of deploy_bundle.py:136-146 as a callable (the script itself cannot be imported: it parses argv and
+    opens a TF session at import time).  Needs cv2."""
+    import cv2
+    tree = _parse('deploy_bundle.py')
+    fn = [n for n in tree.body if isinstance(n, ast.FunctionDef) and n.name == 'warpRevBundle2']
+    assert len(fn) == 1
+    ns = dict(cv2=cv2, width=width, height=height)
+    return _exec_nodes(fn, ns, 'deploy_bundle.py')['warpRevBundle2']

@@ -202,6 +202,26 @@ def test_tma_rejects_shapes_it_cannot_serve(mgw):
     mgw.set_impl('auto')
 
 
+def test_backward_accumulates_into_callers_dU(mgw):
+    """mgw_warp_bwd_acc / mgw_mesh_warp_bwd_acc: dU += gradient, never zero-filled by the library."""
+    g = load_golden('mesh_tma_fold_clamp_shift')
+    U, d_out, d_img = golden_inputs('mesh_tma_fold_clamp_shift', g)
+    Ud, Hd, th = dev(U[1:]), dev(g['ref_Hs'][1:]), dev(g['theta'][1:])
+    go, gi = dev(d_out[1:]), dev(d_img[1:])
+    for impl in IMPLS:
+        mgw.set_impl(impl)
+        dU, dHs = mgw.ops.warp_bwd(Ud, Hd, go, gi)
+        buf = torch.full_like(Ud, 3.0)
+        dU2, dHs2 = mgw.ops.warp_bwd(Ud, Hd, go, gi, accumulate_into=buf)
+        assert dU2.data_ptr() == buf.data_ptr() and relmax(dHs2.cpu().numpy(), dHs.cpu().numpy()) < 1e-5
+        assert relmax((buf - 3.0).cpu().numpy(), dU.cpu().numpy()) < 1e-5
+        buf = torch.full_like(Ud, -1.0)
+        dU3, dth3 = mgw.ops.mesh_warp_bwd(Ud, th, mgw.ops.solve_h_fwd(th), go, gi, accumulate_into=buf)
+        dU4, dth4 = mgw.ops.mesh_warp_bwd(Ud, th, mgw.ops.solve_h_fwd(th), go, gi)
+        assert relmax((buf + 1.0).cpu().numpy(), dU4.cpu().numpy()) < 1e-5 and relmax(dth3.cpu().numpy(), dth4.cpu().numpy()) < 1e-5
+    mgw.set_impl('auto')
+
+
 def test_backward_without_dU_and_without_dimg(mgw):
     g = load_golden('mesh_smooth_s03')
     U, d_out, _ = golden_inputs('mesh_smooth_s03', g)
@@ -369,6 +389,30 @@ def test_full_size_properties(mgw, full, impl):
     # (5) dtheta by central differences in fp64-ish (directional derivative along a random direction)
     dU2, dth = mgw.ops.mesh_warp_bwd(U[:2].contiguous(), th[:2].contiguous(), Hs[:2].contiguous(), G[:2].contiguous(), None)
     assert torch.isfinite(dth).all() and torch.isfinite(dU2).all()
+
+
+# ------------------------------------------------------------------ deploy side: warpRevBundle2
+@pytest.mark.parametrize('tag', ['net', 'ragged', 'identity'])
+def test_deploy_remap_byte_exact(mgw, tag):
+    """mgw_remap_bundle_u8 == the reference's warpRevBundle2 (OpenCV plain path) byte for byte; numpy in -> numpy out."""
+    g = load_golden('deploy_remap')
+    img, xm, ym, ref = g[tag + '_img'], g[tag + '_x_map'], g[tag + '_y_map'], g[tag + '_ref_dst']
+    dst = mgw.warpRevBundle2(img, xm, ym)
+    assert isinstance(dst, np.ndarray) and dst.dtype == np.uint8 and np.array_equal(dst, ref)
+    # batched, on the device, straight from the operator's interleaved x/y maps; sample independence
+    xy = dev(np.stack([xm, ym], -1)[None].repeat(3, 0))
+    xy[1] = torch.flip(xy[1], dims=[0])
+    im3 = torch.tensor(img, device='cuda')[None].repeat(3, 1, 1, 1)
+    out3 = mgw.ops.remap_bundle_u8(im3, xy)
+    assert np.array_equal(out3[0].cpu().numpy(), ref) and np.array_equal(out3[2].cpu().numpy(), ref)
+    import deploy_ref
+    assert np.array_equal(out3[1].cpu().numpy(), deploy_ref.warp_rev_bundle2(img, xy[1, ..., 0].cpu().numpy(), xy[1, ..., 1].cpu().numpy()))
+    # one channel, and coordinates that are NaN / far outside: constant border 0 like cv2.remap
+    xy1 = dev(np.stack([xm, ym], -1)[None].copy())
+    xy1[0, :4, :4, 0] = float('nan'); xy1[0, 4:8, :4, 1] = 1e30
+    g1 = mgw.ops.remap_bundle_u8(torch.tensor(img[None, ..., :1].copy(), device='cuda'), xy1)
+    want = deploy_ref.warp_rev_bundle2(img[..., :1], np.nan_to_num(xy1[0, ..., 0].cpu().numpy(), nan=-1e30), xy1[0, ..., 1].cpu().numpy())
+    assert np.array_equal(g1[0].cpu().numpy(), want)
 
 
 def test_errors_are_loud(mgw):

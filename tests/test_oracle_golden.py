@@ -139,3 +139,34 @@ def test_golden_is_reference_output():
     g = load_golden(name)
     for k in ('ref_Hs', 'ref_out', 'ref_img', 'ref_dtheta', 'ref_dU'):
         assert bits_equal(fx[k], g[k]).all(), k
+
+
+# ------------------------------------------------------------------ deploy side: warpRevBundle2 (deploy_bundle.py:136-146)
+DEPLOY_CASES = ['net', 'ragged', 'identity']
+
+
+@pytest.mark.parametrize('tag', DEPLOY_CASES)
+def test_deploy_oracle_matches_the_reference_output(tag):
+    """oracle/deploy_ref.py (numpy) == the reference's warpRevBundle2 run on OpenCV (plain C++ path), byte for byte."""
+    import deploy_ref
+    g = load_golden('deploy_remap')
+    dst = deploy_ref.warp_rev_bundle2(g[tag + '_img'], g[tag + '_x_map'], g[tag + '_y_map'])
+    assert np.array_equal(dst, g[tag + '_ref_dst'])
+    # what OpenCV's SIMD-dispatched build does to the same call (recorded when the fixture was made): a handful of bytes
+    assert float(g[tag + '_opt_diff_frac']) < 1e-3
+
+
+@pytest.mark.reference
+def test_deploy_golden_is_reference_output():
+    """regenerates one deploy fixture from /root/reference (needs cv2) and compares with the committed one."""
+    cv2 = pytest.importorskip('cv2')
+    import ref_loader
+    g = load_golden('deploy_remap')
+    h, w = g['ragged_x_map'].shape
+    fn = ref_loader.deploy_warp_rev_bundle2(h, w)
+    cv2.setUseOptimized(False)
+    try:
+        dst = fn(g['ragged_img'], g['ragged_x_map'].copy(), g['ragged_y_map'].copy())
+    finally:
+        cv2.setUseOptimized(True)
+    assert np.array_equal(dst, g['ragged_ref_dst'])

@@ -77,6 +77,59 @@ res['config4_1080p_stream'] = {
     'note': 'host-to-host is PCIe-bound: 24.9 MB each way per fp32 1080p frame'}
 
 
+# ---- deploy-style per-frame loop at network size (deploy_bundle.py:285-303): the 1-channel current frame goes through the
+# operator (K1 + K2, C = 1), its x/y maps warp the uint8 colour frame (mgw_remap_bundle_u8); uint8 frames travel over PCIe
+hn, wn = 288, 512
+gray_h = torch.tensor(synth.noise_image(1, hn, wn, 1, 7)).pin_memory()
+col_h = torch.randint(0, 256, (1, hn, wn, 3), dtype=torch.uint8).pin_memory()
+gray_d = torch.empty((1, hn, wn, 1), device=dev); col_d = torch.empty((1, hn, wn, 3), device=dev, dtype=torch.uint8)
+o1 = torch.empty_like(gray_d); b1 = torch.empty((1, hn, wn), device=dev); xy1 = torch.empty((1, hn, wn, 2), device=dev)
+Hs1 = torch.empty((1, 4, 4, 9), device=dev); dst_d = torch.empty_like(col_d); dst_h = torch.empty((1, hn, wn, 3), dtype=torch.uint8).pin_memory()
+ws1 = torch.empty(lib.mgw_remap_bundle_u8_workspace_bytes(1, hn, wn) // 4 + 2, device=dev)
+with torch.cuda.stream(s):
+    def frame_call():
+        st = torch.cuda.current_stream().cuda_stream
+        check(lib.mgw_mesh_warp_fwd(P(gray_d), P(th), 1, hn, wn, 1, 4, 4, P(Hs1), P(o1), P(b1), P(xy1), st), 'fwd')
+        check(lib.mgw_remap_bundle_u8(P(col_d), P(xy1), 1, hn, wn, 3, P(dst_d), P(ws1), st), 'remap')
+    gray_d.copy_(gray_h, non_blocking=True); col_d.copy_(col_h, non_blocking=True)
+    for _ in range(3):
+        frame_call()
+    s.synchronize()
+    g2 = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g2, stream=s):
+        frame_call()
+    dev_frame = dev_time(g2.replay, 200, flush_l2=False)
+    dev_remap = dev_time(lambda: check(lib.mgw_remap_bundle_u8(P(col_d), P(xy1), 1, hn, wn, 3, P(dst_d), P(ws1),
+                                                               torch.cuda.current_stream().cuda_stream), 'remap'), 200, flush_l2=False)
+    lat3 = []
+    for i in range(1000):
+        t0 = time.perf_counter()
+        gray_d.copy_(gray_h, non_blocking=True); col_d.copy_(col_h, non_blocking=True)
+        g2.replay()
+        dst_h.copy_(dst_d, non_blocking=True)
+        s.synchronize()
+        lat3.append((time.perf_counter() - t0) * 1e6)
+cpu_us = None
+try:
+    import cv2
+    xm = xy1[0, ..., 0].cpu().numpy().copy(); ym = xy1[0, ..., 1].cpu().numpy().copy(); cimg = col_h[0].numpy()
+    def cpu_remap():
+        a = cv2.resize(cv2.resize(xm, (wn // 4, hn // 4)), (wn, hn)); b = cv2.resize(cv2.resize(ym, (wn // 4, hn // 4)), (wn, hn))
+        return cv2.remap(cimg, (a + 1) / 2 * wn, (b + 1) / 2 * hn, cv2.INTER_LINEAR)
+    cpu_remap()
+    tt = []
+    for _ in range(50):
+        t0 = time.perf_counter(); cpu_remap(); tt.append((time.perf_counter() - t0) * 1e6)
+    cpu_us = float(np.median(tt))
+except Exception as e:      # noqa: BLE001
+    cpu_us = 'cv2 unavailable: %s' % e
+res['deploy_frame_288x512'] = {
+    'us_device_graph_replay_warp_plus_remap': dev_frame, 'us_device_remap_only': dev_remap,
+    'us_p50_host_to_host_u8_frames': float(np.percentile(lat3, 50)), 'us_p99_host_to_host': float(np.percentile(lat3, 99)),
+    'us_cpu_opencv_remap_only': cpu_us, 'cpu_threads': os.cpu_count(),
+    'note': '1x288x512: H2D gray fp32 + colour u8, K1 + K2 (C=1) + maps/4 + remap, D2H colour u8; CPU = the same three cv2 calls'}
+
+
 # ---- config #3: StabNet-shaped forward, batch 16, 13-channel 288x512 input (configs/v2_93.py:19-22,40)
 def bottleneck(cin, mid, stride):
     return nn.ModuleDict(dict(
