@@ -108,7 +108,7 @@ def run_reference(args):
     inp = synth_inputs(ns)
     for _ in range(max(args.warmup, 1)):
         cpu_port_step(inp, ns)
-    steps = max(1, min(args.steps, 12))
+    steps = max(1, min(args.steps, 60))
     t = sum(cpu_port_step(inp, ns) for _ in range(steps))
     val = ns * H * W * steps / t / 1e6
     sample = '%d of 32 frames of configs[1] per step (fwd+bwd, dU+dtheta), %d steps' % (ns, steps)
@@ -130,7 +130,7 @@ def main():
     ap.add_argument('--warmup', type=int, default=5)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--batch', type=int, default=32, help='frames per GPU')
-    ap.add_argument('--cpu-sample', type=int, default=4, help='frames per CPU-baseline step')
+    ap.add_argument('--cpu-sample', type=int, default=32, help='frames per CPU-baseline step (of the 32-frame batch)')
     ap.add_argument('--no-cpu-baseline', action='store_true', help='skip the CPU leg (profiling runs)')
     ap.add_argument('--kernel-impl', default='auto', choices=['auto', 'generic', 'tma', 'pipe'])
     ap.add_argument('--no-graph', action='store_true', help='launch the step eagerly instead of replaying CUDA graphs')
@@ -157,11 +157,12 @@ def main():
     for k in range(R):
         sets.append({key: torch.tensor(np.roll(v, k, axis=0), device=dev) for key, v in base.items()})
     feats = torch.randn(n, 512, device=dev)
-    reducer = mgw.parallel.MeshHeadGradReducer(512, 2 * (GH + 1) * (GW + 1), dev)
+    reducer = mgw.parallel.MeshHeadGradReducer(512, 2 * (GH + 1) * (GW + 1), dev, nbuf=R)
 
     # dU of the step: zero-filled on a side stream while the forward runs, then accumulated into (mgw_mesh_warp_bwd_acc).
     # The zero-fill is inside the timed step; it just does not sit on the critical path between forward and backward.
     dU_buf = torch.empty_like(sets[0]['U'])
+    dth_slots = [torch.zeros_like(sets[0]['theta']) for _ in range(R)]
     side = torch.cuda.Stream(device=dev)
 
     def step_eager(i):
@@ -170,13 +171,15 @@ def main():
         side.wait_stream(cur)
         with torch.cuda.stream(side):
             dU_buf.zero_()
+        if world > 1:
+            # head gradient (features^T . dtheta) and all-reduce of the PREVIOUS step, on a side stream under this step's kernels
+            reducer.launch(slot=(i - 1) % R, features=feats, dtheta=dth_slots[(i - 1) % R])
         out, black, img, Hs = ops.mesh_warp_fwd(s['U'], s['theta'])
         cur.wait_stream(side)
-        dU, dtheta = ops.mesh_warp_bwd(s['U'], s['theta'], Hs, s['d_out'], s['d_img'], accumulate_into=dU_buf)
+        dU, dtheta = ops.mesh_warp_bwd(s['U'], s['theta'], Hs, s['d_out'], s['d_img'], accumulate_into=dU_buf,
+                                       dtheta_out=dth_slots[i % R])
         if world > 1:
-            reducer.wait()
-            reducer.head_grad(feats, dtheta)
-            reducer.launch()
+            reducer.wait()                          # join: fork and join both lie inside the step (CUDA-graph capturable)
         return dtheta
 
     # The step is launch-bound on the host once NCCL is in it (a dozen launches for ~160 us of GPU work): capture one
@@ -193,10 +196,9 @@ def main():
             graphs = []
             for i in range(R):
                 gph = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(gph):
+                # thread_local: the NCCL watchdog thread polls CUDA events while we capture
+                with torch.cuda.graph(gph, capture_error_mode='thread_local'):
                     step_eager(i)
-                    if world > 1:
-                        reducer.wait()
                 graphs.append(gph)
             torch.cuda.synchronize()
         except Exception as e:      # noqa: BLE001
@@ -272,8 +274,7 @@ def main():
     ms_e2e = timed(e2e_step, Ke, 3)
 
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
+        finish(world)
         return
     peak, peak_src = peaks()
     pix_per_step = P * world
@@ -317,14 +318,26 @@ def main():
         ns = args.cpu_sample
         cpu_port_step(base, ns)
         ts, t_start = [], time.perf_counter()
-        while len(ts) < 3 or (time.perf_counter() - t_start < 10 and len(ts) < 20):
+        while len(ts) < 3 or (time.perf_counter() - t_start < 12 and len(ts) < 200):
             ts.append(cpu_port_step(base, ns))
         line['cpu_baseline'] = {'value': ns * H * W / float(np.mean(ts)) / 1e6, 'unit': 'Mpix/s', 'cores': torch.get_num_threads(),
                                 'kind': 'port', 'sample': '%d of %d frames of the same workload, fwd+bwd, mean of %d runs (%.1f s of CPU work)'
                                 % (ns, n, len(ts), sum(ts))}
     print(json.dumps(line))
+    finish(world)
+
+
+def finish(world):
+    """multi-rank teardown: CUDA graphs that captured NCCL kernels are still alive, and destroying the process group under
+    them can hang; flush and leave (exit code 0) once every rank is done."""
+    sys.stdout.flush()
+    sys.stderr.flush()
     if world > 1:
-        dist.destroy_process_group()
+        import torch.distributed as dist
+        torch.cuda.synchronize()
+        dist.barrier()
+        torch.cuda.synchronize()
+        os._exit(0)
 
 
 if __name__ == '__main__':

@@ -42,32 +42,50 @@ def shard(t, rank, world):
 class MeshHeadGradReducer:
     """Sums the mesh-head gradient over ranks with one all-reduce per step on a side stream.
 
-    head_grad(features [n_local,F], dtheta [n_local,gh+1,gw+1,2]) -> flat [F*V + V] buffer (dW = features^T . dtheta,
-    db = sum_n dtheta), already scaled for the GLOBAL batch by the losses.  launch() starts the all-reduce after the
-    producing stream; wait() makes the current stream wait for it (call it right before the optimizer step).
+    head_grad(features [n_local,F], dtheta [n_local,gh+1,gw+1,2], slot) -> flat [F*V + V] buffer (dW = features^T . dtheta,
+    db = sum_n dtheta), already scaled for the GLOBAL batch by the losses.  launch(slot) forks the side stream from the
+    current one and starts the all-reduce of that slot's buffer there; wait() joins it back (call it right before the
+    optimizer step that consumes the buffer).  With nbuf > 1 a step can compute its gradient into one slot while the previous
+    step's slot is still being reduced -- the form that can be captured in a CUDA graph (fork and join inside one capture).
     """
 
-    def __init__(self, n_features, n_out, device):
-        self.buf = torch.zeros(n_features * n_out + n_out, device=device, dtype=torch.float32)
+    def __init__(self, n_features, n_out, device, nbuf=1):
+        self.bufs = [torch.zeros(n_features * n_out + n_out, device=device, dtype=torch.float32) for _ in range(nbuf)]
         self.nf, self.no = n_features, n_out
         self.side = torch.cuda.Stream(device=device) if torch.device(device).type == 'cuda' else None
         self.work = None
+        self.last = 0
 
-    def head_grad(self, features, dtheta):
+    @property
+    def buf(self):
+        return self.bufs[0]
+
+    def head_grad(self, features, dtheta, slot=0):
+        buf = self.bufs[slot]
         d = dtheta.reshape(dtheta.shape[0], self.no)
-        torch.mm(features.t(), d, out=self.buf[:self.nf * self.no].view(self.nf, self.no))
-        torch.sum(d, dim=0, out=self.buf[self.nf * self.no:])
-        return self.buf
+        torch.mm(features.t(), d, out=buf[:self.nf * self.no].view(self.nf, self.no))
+        torch.sum(d, dim=0, out=buf[self.nf * self.no:])
+        return buf
 
-    def launch(self):
-        if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
-            return
+    def launch(self, slot=0, features=None, dtheta=None):
+        """starts the all-reduce of slot `slot` on the side stream; with (features, dtheta) the head gradient itself is
+        formed there first, so nothing of the reduction sits on the stream that runs the warp kernels."""
+        self.last = slot
+        multi = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
         if self.side is None:
-            self.work = dist.all_reduce(self.buf, op=dist.ReduceOp.SUM, async_op=True)
+            if features is not None:
+                self.head_grad(features, dtheta, slot)
+            if multi:
+                self.work = dist.all_reduce(self.bufs[slot], op=dist.ReduceOp.SUM, async_op=True)
+            return
+        if not multi and features is None:
             return
         self.side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(self.side):
-            dist.all_reduce(self.buf, op=dist.ReduceOp.SUM)
+            if features is not None:
+                self.head_grad(features, dtheta, slot)
+            if multi:
+                dist.all_reduce(self.bufs[slot], op=dist.ReduceOp.SUM)
 
     def wait(self):
         if self.side is not None:
@@ -75,4 +93,4 @@ class MeshHeadGradReducer:
         elif self.work is not None:
             self.work.wait()
             self.work = None
-        return self.buf
+        return self.bufs[self.last]
