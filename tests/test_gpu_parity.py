@@ -222,6 +222,28 @@ def test_backward_accumulates_into_callers_dU(mgw):
     mgw.set_impl('auto')
 
 
+@pytest.mark.parametrize('name', ['mesh_full_noise_s05', 'mesh_tma_ragged', 'mesh_tma_c1'])
+def test_backward_workspace_needs_no_initialisation(mgw, name):
+    """the dH partial slots are all written (uniform mesh) or zero-filled by the library (ragged): a NaN-filled workspace
+    must give the same dtheta as a zeroed one."""
+    from dovs_b200._lib import lib, check
+    g = load_golden(name)
+    U, d_out, d_img = golden_inputs(name, g)
+    Ud, th, go, gi = dev(U), dev(g['theta']), dev(d_out), dev(d_img)
+    Hs = mgw.ops.solve_h_fwd(th)
+    n, h, w, c = Ud.shape
+    gh, gw = Hs.shape[1:3]
+    nbytes = lib.mgw_mesh_warp_bwd_workspace_bytes(n, h, w, c, gh, gw)
+    res = []
+    for fill in (0.0, float('nan')):
+        ws = torch.full((nbytes // 4 + 64,), fill, device='cuda')
+        dU, dth = torch.empty_like(Ud), torch.empty_like(th)
+        check(lib.mgw_mesh_warp_bwd(Ud.data_ptr(), th.data_ptr(), Hs.data_ptr(), go.data_ptr(), gi.data_ptr(), n, h, w, c, gh, gw,
+                                    dU.data_ptr(), dth.data_ptr(), ws.data_ptr(), torch.cuda.current_stream().cuda_stream), 'bwd')
+        res.append(dth.clone())
+    assert torch.isfinite(res[1]).all() and torch.equal(res[0], res[1])
+
+
 def test_backward_without_dU_and_without_dimg(mgw):
     g = load_golden('mesh_smooth_s03')
     U, d_out, _ = golden_inputs('mesh_smooth_s03', g)

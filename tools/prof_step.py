@@ -18,6 +18,6 @@ for _ in range(reps):
     flush.zero_()
     out, black, img, Hs = ops.mesh_warp_fwd(U, th)
     flush.zero_()
-    dU, dth = ops.mesh_warp_bwd(U, th, Hs, g, gi)
+    dU, dth = ops.mesh_warp_bwd(U, th, Hs, g, gi, want_dU=not os.environ.get('PROF_NODU'))
 torch.cuda.synchronize()
 print('ok', float(dth.abs().max()), mgw.launch_count())
