@@ -193,6 +193,48 @@ def test_pipe_path_is_taken_and_matches_generic(mgw, name):
     mgw.set_impl('auto')
 
 
+def _random_shapes():
+    rng = np.random.RandomState(2024)
+    shapes = []
+    for _ in range(14):
+        gh, gw = int(rng.choice([1, 2, 3, 4])), int(rng.choice([1, 2, 3, 4, 6]))
+        c = int(rng.choice([1, 3, 4]))
+        n = int(rng.choice([1, 2, 3]))
+        h = int(rng.randint(max(24, 9 * gh), 200))
+        w = 4 * int(rng.randint(max(16, 9 * gw), 70))
+        shapes.append((n, h, w, c, gh, gw, float(rng.choice([0.0, 0.03, 0.08, 0.2])), int(rng.randint(1 << 30))))
+    return shapes
+
+
+@pytest.mark.parametrize('shape', _random_shapes(), ids=lambda s: '%dx%dx%dx%d_g%dx%d_s%g' % s[:7])
+def test_random_shapes_all_kernel_families_agree(mgw, shape):
+    """whatever family `auto` picks for a shape (pipeline, tiles, generic -- ragged meshes, tiles shifted onto their
+    neighbours, boxes that overflow, clamped and folded vertices), the forward equals the generic kernels bit for bit and
+    the backward agrees to rounding."""
+    import synth
+    n, h, w, c, gh, gw, sigma, seed = shape
+    U = dev(synth.noise_image(n, h, w, c, seed))
+    th = dev(synth.random_mesh(n, gh, gw, sigma, seed + 1))
+    go = dev(synth.randn((n, h, w, c), seed + 2)); gi = dev(synth.randn((n, h, w, 2), seed + 3, 0.1))
+    mgw.set_impl('generic')
+    o_g, b_g, i_g, Hs = mgw.ops.mesh_warp_fwd(U, th)
+    dU_g, dH_g = mgw.ops.warp_bwd(U, Hs, go, gi)
+    mgw.set_impl('auto')
+    o_a, b_a, i_a, Hs_a = mgw.ops.mesh_warp_fwd(U, th)
+    dU_a, dH_a = mgw.ops.warp_bwd(U, Hs, go, gi)
+    assert torch.equal(Hs, Hs_a)
+    fin = torch.isfinite(o_g)
+    assert torch.equal(o_g.view(torch.int32)[fin], o_a.view(torch.int32)[fin]) and torch.equal(torch.isfinite(o_a), fin)
+    assert torch.equal(b_g, b_a)
+    fi = torch.isfinite(i_g)
+    assert torch.equal(i_g.view(torch.int32)[fi], i_a.view(torch.int32)[fi])
+    # gradients at the SAME Hs, before the adjoint solve (which amplifies fp32 summation noise by the conditioning of the
+    # cell's 8x8 system, in any implementation); folded cells (sigma 0.2) scatter order-dependent garbage everywhere
+    if sigma <= 0.08 and torch.isfinite(dU_g).all() and torch.isfinite(dH_g).all():
+        assert relmax(dU_a.cpu().numpy(), dU_g.cpu().numpy()) < 5e-5
+        assert relmax(dH_a.cpu().numpy(), dH_g.cpu().numpy()) < 5e-5
+
+
 def test_tma_rejects_shapes_it_cannot_serve(mgw):
     g = load_golden('mesh_ragged_c1')            # 50 x 70: row pitch not a multiple of 16 bytes
     U, _, _ = golden_inputs('mesh_ragged_c1', g)

@@ -1,4 +1,5 @@
-cd tools
+cd "$(dirname "$0")"
+[ -x ./tma_bw ] || nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -o tma_bw tma_bw.cu -lcuda
 # box bi br, tile twf th, S, ctas/SM, xoff
 ./tma_bw 192 40  96 24 3 2 0
 ./tma_bw 192 40  96 24 3 2 -12
