@@ -316,8 +316,13 @@ struct LossBwd {
 #ifndef MGW_BWD_MINB
 #define MGW_BWD_MINB (NT == 256 ? (K <= 3 ? 4 : 3) : 2)
 #endif
-template <int C, int TW, int K, int NT, bool LOSS>
-__global__ void __launch_bounds__(NT, MGW_BWD_MINB)
+#ifndef MGW_BWD_NODU_MINB
+#define MGW_BWD_NODU_MINB (NT == 256 ? 4 : 2)
+#endif
+// DU = false is the variant for a placeholder U (the reference's own training graph, s_net_bundle_nobm.py:281): no
+// accumulator box, no scatter code, fewer registers -> one more CTA per SM.
+template <int C, int TW, int K, int NT, bool LOSS, bool DU>
+__global__ void __launch_bounds__(NT, DU ? MGW_BWD_MINB : MGW_BWD_NODU_MINB)
 warp_bwd_tma_kernel(const __grid_constant__ CUtensorMap mapU, const __grid_constant__ CUtensorMap mapDU,
                     const float* __restrict__ U, const float* __restrict__ Hs, const float* __restrict__ d_out,
                     const float* __restrict__ d_img, const __grid_constant__ TileCfg cfg, float* __restrict__ dU,
@@ -368,7 +373,7 @@ warp_bwd_tma_kernel(const __grid_constant__ CUtensorMap mapU, const __grid_const
             }
         }
     }
-    if (dU) {
+    if (DU) {
         int4* a4 = reinterpret_cast<int4*>(s_acc);
 #pragma unroll
         for (int i = 0; i < (G::kBoxF / 4 + NT - 1) / NT; ++i)
@@ -385,7 +390,7 @@ warp_bwd_tma_kernel(const __grid_constant__ CUtensorMap mapU, const __grid_const
         }
     }
     // ---- per-tile fixed-point scale from max|d_out| (Inf/NaN anywhere in the tile disables the fixed-point path)
-    if (dU) {
+    if (DU) {
         // max over |d_out| as unsigned bit patterns: Inf/NaN (>= 0x7f800000) win the max, one REDUX per warp
         unsigned m = 0u;
 #pragma unroll
@@ -399,7 +404,7 @@ warp_bwd_tma_kernel(const __grid_constant__ CUtensorMap mapU, const __grid_const
     const int bx0 = ti->bx0, by0 = ti->by0;
     int fixed = 0;
     float scale = 0.0f, inv_scale = 0.0f;
-    if (dU) {
+    if (DU) {
         unsigned mb = 0u;
 #pragma unroll
         for (int w = 0; w < NT / 32; ++w) mb = max(mb, (unsigned)__float_as_int(ti->wmax[w]));
@@ -421,7 +426,7 @@ warp_bwd_tma_kernel(const __grid_constant__ CUtensorMap mapU, const __grid_const
     const float halfW = 0.5f * (float)cfg.W, halfH = 0.5f * (float)cfg.H;
 
     tma::mbar_wait(bar, 0);
-    if (ti->interior && (fixed || !dU)) {
+    if (ti->interior && (fixed || !DU)) {
         // ---- fast path: every tap unclipped and inside the box; shared-memory offsets are compile-time constants
 #pragma unroll
         for (int k = 0; k < K; ++k) {
@@ -447,7 +452,7 @@ warp_bwd_tma_kernel(const __grid_constant__ CUtensorMap mapU, const __grid_const
                     const float gch = gout[k][ch];
                     sa = fmaf(gch, pa[ch], sa); sb = fmaf(gch, pa[G::kRowF + ch], sb);
                     sc = fmaf(gch, pa[C + ch], sc); sd = fmaf(gch, pa[G::kRowF + C + ch], sd);
-                    if (dU) {
+                    if (DU) {
                         const float gs = gch * scale;
                         atomicAdd(qa + ch, fixed_of(wa, gs));
                         atomicAdd(qa + G::kRowF + ch, fixed_of(wb, gs));
@@ -461,7 +466,7 @@ warp_bwd_tma_kernel(const __grid_constant__ CUtensorMap mapU, const __grid_const
         }
     } else {
         const float* Un = U + (size_t)tl.n * cfg.H * cfg.W * C;
-        float* dUn = dU ? dU + (size_t)tl.n * cfg.H * cfg.W * C : nullptr;
+        float* dUn = DU ? dU + (size_t)tl.n * cfg.H * cfg.W * C : nullptr;
 #pragma unroll
         for (int k = 0; k < K; ++k) {
             const int row = tl.r0 + g * K + k;
@@ -477,7 +482,7 @@ warp_bwd_tma_kernel(const __grid_constant__ CUtensorMap mapU, const __grid_const
                 const bool inbox = sx0 >= 0 && sx1 < G::SBW && sy0 >= 0 && sy1 < G::SBH;
                 const float wa = t.ax * t.ay, wb = t.ax * t.by, wc = t.bx * t.ay, wd = t.bx * t.by;
                 float gx = 0.0f, gy = 0.0f;
-                const bool scatter = (dU != nullptr) && taps_scatter(t);
+                const bool scatter = DU && taps_scatter(t);
                 const size_t ga = ((size_t)t.y0 * cfg.W + t.x0) * C, gb = ((size_t)t.y1 * cfg.W + t.x0) * C;
                 const size_t gc = ((size_t)t.y0 * cfg.W + t.x1) * C, gd = ((size_t)t.y1 * cfg.W + t.x1) * C;
                 const int ia = sy0 * G::kRowF + sx0 * C, ib = sy1 * G::kRowF + sx0 * C;
@@ -653,15 +658,24 @@ static int launch_bwd_v(const float* U, const float* Hs, const float* d_out, con
     TRY_RC(make_map(&mU, U, c.W * C, c.H, c.N, G::kRowF, G::SBH));
     if (dU) TRY_RC(make_map(&mDU, dU, c.W * C, c.H, c.N, G::kRowF, G::SBH)); else mDU = mU;
     const size_t smem = (size_t)(G::kBoxF + 256 + (dU ? G::kBoxF : 0)) * 4 + 64;
-    if (loss) {
-        static bool attr_l[64] = {};
-        TRY_RC(allow_smem(warp_bwd_tma_kernel<C, TW, K, NT, true>, attr_l, "warp_bwd_tma(loss)"));
-        warp_bwd_tma_kernel<C, TW, K, NT, true><<<dim3(p.ntx, p.nty, c.N), NT, smem, st>>>(mU, mDU, U, Hs, nullptr, d_img, c, dU, parts, *loss);
-        return check_launch("warp_bwd_tma(loss)");
+    const dim3 grid(p.ntx, p.nty, c.N);
+    if (loss && dU) {
+        static bool attr[64] = {};
+        TRY_RC(allow_smem(warp_bwd_tma_kernel<C, TW, K, NT, true, true>, attr, "warp_bwd_tma(loss)"));
+        warp_bwd_tma_kernel<C, TW, K, NT, true, true><<<grid, NT, smem, st>>>(mU, mDU, U, Hs, nullptr, d_img, c, dU, parts, *loss);
+    } else if (loss) {
+        static bool attr[64] = {};
+        TRY_RC(allow_smem(warp_bwd_tma_kernel<C, TW, K, NT, true, false>, attr, "warp_bwd_tma(loss, no dU)"));
+        warp_bwd_tma_kernel<C, TW, K, NT, true, false><<<grid, NT, smem, st>>>(mU, mDU, U, Hs, nullptr, d_img, c, nullptr, parts, *loss);
+    } else if (dU) {
+        static bool attr[64] = {};
+        TRY_RC(allow_smem(warp_bwd_tma_kernel<C, TW, K, NT, false, true>, attr, "warp_bwd_tma"));
+        warp_bwd_tma_kernel<C, TW, K, NT, false, true><<<grid, NT, smem, st>>>(mU, mDU, U, Hs, d_out, d_img, c, dU, parts, LossBwd{});
+    } else {
+        static bool attr[64] = {};
+        TRY_RC(allow_smem(warp_bwd_tma_kernel<C, TW, K, NT, false, false>, attr, "warp_bwd_tma(no dU)"));
+        warp_bwd_tma_kernel<C, TW, K, NT, false, false><<<grid, NT, smem, st>>>(mU, mDU, U, Hs, d_out, d_img, c, nullptr, parts, LossBwd{});
     }
-    static bool attr[64] = {};
-    TRY_RC(allow_smem(warp_bwd_tma_kernel<C, TW, K, NT, false>, attr, "warp_bwd_tma"));
-    warp_bwd_tma_kernel<C, TW, K, NT, false><<<dim3(p.ntx, p.nty, c.N), NT, smem, st>>>(mU, mDU, U, Hs, d_out, d_img, c, dU, parts, LossBwd{});
     return check_launch("warp_bwd_tma");
 }
 
