@@ -163,12 +163,21 @@ temp_loss_kernel(const float* __restrict__ out1, const float* __restrict__ black
 }
 
 // ---------------------------------------------------------------- launchers
-static unsigned blocks_for(int HW) { unsigned b = (unsigned)((HW + 255) / 256); return b > 148 * 4 ? 148 * 4 : b; }
+// blocks per sample of the grid-stride reductions: about 8 resident blocks per SM over the whole batch (148 SMs), so that a
+// block amortises its two block-wide reductions and its two atomics over many pixels (one pixel per thread made these
+// kernels latency-bound: 58 us for 132 MB)
+static unsigned blocks_for(int HW, int N)
+{
+    const unsigned full = (unsigned)((HW + 255) / 256);
+    unsigned per = (unsigned)((148 * 8 + N - 1) / N);
+    if (per < 1) per = 1;
+    return per < full ? per : full;
+}
 
 int launch_img_loss_fwd(const float* out, const float* y, const float* black, int N, int H, int W, int C, float* sums, cudaStream_t st)
 {
     cudaMemsetAsync(sums, 0, sizeof(float) * 2 * N, st);
-    img_loss_fwd_kernel<<<dim3(blocks_for(H * W), N), 256, 0, st>>>(out, y, black, H * W, C, sums);
+    img_loss_fwd_kernel<<<dim3(blocks_for(H * W, N), N), 256, 0, st>>>(out, y, black, H * W, C, sums);
     return check_launch("img_loss_fwd");
 }
 
@@ -198,7 +207,7 @@ int launch_temp_loss_fwd(const float* out1, const float* black1, const float* ou
                          const float* flow, int N, int H, int W, int C, float* sums, cudaStream_t st)
 {
     cudaMemsetAsync(sums, 0, sizeof(float) * 2 * N, st);
-    temp_loss_kernel<false><<<dim3(blocks_for(H * W), N), 256, 0, st>>>(out1, black1, out2, black2, flow, nullptr, 0.0f,
+    temp_loss_kernel<false><<<dim3(blocks_for(H * W, N), N), 256, 0, st>>>(out1, black1, out2, black2, flow, nullptr, 0.0f,
                                                                         N, H, W, C, sums, nullptr, nullptr);
     return check_launch("temp_loss_fwd");
 }
@@ -208,7 +217,7 @@ int launch_temp_loss_bwd(const float* out1, const float* black1, const float* ou
                          float* d_out1, float* d_out2, cudaStream_t st)
 {
     cudaMemsetAsync(d_out2, 0, sizeof(float) * (size_t)N * H * W * C, st);
-    temp_loss_kernel<true><<<dim3(blocks_for(H * W), N), 256, 0, st>>>(out1, black1, out2, black2, flow, sums, upstream,
+    temp_loss_kernel<true><<<dim3(blocks_for(H * W, N), N), 256, 0, st>>>(out1, black1, out2, black2, flow, sums, upstream,
                                                                        N, H, W, C, nullptr, d_out1, d_out2);
     return check_launch("temp_loss_bwd");
 }
