@@ -365,6 +365,23 @@ int mgw_remap_bundle_u8(const uint8_t* img, const float* xy, int N, int H, int W
     return launch_remap_bundle_u8(img, xy, N, H, W, C, dst, workspace, (cudaStream_t)stream);
 }
 
+int mgw_stream_assemble(const float* frames, const float* masks, int depth, int head, const int* taps, int ntaps, int use_masks,
+                        const float* cur, int H, int W, float* in_x, void* stream)
+{
+    REQUIRE(frames && taps && cur && in_x && (masks || !use_masks), "mgw_stream_assemble: null pointer");
+    REQUIRE(depth > 0 && head >= 0 && head < depth && H > 0 && W > 0 && (long long)H * W < (1LL << 31), "mgw_stream_assemble: bad sizes");
+    return launch_stream_assemble(frames, masks, depth, head, taps, ntaps, use_masks, cur, H, W, in_x, (cudaStream_t)stream);
+}
+
+int mgw_stream_push(float* frames, float* masks, int depth, int slot, const float* img, const float* black, int H, int W,
+                    float* frame_out, int out_stride, void* stream)
+{
+    REQUIRE(img && black && (frames || frame_out), "mgw_stream_push: null pointer");
+    REQUIRE(depth > 0 && slot >= 0 && slot < depth && H > 0 && W > 0 && (long long)H * W < (1LL << 31) && out_stride >= 1,
+            "mgw_stream_push: bad sizes");
+    return launch_stream_push(frames, masks, depth, slot, img, black, H, W, frame_out, out_stride, (cudaStream_t)stream);
+}
+
 int mgw_img_loss_fwd(const float* out, const float* y, const float* black, int N, int H, int W, int C, float* sums, void* stream)
 {
     REQUIRE(out && y && black && sums, "mgw_img_loss_fwd: null pointer");

@@ -85,4 +85,10 @@ size_t remap_bundle_workspace_bytes(int N, int H, int W);
 int launch_remap_bundle_u8(const uint8_t* img, const float* xy, int N, int H, int W, int C, uint8_t* dst, void* workspace,
                            cudaStream_t st);
 
+// mgw_stream.cu : deploy-side streaming state (device-resident history rings, deploy_bundle.py:204-232,259-295,319-327)
+int launch_stream_assemble(const float* frames, const float* masks, int depth, int head, const int* taps_host, int ntaps, int use_masks,
+                           const float* cur, int H, int W, float* in_x, cudaStream_t st);
+int launch_stream_push(float* frames, float* masks, int depth, int slot, const float* img, const float* black, int H, int W,
+                       float* frame_out, int out_stride, cudaStream_t st);
+
 }  // namespace mgw

@@ -11,7 +11,7 @@ import torch
 
 from . import ops
 
-__all__ = ['warpRevBundle2']
+__all__ = ['warpRevBundle2', 'StreamState']
 
 
 def warpRevBundle2(img, x_map, y_map, device=None):
@@ -32,3 +32,43 @@ def warpRevBundle2(img, x_map, y_map, device=None):
     if single:
         dst = dst[0]
     return dst.cpu().numpy() if as_numpy else dst
+
+
+class StreamState:
+    """The per-video state of deploy_bundle.py on the device: the last `depth` stabilised frames and their black masks
+    (the reference's before_frames / before_masks lists, :221-224) as rings, the 13-channel network input assembled from
+    the index taps in one launch (:259-274), the refine re-feed (:292-295) and the per-frame update (:319-328).
+
+        st = StreamState(first_frame)                    # first_frame: [H,W] fp32 (cvt_img2train output)
+        for frame in video:
+            in_x = st.assemble(frame)                    # [1,H,W,13] = 6 masks + 6 frames + current
+            for _ in range(refine):
+                img, black = net(in_x)                   # the network + the multi-grid warp
+                st.refeed(in_x, img, black)              # in_x[..., -1] = img - black
+            st.push(img, black)
+    """
+
+    def __init__(self, first_frame, depth=32, taps=(1, 2, 4, 8, 16, 32), use_masks=True, device='cuda'):
+        f = torch.as_tensor(first_frame, dtype=torch.float32).to(device)
+        h, w = f.shape
+        self.frames = f.reshape(1, h, w).repeat(depth, 1, 1).contiguous()
+        self.masks = torch.zeros((depth, h, w), device=f.device, dtype=torch.float32)
+        self.depth, self.taps, self.use_masks, self.head = depth, tuple(int(t) for t in taps), use_masks, depth - 1
+
+    def assemble(self, cur):
+        cur = torch.as_tensor(cur, dtype=torch.float32).to(self.frames.device).reshape(self.frames.shape[1:]).contiguous()
+        return ops.stream_assemble(self.frames, self.masks, self.head, self.taps, cur, self.use_masks)
+
+    def refeed(self, in_x, img, black):
+        ops.stream_push(None, None, 0, img.reshape(self.frames.shape[1:]).contiguous(), black.reshape(self.frames.shape[1:]).contiguous(),
+                        refeed_into=in_x)
+
+    def push(self, img, black):
+        self.head = (self.head + 1) % self.depth
+        ops.stream_push(self.frames, self.masks, self.head, img.reshape(self.frames.shape[1:]).contiguous(),
+                        black.reshape(self.frames.shape[1:]).contiguous())
+
+    def history(self):
+        """(frames, masks) oldest first, as the reference's lists hold them"""
+        order = [(self.head + 1 + k) % self.depth for k in range(self.depth)]
+        return self.frames[order], self.masks[order]

@@ -320,3 +320,34 @@ def remap_bundle_u8(img, xy):
     with torch.cuda.device(img.device):
         check(lib.mgw_remap_bundle_u8(_p(img), _p(xy), n, h, w, c, _p(dst), _p(ws), _st()), 'mgw_remap_bundle_u8')
     return dst
+
+
+def stream_assemble(frames, masks, head, taps, cur, use_masks=True):
+    """deploy_bundle.py:259-274 on the device: frames / masks [depth,H,W] rings (newest entry at slot `head`), cur [H,W]
+    -> in_x [1,H,W,nch] = [masks[-i] for i in taps] + [frames[-i] for i in taps] + [cur]."""
+    import ctypes
+    frames, cur = _chk(frames, 'frames'), _chk(cur, 'cur')
+    masks = _chk(masks, 'masks') if use_masks else None
+    depth, h, w = frames.shape
+    nch = (2 if use_masks else 1) * len(taps) + 1
+    in_x = torch.empty((1, h, w, nch), device=frames.device, dtype=torch.float32)
+    arr = (ctypes.c_int * len(taps))(*[int(t) for t in taps])
+    with torch.cuda.device(frames.device):
+        check(lib.mgw_stream_assemble(_p(frames), _p(masks), depth, int(head), arr, len(taps), 1 if use_masks else 0, _p(cur), h, w,
+                                      _p(in_x), _st()), 'mgw_stream_assemble')
+    return in_x
+
+
+def stream_push(frames, masks, slot, img, black, refeed_into=None):
+    """deploy_bundle.py:292-295,319-328: frame = img + black*(-1) -> frames[slot], black -> masks[slot]; refeed_into: an
+    assembled in_x [1,H,W,nch] whose LAST channel receives the frame (the refine loop).  frames/masks None: re-feed only."""
+    img, black = _chk(img, 'img'), _chk(black, 'black')
+    ref = frames if frames is not None else refeed_into
+    depth, h, w = (frames.shape if frames is not None else (1, refeed_into.shape[1], refeed_into.shape[2]))
+    fo, stride = None, 1
+    if refeed_into is not None:
+        refeed_into = _chk(refeed_into, 'refeed_into')
+        stride = refeed_into.shape[-1]
+        fo = refeed_into.data_ptr() + 4 * (stride - 1)
+    with torch.cuda.device(ref.device):
+        check(lib.mgw_stream_push(_p(frames), _p(masks), depth, int(slot), _p(img), _p(black), h, w, fo, stride, _st()), 'mgw_stream_push')

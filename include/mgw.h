@@ -121,6 +121,18 @@ MGW_API size_t mgw_remap_bundle_u8_workspace_bytes(int N, int H, int W);
 MGW_API int mgw_remap_bundle_u8(const uint8_t* img, const float* xy, int N, int H, int W, int C, uint8_t* dst, void* workspace,
                         void* stream);
 
+/* ---- f2 (deploy side): the streaming state of deploy_bundle.py:204-232,259-295,319-327 -----------------------------
+ * frames, masks: device rings [depth][H][W] (the reference's before_frames / before_masks lists, depth = before_ch = 32);
+ * `head` = slot of the newest entry, so that list[-i] is slot (head - (i-1)) mod depth.
+ * mgw_stream_assemble: in_x [H,W,nch] = [masks[-i] for i in taps (if use_masks)] + [frames[-i] for i in taps] + [cur]
+ *   (taps: HOST array of ntaps <= 32 ints, the reference's indices[1:] = 1,2,4,8,16,32; cur [H,W] = the current frame).
+ * mgw_stream_push: frame = img + black*(-1) -> frames[slot], black -> masks[slot] (either ring nullable), and optionally
+ *   frame -> frame_out[p * out_stride] (the refine re-feed tmp_in_x[..., -1] = frame: pass in_x + nch-1 and nch). */
+MGW_API int mgw_stream_assemble(const float* frames, const float* masks, int depth, int head, const int* taps, int ntaps,
+                        int use_masks, const float* cur, int H, int W, float* in_x, void* stream);
+MGW_API int mgw_stream_push(float* frames, float* masks, int depth, int slot, const float* img, const float* black, int H, int W,
+                    float* frame_out, int out_stride, void* stream);
+
 /* ---- a6: interpolate(im, x, y, out_size), spatial_transformer.py:200-281 ------------------------------
  * im [N,IH,IW,C]; x,y [N,OH,OW] normalised coords -> out [N,OH,OW,C]. */
 MGW_API int mgw_interp_fwd(const float* im, const float* x, const float* y, int N, int IH, int IW, int C, int OH, int OW,

@@ -107,3 +107,46 @@ def warp_rev_bundle2(img, x_map, y_map):
     """deploy_bundle.py:136-146 for one uint8 frame [H,W,3] and the network's x_map / y_map [H,W]."""
     xp, yp = smooth_maps(np.asarray(x_map, np.float32), np.asarray(y_map, np.float32))
     return remap_linear_u8(img, xp, yp)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# streaming state of deploy_bundle.py (:204-232 initialisation, :259-274 input assembly, :284-295 refine, :319-328 update)
+class StreamStateRef:
+    """Restatement of the reference's per-frame list handling: before_frames / before_masks are lists of `depth` arrays
+    [1,H,W,1]; the network input is [masks[-i] for i in taps] + [frames[-i] for i in taps] + [current frame] along the
+    channel axis; after the network has run, frame = img + black*(-1) is appended (and the oldest entry dropped)."""
+
+    def __init__(self, first_frame, depth=32, taps=(1, 2, 4, 8, 16, 32), use_masks=True):
+        h, w = first_frame.shape
+        f = np.asarray(first_frame, np.float32).reshape(1, h, w, 1)
+        self.frames = [f.copy() for _ in range(depth)]                                  # :221-223
+        self.masks = [np.zeros((1, h, w, 1), np.float32) for _ in range(depth)]         # :224
+        self.taps, self.use_masks, self.h, self.w = tuple(taps), use_masks, h, w
+
+    def assemble(self, cur):
+        in_x = []
+        if self.use_masks:
+            in_x += [self.masks[-i] for i in self.taps]
+        in_x += [self.frames[-i] for i in self.taps]
+        in_x.append(np.asarray(cur, np.float32).reshape(1, self.h, self.w, 1))
+        return np.concatenate(in_x, axis=3)
+
+    def frame_of(self, img, black):
+        return (np.asarray(img, np.float32).reshape(self.h, self.w) + np.asarray(black, np.float32).reshape(self.h, self.w) *
+                np.float32(-1)).astype(np.float32)
+
+    def push(self, img, black):
+        self.frames.append(self.frame_of(img, black).reshape(1, self.h, self.w, 1))
+        self.masks.append(np.asarray(black, np.float32).reshape(1, self.h, self.w, 1))
+        self.frames.pop(0)
+        self.masks.pop(0)
+
+
+def stream_fake_net(in_x, k):
+    """deterministic stand-in for the network (sess.run at deploy_bundle.py:286) used by the stream fixtures and tests:
+    output image and black mask [1,H,W,1] / [1,H,W] from the assembled input [1,H,W,13] and the frame number"""
+    h, w = in_x.shape[1:3]
+    r = np.random.RandomState(1000 + k)
+    img = (0.7 * in_x[0, :, :, -1] + 0.3 * in_x[0, :, :, 6] + 0.05 * r.standard_normal((h, w))).astype(np.float32)
+    black = (r.random_sample((h, w)) < 0.1).astype(np.float32)
+    return img.reshape(1, h, w, 1), black.reshape(1, h, w)

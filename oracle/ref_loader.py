@@ -148,3 +148,24 @@ def deploy_warp_rev_bundle2(height, width):
     assert len(fn) == 1
     ns = dict(cv2=cv2, width=width, height=height)
     return _exec_nodes(fn, ns, 'deploy_bundle.py')['warpRevBundle2']
+
+
+def deploy_stream_blocks():
+    """The per-frame state handling of deploy_bundle.py as three code objects compiled from the reference's own statements
+    (picked out of the `while(True)` loop by line range; the script cannot be imported):
+      'assemble' :259-283  in_x from before_masks / before_frames / after_frames (+ tmp_in_x = in_x.copy())
+      'refine'   :284-295  for j in range(args.refine): sess.run -> frame = img + black*(-1) -> tmp_in_x[..., -1] = frame
+      'update'   :319-328  before_frames.append(frame) / before_masks.append(black) / pop(0)
+    They run in a namespace that supplies np, args, the lists, height, width, input_mask, MaxSpan, black_mask, time and a
+    stand-in `sess` with a run() method."""
+    tree = _parse('deploy_bundle.py')
+    loops = [n for n in ast.walk(tree) if isinstance(n, ast.While)]
+    assert len(loops) == 1
+    body = loops[0].body
+
+    def pick(lo, hi):
+        nodes = [n for n in body if lo <= n.lineno <= hi]
+        assert nodes and nodes[0].lineno == lo, (lo, [n.lineno for n in nodes])
+        return compile(ast.Module(body=nodes, type_ignores=[]), os.path.join(REF, 'deploy_bundle.py'), 'exec')
+
+    return {'assemble': pick(259, 283), 'refine': pick(284, 295), 'update': pick(319, 328)}

@@ -479,6 +479,24 @@ def test_deploy_remap_byte_exact(mgw, tag):
     assert np.array_equal(g1[0].cpu().numpy(), want)
 
 
+def test_deploy_stream_state_exact(mgw):
+    """StreamState (device rings, mgw_stream_assemble / mgw_stream_push) == the reference's per-frame list handling."""
+    import deploy_ref
+    g = load_golden('deploy_stream')
+    st = mgw.StreamState(g['first'])
+    for k in range(g['cur_frames'].shape[0]):
+        in_x = st.assemble(g['cur_frames'][k])
+        assert np.array_equal(in_x.cpu().numpy(), g['in_x'][k])
+        for _ in range(int(g['refine'])):
+            img, black = deploy_ref.stream_fake_net(in_x.cpu().numpy(), k)
+            img_d, black_d = dev(img), dev(black)
+            st.refeed(in_x, img_d, black_d)
+        assert np.array_equal(in_x.cpu().numpy(), g['tmp_in_x'][k])
+        st.push(img_d, black_d)
+    fr, mk = st.history()
+    assert np.array_equal(fr.cpu().numpy()[..., None], g['final_frames']) and np.array_equal(mk.cpu().numpy()[..., None], g['final_masks'])
+
+
 def test_errors_are_loud(mgw):
     with pytest.raises(RuntimeError):
         mgw.transformer(torch.zeros(1, 8, 8, 3), torch.zeros(1, 5, 5, 2))          # CPU tensors: no fallback

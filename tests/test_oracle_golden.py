@@ -170,3 +170,30 @@ def test_deploy_golden_is_reference_output():
     finally:
         cv2.setUseOptimized(True)
     assert np.array_equal(dst, g['ragged_ref_dst'])
+
+
+# ------------------------------------------------------------------ deploy side: streaming state (deploy_bundle.py:204-328)
+def test_stream_oracle_matches_the_reference_statements():
+    """oracle/deploy_ref.StreamStateRef == the reference's own list handling (its statements exec'd, oracle/make_golden.py)."""
+    import deploy_ref
+    g = load_golden('deploy_stream')
+    st = deploy_ref.StreamStateRef(g['first'])
+    for k in range(g['cur_frames'].shape[0]):
+        in_x = st.assemble(g['cur_frames'][k])
+        assert np.array_equal(in_x, g['in_x'][k])
+        tmp = in_x.copy()
+        for _ in range(int(g['refine'])):
+            img, black = deploy_ref.stream_fake_net(tmp, k)
+            tmp[0, :, :, -1] = st.frame_of(img, black)
+        assert np.array_equal(tmp, g['tmp_in_x'][k])
+        st.push(img, black)
+    assert np.array_equal(np.concatenate(st.frames, 0), g['final_frames'])
+    assert np.array_equal(np.concatenate(st.masks, 0), g['final_masks'])
+
+
+@pytest.mark.reference
+def test_stream_golden_is_reference_output():
+    """the reference's statements are still where ref_loader picks them (line ranges of deploy_bundle.py)"""
+    import ref_loader
+    blocks = ref_loader.deploy_stream_blocks()
+    assert set(blocks) == {'assemble', 'refine', 'update'}

@@ -109,6 +109,32 @@ with torch.cuda.stream(s):
         dst_h.copy_(dst_d, non_blocking=True)
         s.synchronize()
         lat3.append((time.perf_counter() - t0) * 1e6)
+# the streaming state around it (deploy_bundle.py:259-274,319-328): input assembly from the history rings + push of the new frame
+state = mgw.StreamState(gray_h[0, ..., 0])
+cur2d = gray_d[0, ..., 0].contiguous()
+img2d, blk2d = o1[0, ..., 0].contiguous(), b1[0].contiguous()
+with torch.cuda.stream(s):
+    def state_call():
+        in_x = state.assemble(cur2d)
+        state.push(img2d, blk2d)
+        return in_x
+    dev_state = dev_time(state_call, 200, flush_l2=False)
+cpu_state_us = None
+try:
+    import collections
+    fr = [np.zeros((1, hn, wn, 1), np.float32) for _ in range(32)]; mk = [np.zeros((1, hn, wn, 1), np.float32) for _ in range(32)]
+    curn = gray_h.numpy().reshape(1, hn, wn, 1); imgn = np.zeros((hn, wn), np.float32); blkn = np.zeros((hn, wn), np.float32)
+    def cpu_state():
+        taps = (1, 2, 4, 8, 16, 32)
+        x = np.concatenate([mk[-i] for i in taps] + [fr[-i] for i in taps] + [curn], axis=3)
+        fr.append((imgn + blkn * (-1)).reshape(1, hn, wn, 1)); mk.append(blkn.reshape(1, hn, wn, 1)); fr.pop(0); mk.pop(0)
+        return x
+    tt = []
+    for _ in range(50):
+        t0 = time.perf_counter(); cpu_state(); tt.append((time.perf_counter() - t0) * 1e6)
+    cpu_state_us = float(np.median(tt))
+except Exception as e:      # noqa: BLE001
+    cpu_state_us = str(e)
 cpu_us = None
 try:
     import cv2
@@ -127,6 +153,7 @@ res['deploy_frame_288x512'] = {
     'us_device_graph_replay_warp_plus_remap': dev_frame, 'us_device_remap_only': dev_remap,
     'us_p50_host_to_host_u8_frames': float(np.percentile(lat3, 50)), 'us_p99_host_to_host': float(np.percentile(lat3, 99)),
     'us_cpu_opencv_remap_only': cpu_us, 'cpu_threads': os.cpu_count(),
+    'us_device_stream_state_assemble_plus_push': dev_state, 'us_cpu_numpy_stream_state': cpu_state_us,
     'note': '1x288x512: H2D gray fp32 + colour u8, K1 + K2 (C=1) + maps/4 + remap, D2H colour u8; CPU = the same three cv2 calls'}
 
 
