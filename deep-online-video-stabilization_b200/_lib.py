@@ -39,6 +39,11 @@ SIGNATURES = {
     'mgw_remap_bundle_u8': (c_i, [c_f, c_f, c_i, c_i, c_i, c_i, c_f, c_f, c_st]),
     'mgw_stream_assemble': (c_i, [c_f, c_f, c_i, c_i, ctypes.POINTER(ctypes.c_int), c_i, c_i, c_f, c_i, c_i, c_f, c_st]),
     'mgw_stream_push': (c_i, [c_f, c_f, c_i, c_i, c_f, c_f, c_i, c_i, c_f, c_i, c_st]),
+    'mgw_vertex_losses_fwd': (c_i, [c_f, c_f, c_f, c_i, c_i, c_i, c_fl, c_f, c_f, c_st]),
+    'mgw_vertex_losses_bwd': (c_i, [c_f, c_f, c_f, c_i, c_i, c_i, c_fl, c_f, c_f, c_f, c_f, c_st]),
+    'mgw_black_accumulate': (c_i, [c_f, c_f, c_i, c_st]),
+    'mgw_crop_rect_workspace_bytes': (ctypes.c_size_t, [c_i, c_i]),
+    'mgw_crop_rect': (c_i, [c_f, c_i, c_i, c_i, c_f, c_f, c_st]),
     'mgw_interp_fwd': (c_i, [c_f, c_f, c_f] + [c_i] * 6 + [c_f, c_st]),
     'mgw_interp_bwd': (c_i, [c_f, c_f, c_f, c_f] + [c_i] * 6 + [c_f, c_f, c_f, c_st]),
     'mgw_homography_warp_fwd': (c_i, [c_f, c_f] + [c_i] * 6 + [c_f, c_f, c_f, c_st]),

@@ -382,6 +382,44 @@ int mgw_stream_push(float* frames, float* masks, int depth, int slot, const floa
     return launch_stream_push(frames, masks, depth, slot, img, black, H, W, frame_out, out_stride, (cudaStream_t)stream);
 }
 
+int mgw_vertex_losses_fwd(const float* theta, const float* pts1, const float* pts2, int N, int gh, int gw, float do_crop_rate,
+                          float* sums, float* black_err, void* stream)
+{
+    REQUIRE(sums && (theta || pts1 || pts2), "mgw_vertex_losses_fwd: null pointer");
+    REQUIRE(!black_err || pts1, "mgw_vertex_losses_fwd: black_err needs pts1");
+    REQUIRE(N > 0 && gh > 0 && gw > 0 && do_crop_rate > 0.0f && (long long)N * (gh + 1) * (gw + 1) * 2 < (1LL << 31),
+            "mgw_vertex_losses_fwd: bad sizes");
+    return launch_vertex_losses_fwd(theta, pts1, pts2, N, gh, gw, do_crop_rate, sums, black_err, (cudaStream_t)stream);
+}
+
+int mgw_vertex_losses_bwd(const float* theta, const float* pts1, const float* pts2, int N, int gh, int gw, float do_crop_rate,
+                          const float* f, float* d_theta, float* d_pts1, float* d_pts2,
+                          void* stream)
+{
+    REQUIRE(f && (!d_theta || theta) && (!d_pts1 || pts1) && (!d_pts2 || pts2) && (d_theta || d_pts1 || d_pts2),
+            "mgw_vertex_losses_bwd: a gradient was requested without its input");
+    REQUIRE(N > 0 && gh > 0 && gw > 0 && do_crop_rate > 0.0f && (long long)N * (gh + 1) * (gw + 1) * 2 < (1LL << 31),
+            "mgw_vertex_losses_bwd: bad sizes");
+    return launch_vertex_losses_bwd(theta, pts1, pts2, N, gh, gw, do_crop_rate, f, d_theta, d_pts1, d_pts2,
+                                    (cudaStream_t)stream);
+}
+
+int mgw_black_accumulate(const float* black, int32_t* all_black, int n, void* stream)
+{
+    REQUIRE(black && all_black, "mgw_black_accumulate: null pointer");
+    REQUIRE(n > 0, "mgw_black_accumulate: bad sizes");
+    return launch_black_accumulate(black, all_black, n, (cudaStream_t)stream);
+}
+
+size_t mgw_crop_rect_workspace_bytes(int H, int W) { return (H > 0 && W > 0) ? crop_rect_workspace_bytes(H, W) : 0; }
+
+int mgw_crop_rect(const int32_t* all_black, int H, int W, int step, void* workspace, int32_t* rect, void* stream)
+{
+    REQUIRE(all_black && workspace && rect, "mgw_crop_rect: null pointer");
+    REQUIRE(H > 0 && W > 0 && step > 0 && (long long)H * W < (1LL << 31), "mgw_crop_rect: bad sizes");
+    return launch_crop_rect(all_black, H, W, step, workspace, rect, (cudaStream_t)stream);
+}
+
 int mgw_img_loss_fwd(const float* out, const float* y, const float* black, int N, int H, int W, int C, float* sums, void* stream)
 {
     REQUIRE(out && y && black && sums, "mgw_img_loss_fwd: null pointer");

@@ -85,6 +85,18 @@ size_t remap_bundle_workspace_bytes(int N, int H, int W);
 int launch_remap_bundle_u8(const uint8_t* img, const float* xy, int N, int H, int W, int C, uint8_t* dst, void* workspace,
                            cudaStream_t st);
 
+// mgw_vertex_loss.cu : vertex regularisers (s_net_bundle_nobm.py:139-210,246-247)
+int launch_vertex_losses_fwd(const float* theta, const float* pts1, const float* pts2, int N, int gh, int gw, float do_crop_rate,
+                             float* sums, float* black_err, cudaStream_t st);
+int launch_vertex_losses_bwd(const float* theta, const float* pts1, const float* pts2, int N, int gh, int gw, float do_crop_rate,
+                             const float* f, float* d_theta, float* d_pts1, float* d_pts2,
+                             cudaStream_t st);
+
+// mgw_crop.cu : deploy-side crop (deploy_bundle.py:240,291,344-365)
+int launch_black_accumulate(const float* black, int32_t* all_black, int n, cudaStream_t st);
+size_t crop_rect_workspace_bytes(int H, int W);
+int launch_crop_rect(const int32_t* all_black, int H, int W, int step, void* workspace, int32_t* rect, cudaStream_t st);
+
 // mgw_stream.cu : deploy-side streaming state (device-resident history rings, deploy_bundle.py:204-232,259-295,319-327)
 int launch_stream_assemble(const float* frames, const float* masks, int depth, int head, const int* taps_host, int ntaps, int use_masks,
                            const float* cur, int H, int W, float* in_x, cudaStream_t st);

@@ -11,7 +11,7 @@ import torch
 
 from . import ops
 
-__all__ = ['warpRevBundle2', 'StreamState']
+__all__ = ['warpRevBundle2', 'StreamState', 'CropState']
 
 
 def warpRevBundle2(img, x_map, y_map, device=None):
@@ -72,3 +72,31 @@ class StreamState:
         """(frames, masks) oldest first, as the reference's lists hold them"""
         order = [(self.head + 1 + k) % self.depth for k in range(self.depth)]
         return self.frames[order], self.masks[order]
+
+
+class CropState:
+    """The crop bookkeeping of deploy_bundle.py: `all_black` (:240) gathers every black mask the network produced (:291),
+    and after the last frame the largest never-black rectangle on the 10-pixel corner lattice (:344-365) is cut out of
+    every output frame (:368-370).
+
+        crop = CropState(height, width)
+        ... crop.add(black) after every network evaluation ...
+        top, left, bottom, right = crop.rect()
+        cut = crop.cut(frame)                            # frame[top:bottom+1, left:right+1, :]
+    """
+
+    def __init__(self, height, width, device='cuda'):
+        self.all_black = torch.zeros((height, width), device=device, dtype=torch.int32)
+
+    def add(self, black):
+        ops.black_accumulate(self.all_black, black)
+
+    def rect(self, step=10):
+        r = [int(v) for v in ops.crop_rect(self.all_black, step).cpu()]
+        if r[0] < 0:
+            raise IndexError('no black-free rectangle: every lattice corner has been black (the reference fails on ans[3] here)')
+        return r
+
+    def cut(self, frame, step=10):
+        t, l, b, r = self.rect(step)
+        return frame[..., t:b + 1, l:r + 1, :]

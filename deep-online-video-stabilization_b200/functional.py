@@ -158,3 +158,26 @@ class TempLoss(torch.autograd.Function):
         batch, use = ctx.cfg
         d1, d2 = ops.temp_loss_bwd(out1, black1, out2, black2, flow, sums, float(g) * use * out1.shape[0] / batch)
         return d1, None, d2, None, None, None, None
+
+
+class VertexLosses(torch.autograd.Function):
+    """The four vertex regularisers (reference s_net_bundle_nobm.py:139-210,246-247) as SUMS [4]: |theta|, black_err^2,
+    distortion residuals^2, lattice second differences^2.  Any input may be None."""
+
+    @staticmethod
+    def forward(ctx, theta, pts1, pts2, gh, gw, do_crop_rate):
+        c = [None if t is None else t.contiguous() for t in (theta, pts1, pts2)]
+        sums = ops.vertex_losses_fwd(c[0], c[1], c[2], gh, gw, do_crop_rate)
+        ctx.present = [t is not None for t in c]
+        ctx.save_for_backward(*[t for t in c if t is not None])
+        ctx.cfg = (gh, gw, do_crop_rate)
+        return sums
+
+    @staticmethod
+    def backward(ctx, g):
+        it = iter(ctx.saved_tensors)
+        theta, pts1, pts2 = [next(it) if p else None for p in ctx.present]
+        gh, gw, rate = ctx.cfg
+        need = tuple(ctx.needs_input_grad[k] for k in range(3))
+        d = ops.vertex_losses_bwd(theta, pts1, pts2, gh, gw, g.contiguous(), rate, need)
+        return d[0], d[1], d[2], None, None, None

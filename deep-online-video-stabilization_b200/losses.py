@@ -3,7 +3,10 @@
 Mirrors the reference expressions; `batch_size` defaults to the leading dimension (the reference hard-wires the
 config constant, s_net_bundle_nobm.py:348,352) and is the GLOBAL batch under data parallelism.
 """
+import torch
+
 from . import functional as F
+from . import ops
 
 
 def get_4_pts(theta, batch_size=None, grid=(4, 4), do_crop_rate=0.8):
@@ -33,3 +36,82 @@ def temp_loss(out1, black1, out2, black2, flow, use_temp_loss=1.0, batch_size=No
     n, h, w, _ = out1.shape
     return F.TempLoss.apply(out1, black1.reshape(n, h, w), out2, black2.reshape(n, h, w), flow, float(batch_size or n),
                             float(use_temp_loss))
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# vertex regularisers and the loss schedule (s_net_bundle_nobm.py:139-210,246-247,312-317,354-359; train_bundle_nobm.py:219-236)
+def _grid_of(pts1=None, pts2=None):
+    if pts1 is not None:
+        return int(pts1.shape[1]), int(pts1.shape[2])
+    return int(pts2.shape[1]) - 1, int(pts2.shape[2]) - 1
+
+
+def vertex_losses(theta, pts1, pts2, do_crop_rate=0.8, batch_size=None):
+    """All four head-only terms in one launch -> (id_loss_unscaled, black_pos_loss_ungated, distortion_loss, consistency_loss).
+    id_loss_unscaled = mean|theta| (the reference multiplies by id_mul, :246); black_pos_loss_ungated = mean(black_err^2)
+    (the reference multiplies by use_black_loss, :316).  batch_size: the divisor's batch (GLOBAL batch under data parallelism)."""
+    gh, gw = _grid_of(pts1, pts2)
+    n = float(batch_size or next(t for t in (theta, pts1, pts2) if t is not None).shape[0])
+    sums = F.VertexLosses.apply(theta, pts1, pts2, gh, gw, float(do_crop_rate))
+    terms = 2 * (max(gh - 1, 0) * (gw + 1) + (gh + 1) * max(gw - 1, 0))
+    return (sums[0] / (n * 2 * (gh + 1) * (gw + 1)), sums[1] / (n * gh * gw * 8), sums[2] / (n * gh * gw * 2) / 8,
+            sums[3] / (n * 2 * terms) if terms else sums[3] * 0)
+
+
+def get_black_pos(pts, do_crop_rate=0.8):
+    """reference s_net_bundle_nobm.py:139-148 -> black_err [N, gh*gw*8] (the display tensor ret['black_pos'] before squaring;
+    the differentiable path is vertex_losses / get_black_pos_loss)."""
+    gh, gw = _grid_of(pts)
+    _, err = ops.vertex_losses_fwd(None, pts.detach().contiguous(), None, gh, gw, float(do_crop_rate), want_black_err=True)
+    return err.reshape(pts.shape[0], -1)
+
+
+def get_black_pos_loss(pts1, use_black_loss=1.0, do_crop_rate=0.8, batch_size=None):
+    """reference s_net_bundle_nobm.py:312-317"""
+    return vertex_losses(None, pts1, None, do_crop_rate, batch_size)[1] * use_black_loss
+
+
+def get_distortion_loss(pts, batch_size=None):
+    """reference s_net_bundle_nobm.py:168-184 (pts = pts1 [N,gh,gw,8])"""
+    return vertex_losses(None, pts, None, 0.8, batch_size)[2]
+
+
+def get_consistency_loss(pts, batch_size=None):
+    """reference s_net_bundle_nobm.py:186-210 (pts = pts2 [N,gh+1,gw+1,2])"""
+    return vertex_losses(None, None, pts, 0.8, batch_size)[3]
+
+
+def loss_gates(i, no_theta_iter=1000000, do_temp_loss_iter=5000, do_theta_10_iter=-1, do_black_loss_iter=1000,
+               do_theta_only_iter=100):
+    """reference train_bundle_nobm.py:219-236 (defaults: configs/v2_93.py:39-43) -> dict(use_theta, use_temp, use_black, theta_only)
+    for training iteration i."""
+    use_theta = 0 if i > no_theta_iter else 1
+    if i <= do_theta_10_iter:
+        use_theta = 10
+    return dict(use_theta=use_theta, use_temp=1 if i >= do_temp_loss_iter else 0, use_black=1 if i >= do_black_loss_iter else 0,
+                theta_only=1 if i <= do_theta_only_iter else 0)
+
+
+# configs/v2_93.py:7-13,44-48
+V2_93_MULS = dict(feature_mul=1.0, theta_mul=400 / 2500, regu_mul=30 / 2500, img_mul=50.0, temp_mul=500.0, black_mul=300000 / 2500,
+                  id_mul=10 / 2500, distortion_mul=1.0, consistency_mul=20.0, grid_theta_mul=0.0)
+
+
+def total_loss(theta, pts1, pts2, img_loss, feature_loss, regu_loss=0.0, use_black_loss=1.0, use_theta_only=0.0, mul=None,
+               do_crop_rate=0.8, batch_size=None):
+    """reference s_net_bundle_nobm.py:308-317,354-359 for one pass: the head-only terms come from ONE launch of the vertex-loss
+    kernel; img_loss / feature_loss are the (already computed) image-side terms, regu_loss the network's weight regulariser.
+    -> (total_loss, dict of the weighted parts as in the reference's `ret`)."""
+    m = dict(V2_93_MULS)
+    m.update(mul or {})
+    idl, black, dist, cons = vertex_losses(theta, pts1, pts2, do_crop_rate, batch_size)
+    theta_loss = idl * m['id_mul']                      # id_loss == id2_loss (:246-247)
+    black = black * use_black_loss
+    total = theta_loss * m['theta_mul'] + theta_loss * m['grid_theta_mul'] + (1 - use_theta_only) * (
+        img_loss * m['img_mul'] + regu_loss * m['regu_mul'] + black * m['black_mul'] + dist * m['distortion_mul'] +
+        cons * m['consistency_mul'] + feature_loss * m['feature_mul'])
+    parts = dict(theta_loss=theta_loss * m['theta_mul'], grid_theta_loss=theta_loss * m['grid_theta_mul'], black_loss=black * m['black_mul'],
+                 distortion_loss=dist * m['distortion_mul'], consistency_loss=cons * m['consistency_mul'],
+                 feature_loss=feature_loss * m['feature_mul'], img_loss=img_loss * m['img_mul'],
+                 regu_loss=torch.as_tensor(regu_loss) * m['regu_mul'])
+    return total, parts

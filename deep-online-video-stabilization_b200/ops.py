@@ -351,3 +351,54 @@ def stream_push(frames, masks, slot, img, black, refeed_into=None):
         fo = refeed_into.data_ptr() + 4 * (stride - 1)
     with torch.cuda.device(ref.device):
         check(lib.mgw_stream_push(_p(frames), _p(masks), depth, int(slot), _p(img), _p(black), h, w, fo, stride, _st()), 'mgw_stream_push')
+
+
+def black_accumulate(all_black, black):
+    """deploy_bundle.py:291: all_black = all_black + np.round(black).astype(np.int64), in place on the device (int32 counts)."""
+    black, all_black = _chk(black, 'black'), _chk(all_black, 'all_black', torch.int32)
+    if black.numel() != all_black.numel():
+        raise ValueError('black has %d pixels, all_black %d' % (black.numel(), all_black.numel()))
+    with torch.cuda.device(black.device):
+        check(lib.mgw_black_accumulate(_p(black), _p(all_black), black.numel(), _st()), 'mgw_black_accumulate')
+    return all_black
+
+
+def crop_rect(all_black, step=10):
+    """deploy_bundle.py:344-365: [top, left, bottom, right] (inclusive, int32 device tensor) of the largest never-black
+    rectangle anchored on the `step` lattice of the top-left quadrant; -1s when there is none."""
+    all_black = _chk(all_black, 'all_black', torch.int32)
+    h, w = all_black.shape
+    ws = torch.empty(lib.mgw_crop_rect_workspace_bytes(h, w), device=all_black.device, dtype=torch.uint8)
+    rect = torch.empty(4, device=all_black.device, dtype=torch.int32)
+    with torch.cuda.device(all_black.device):
+        check(lib.mgw_crop_rect(_p(all_black), h, w, int(step), _p(ws), _p(rect), _st()), 'mgw_crop_rect')
+    return rect
+
+
+def vertex_losses_fwd(theta, pts1, pts2, gh, gw, do_crop_rate=0.8, want_black_err=False):
+    """sums[4] of mgw_vertex_losses_fwd (id, black_pos, distortion, consistency); inputs may be None (term skipped)."""
+    theta = None if theta is None else _chk(theta, 'theta')
+    pts1 = None if pts1 is None else _chk(pts1, 'pts1')
+    pts2 = None if pts2 is None else _chk(pts2, 'pts2')
+    ref = next(t for t in (theta, pts1, pts2) if t is not None)
+    n = ref.shape[0]
+    for t, cnt, name in ((theta, 2 * (gh + 1) * (gw + 1), 'theta'), (pts1, gh * gw * 8, 'pts1'), (pts2, 2 * (gh + 1) * (gw + 1), 'pts2')):
+        if t is not None and (t.shape[0] != n or t.numel() != n * cnt):
+            raise ValueError('%s has shape %s for a %dx%d grid, batch %d' % (name, tuple(t.shape), gh, gw, n))
+    sums = torch.empty(4, device=ref.device, dtype=torch.float32)
+    err = torch.empty((n, gh, gw, 8), device=ref.device, dtype=torch.float32) if want_black_err else None
+    with torch.cuda.device(ref.device):
+        check(lib.mgw_vertex_losses_fwd(_p(theta), _p(pts1), _p(pts2), n, gh, gw, do_crop_rate, _p(sums), _p(err), _st()),
+              'mgw_vertex_losses_fwd')
+    return (sums, err) if want_black_err else sums
+
+
+def vertex_losses_bwd(theta, pts1, pts2, gh, gw, f, do_crop_rate=0.8, need=(True, True, True)):
+    """f [4] (device) = d(total)/d(sums[k]) -> (d_theta, d_pts1, d_pts2), None where not needed."""
+    f = _chk(f, 'f')
+    ref = next(t for t in (theta, pts1, pts2) if t is not None)
+    outs = [torch.empty_like(t) if (t is not None and nd) else None for t, nd in zip((theta, pts1, pts2), need)]
+    with torch.cuda.device(ref.device):
+        check(lib.mgw_vertex_losses_bwd(_p(theta), _p(pts1), _p(pts2), ref.shape[0], gh, gw, do_crop_rate, _p(f),
+                                        _p(outs[0]), _p(outs[1]), _p(outs[2]), _st()), 'mgw_vertex_losses_bwd')
+    return tuple(outs)

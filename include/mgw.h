@@ -133,6 +133,33 @@ MGW_API int mgw_stream_assemble(const float* frames, const float* masks, int dep
 MGW_API int mgw_stream_push(float* frames, float* masks, int depth, int slot, const float* img, const float* black, int H, int W,
                     float* frame_out, int out_stride, void* stream);
 
+/* ---- f4 (training side): the vertex regularisers of s_net_bundle_nobm.py ------------------------------------------------
+ * theta [N, 2*(gh+1)*(gw+1)] (the head output), pts1 [N,gh,gw,8], pts2 [N,gh+1,gw+1,2] (mgw_vertices_fwd's outputs); each
+ * nullable, its terms are then skipped.  sums[4] (device, overwritten):
+ *   [0] sum |theta|                       id loss :246-247        = sums[0] / (N*2*(gh+1)*(gw+1)) * id_mul
+ *   [1] sum black_err^2 over pts1         black_pos :139-148,313-317   mean = sums[1] / (N*gh*gw*8)  (times use_black_loss)
+ *   [2] sum of the 8 squared rotated-edge residuals per cell   distortion :150-184   loss = sums[2] / (N*gh*gw*2) / 8
+ *   [3] sum of squared lattice second differences over pts2    consistency :186-210  loss = sums[3] / (N*2*K),
+ *       K = 2*((gh-1)*(gw+1) + (gh+1)*(gw-1)) listed terms (0 terms -> loss 0)
+ * black_err [N,gh,gw,8] nullable = get_black_pos(pts1) before the reshape.
+ * mgw_vertex_losses_bwd: f[4] (device) = d(total)/d(sums[k]); d_theta (id term only), d_pts1, d_pts2 nullable, overwritten. */
+MGW_API int mgw_vertex_losses_fwd(const float* theta, const float* pts1, const float* pts2, int N, int gh, int gw,
+                          float do_crop_rate, float* sums, float* black_err, void* stream);
+MGW_API int mgw_vertex_losses_bwd(const float* theta, const float* pts1, const float* pts2, int N, int gh, int gw,
+                          float do_crop_rate, const float* f, float* d_theta, float* d_pts1,
+                          float* d_pts2, void* stream);
+
+/* ---- f4 (deploy side): the crop of deploy_bundle.py:240,291,344-365 -------------------------------------------------
+ * mgw_black_accumulate: all_black[p] += round(black[p])  (all_black = all_black + np.round(black).astype(np.int64), :291;
+ *   int32 counts: one increment per network evaluation).
+ * mgw_crop_rect: rect[4] (device) = the reference's `ans` = [top, left, bottom, right] (inclusive) of the largest rectangle
+ *   free of ever-black pixels whose top-left corner (i, j) has i in range(0, H/2, step), j in range(0, W/2, step)
+ *   (step = 10 in the reference), ties resolved like the reference's loops (first found); rect = -1,-1,-1,-1 when every
+ *   corner is black (the reference raises IndexError there).  workspace: mgw_crop_rect_workspace_bytes() device bytes. */
+MGW_API int mgw_black_accumulate(const float* black, int32_t* all_black, int n, void* stream);
+MGW_API size_t mgw_crop_rect_workspace_bytes(int H, int W);
+MGW_API int mgw_crop_rect(const int32_t* all_black, int H, int W, int step, void* workspace, int32_t* rect, void* stream);
+
 /* ---- a6: interpolate(im, x, y, out_size), spatial_transformer.py:200-281 ------------------------------
  * im [N,IH,IW,C]; x,y [N,OH,OW] normalised coords -> out [N,OH,OW,C]. */
 MGW_API int mgw_interp_fwd(const float* im, const float* x, const float* y, int N, int IH, int IW, int C, int OH, int OW,

@@ -150,3 +150,33 @@ def stream_fake_net(in_x, k):
     img = (0.7 * in_x[0, :, :, -1] + 0.3 * in_x[0, :, :, 6] + 0.05 * r.standard_normal((h, w))).astype(np.float32)
     black = (r.random_sample((h, w)) < 0.1).astype(np.float32)
     return img.reshape(1, h, w, 1), black.reshape(1, h, w)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# crop of deploy_bundle.py (:240,291 accumulation; :344-365 search)
+def black_accumulate(all_black, black):
+    """:291  all_black = all_black + np.round(black).astype(np.int64)"""
+    return all_black + np.round(np.asarray(black, np.float32).reshape(all_black.shape)).astype(np.int64)
+
+
+def crop_rect(all_black, step=10):
+    """:344-365 restated without the per-pixel loops: for a corner (i, j) on the lattice the widest black-free rectangle
+    of height hh-i+1 ends at j + min(run[i..hh][j]) - 1, run[r][c] = count of consecutive zeros from (r, c) rightwards; the
+    answer is the FIRST (i, j, hh) in loop order reaching the maximum area (the reference updates on a strict `>`).
+    Returns [i, j, hh, ww] or [] (the reference's `ans`)."""
+    ab = np.asarray(all_black)
+    H, W = ab.shape
+    run = np.zeros((H, W + 1), np.int64)
+    for c in range(W - 1, -1, -1):
+        run[:, c] = np.where(ab[:, c] > 0, 0, run[:, c + 1] + 1)
+    max_s, ans = 0, []
+    for i in range(0, H // 2, step):
+        for j in range(0, W // 2, step):
+            if ab[i, j] > 0:
+                continue
+            w = np.minimum.accumulate(run[i:, j])
+            area = w * np.arange(1, H - i + 1)
+            k = int(np.argmax(area))                       # first maximum
+            if area[k] > max_s:
+                max_s, ans = int(area[k]), [i, j, i + k, j + int(w[k]) - 1]
+    return ans

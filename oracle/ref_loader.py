@@ -102,6 +102,35 @@ def s_net_namespace(height, width, grid_h, grid_w, batch_size, max_matches, do_c
     return _exec_nodes(wanted, ns, 's_net_bundle_nobm.py')
 
 
+def s_net_regularisers(ns):
+    """get_black_pos, calc_distortion_loss, get_distortion_loss, get_consistency_loss of s_net_bundle_nobm.py:139-210 as
+    callables, added to a namespace made by s_net_namespace()."""
+    tree = _parse('s_net_bundle_nobm.py')
+    names = ('get_black_pos', 'calc_distortion_loss', 'get_distortion_loss', 'get_consistency_loss')
+    wanted = [n for n in tree.body if isinstance(n, ast.FunctionDef) and n.name in names]
+    assert len(wanted) == 4
+    return _exec_nodes(wanted, dict(ns), 's_net_bundle_nobm.py')
+
+
+def s_net_black_loss(ns, pts1, use_black_loss):
+    """the black_loss block of inference_stable_net (s_net_bundle_nobm.py:312-317) -> black_pos_loss"""
+    tree = _parse('s_net_bundle_nobm.py')
+    fn = [n for n in tree.body if isinstance(n, ast.FunctionDef) and n.name == 'inference_stable_net'][0]
+    outer = [n for n in fn.body if isinstance(n, ast.With)][0]
+    blocks = [n for n in outer.body if _scope_name(n) == 'black_loss']
+    assert len(blocks) == 1
+    ns = dict(ns)
+    ns.update(pts1=pts1)
+    t = ns['tf']
+    saved = t.placeholder
+    t.placeholder = lambda *a, **k: use_black_loss
+    try:
+        _exec_nodes(blocks, ns, 's_net_bundle_nobm.py')
+    finally:
+        t.placeholder = saved
+    return ns['black_pos_loss'], ns['black_pos']
+
+
 def s_net_losses(ns, matches, mask, flow, h_trans, y, black_pix):
     """feature_loss and img_loss blocks of inference_stable_net (s_net_bundle_nobm.py:335-352)."""
     tree = _parse('s_net_bundle_nobm.py')
@@ -169,3 +198,15 @@ def deploy_stream_blocks():
         return compile(ast.Module(body=nodes, type_ignores=[]), os.path.join(REF, 'deploy_bundle.py'), 'exec')
 
     return {'assemble': pick(259, 283), 'refine': pick(284, 295), 'update': pick(319, 328)}
+
+
+def deploy_crop_block():
+    """The crop search of deploy_bundle.py:344-365 (summed-area table + the four nested loops that leave `max_s`, `ans`) as a
+    code object compiled from the reference's own statements in the `finally:` clause.  Runs in a namespace that supplies
+    np, math, height, width and all_black (int64 [height,width]); prints progress (silence it with quiet())."""
+    tree = _parse('deploy_bundle.py')
+    tries = [n for n in ast.walk(tree) if isinstance(n, ast.Try) and any(m.lineno == 344 for m in n.finalbody)]
+    assert len(tries) == 1
+    nodes = [n for n in tries[0].finalbody if 344 <= n.lineno <= 365]
+    assert [type(n).__name__ for n in nodes] == ['Assign', 'For', 'Assign', 'Assign', 'For'], [type(n).__name__ for n in nodes]
+    return compile(ast.Module(body=nodes, type_ignores=[]), os.path.join(REF, 'deploy_bundle.py'), 'exec')

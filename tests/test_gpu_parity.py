@@ -497,6 +497,114 @@ def test_deploy_stream_state_exact(mgw):
     assert np.array_equal(fr.cpu().numpy()[..., None], g['final_frames']) and np.array_equal(mk.cpu().numpy()[..., None], g['final_masks'])
 
 
+def test_vertex_regularisers_match_the_reference(mgw):
+    """id / black_pos / distortion / consistency (mgw_vertex_losses_fwd/bwd) against the reference's own functions (fixture):
+    values 1e-5 relative, gradients 1e-4 of the largest entry (north_star tolerances; observed ~1e-6)."""
+    g = load_golden('vertex_losses')
+
+    def close(a, b, tol):
+        a, b = np.asarray(a.detach().cpu() if torch.is_tensor(a) else a, np.float64), np.asarray(b, np.float64)
+        assert a.shape == b.shape, (a.shape, b.shape)
+        return np.abs(a - b).max() <= tol * max(np.abs(b).max(), 1e-30) + 1e-12
+
+    for gi, (gh, gw) in enumerate(g['grids']):
+        gh, gw = int(gh), int(gw)
+        head = dev(g['g%d_head' % gi]).requires_grad_(True)
+        raw = dev(g['g%d_raw' % gi]).requires_grad_(True)
+        pts1, pts2 = mgw.get_4_pts(head, grid=(gh, gw))
+        pts1.retain_grad(); pts2.retain_grad()
+        idl, _, dist, cons = mgw.vertex_losses(head, pts1, pts2)
+        black = mgw.get_black_pos_loss(raw)
+        assert mgw.get_black_pos_loss(pts1).item() == 0.0            # clamped vertices cannot overshoot (get_4_pts :58)
+        for tag in ('ref', 'f64'):
+            k = 'g%d_%s_' % (gi, tag)
+            assert close(idl, g[k + 'id'], 1e-5) and close(black, g[k + 'black'], 1e-5), (gh, gw, tag)
+            assert close(dist, g[k + 'dist'], 1e-5) and close(cons, g[k + 'cons'], 1e-5), (gh, gw, tag)
+        assert np.array_equal(mgw.get_black_pos(raw).cpu().numpy(), g['g%d_ref_black_err' % gi])
+        k = 'g%d_f64_' % gi
+        assert close(torch.autograd.grad(idl, head, retain_graph=True)[0], g[k + 'did_dhead'], 1e-6)
+        assert close(torch.autograd.grad(black, raw)[0], g[k + 'dblack_draw'], 1e-5)
+        gd = torch.autograd.grad(dist, [head, pts1], retain_graph=True)
+        assert close(gd[0], g[k + 'ddist_dhead'], 1e-5) and close(gd[1], g[k + 'ddist_dpts1'], 1e-5), (gh, gw)
+        if cons.requires_grad and np.abs(g[k + 'dcons_dpts2']).max() > 0:
+            gc = torch.autograd.grad(cons, [head, pts2], retain_graph=True)
+            assert close(gc[0], g[k + 'dcons_dhead'], 1e-5) and close(gc[1], g[k + 'dcons_dpts2'], 1e-5), (gh, gw)
+        # the named single-term entry points are the same numbers
+        assert float(mgw.get_distortion_loss(pts1)) == float(dist) and float(mgw.get_consistency_loss(pts2)) == float(cons)
+
+
+def test_total_loss_and_schedule(mgw):
+    """total_loss (s_net_bundle_nobm.py:354-359) and loss_gates (train_bundle_nobm.py:219-236) against the restatement; the
+    gradient of the whole head-only part reaches the head through ONE vertex-loss backward + mgw_vertices_bwd."""
+    import vertex_loss_ref as V
+    for i in (0, 100, 101, 999, 1000, 4999, 5000, 10 ** 6 + 1):
+        gates = mgw.loss_gates(i)
+        assert (gates['use_theta'], gates['use_temp'], gates['use_black'], gates['theta_only']) == V.loss_gates(i)
+    g = load_golden('vertex_losses')
+    head_np, raw = g['g0_head'], g['g0_raw']
+    head = dev(head_np).requires_grad_(True)
+    pts1, pts2 = mgw.get_4_pts(head, grid=(4, 4))
+    img_l, feat_l = torch.tensor(0.37, device='cuda'), torch.tensor(0.011, device='cuda')
+    total, parts = mgw.total_loss(head, pts1, pts2, img_l, feat_l, regu_loss=0.5, use_black_loss=1.0, use_theta_only=0.0)
+    p1, p2 = g['g0_f64_pts1'], g['g0_f64_pts2']
+    idl, gid = V.id_loss(head_np.astype(np.float64))
+    bl, _, _ = V.black_pos_loss(p1)
+    dl, gd1 = V.distortion_loss(p1, 4, 4)
+    cl, gc2 = V.consistency_loss(p2, 4, 4)
+    m = mgw.losses.V2_93_MULS
+    want = V.total_loss(idl * m['id_mul'], idl * m['id_mul'], 0.37, 0.5, bl, dl, cl, 0.011, 0.0, m)
+    assert abs(float(total) - want) <= 1e-5 * abs(want)
+    assert abs(float(parts['consistency_loss']) - cl * m['consistency_mul']) <= 1e-5 * abs(cl * m['consistency_mul'])
+    (dh,) = torch.autograd.grad(total, head)
+    want_dh = (gid * m['id_mul'] * (m['theta_mul'] + m['grid_theta_mul']) + g['g0_f64_ddist_dhead'] * m['distortion_mul'] +
+               g['g0_f64_dcons_dhead'] * m['consistency_mul'])
+    assert np.abs(dh.cpu().numpy() - want_dh).max() <= 1e-5 * np.abs(want_dh).max()
+    # theta_only = 1 switches everything but the id terms off
+    t1, _ = mgw.total_loss(head, pts1, pts2, img_l, feat_l, use_theta_only=1.0)
+    assert abs(float(t1) - idl * m['id_mul'] * (m['theta_mul'] + m['grid_theta_mul'])) <= 1e-6 * float(t1)
+
+
+def test_deploy_crop_exact(mgw):
+    """CropState (mgw_black_accumulate / mgw_crop_rect) == the reference's loops (fixture) and the restatement (larger sizes)."""
+    import deploy_ref
+    g = load_golden('deploy_crop')
+    for name in sorted(k[:-4] for k in g if k.endswith('_ans')):
+        ab = torch.as_tensor(g[name + '_all_black'].astype(np.int32)).cuda()
+        rect = mgw.ops.crop_rect(ab).cpu().tolist()
+        want = g[name + '_ans'].tolist()
+        assert rect == (want if want else [-1, -1, -1, -1]), name
+    crop = mgw.CropState(44, 70)
+    crop.all_black.copy_(torch.as_tensor(g['all_corners_black_all_black'].astype(np.int32)))
+    with pytest.raises(IndexError):
+        crop.rect()
+    # accumulation: the reference's own `all_black` after 40 frames x 2 refine passes of the stream fixture
+    s = load_golden('deploy_stream')
+    h, w = s['first'].shape
+    crop, ref = mgw.CropState(h, w), deploy_ref.StreamStateRef(s['first'])
+    for k in range(s['cur_frames'].shape[0]):
+        in_x = ref.assemble(s['cur_frames'][k])
+        for _ in range(int(s['refine'])):
+            img, black = deploy_ref.stream_fake_net(in_x, k)
+            crop.add(dev(black))
+            in_x[..., -1] = ref.frame_of(img, black)
+        ref.push(img, black)
+    assert np.array_equal(crop.all_black.cpu().numpy().astype(np.int64), s['all_black'])
+    # full-size and ragged masks against the restatement, several steps
+    r = np.random.RandomState(3)
+    for (H, W, step, dens) in [(288, 512, 10, 0.0005), (288, 512, 10, 0.0), (287, 509, 7, 0.002), (33, 31, 1, 0.05), (2, 2, 10, 0.0),
+                               (720, 1280, 10, 0.0002)]:
+        ab = (r.random_sample((H, W)) < dens).astype(np.int64) * 3
+        ab[:min(3, H), :] += r.randint(0, 2, (min(3, H), W))
+        ab[:, -2:] += 1
+        got = mgw.ops.crop_rect(torch.as_tensor(ab.astype(np.int32)).cuda(), step).cpu().tolist()
+        want = deploy_ref.crop_rect(ab, step)
+        assert got == (want if want else [-1, -1, -1, -1]), (H, W, step)
+        frame = torch.arange(H * W * 3, device='cuda').reshape(H, W, 3)
+        if want:
+            c = mgw.CropState(H, W); c.all_black.copy_(torch.as_tensor(ab.astype(np.int32)))
+            assert torch.equal(c.cut(frame, step), frame[want[0]:want[2] + 1, want[1]:want[3] + 1, :])
+
+
 def test_errors_are_loud(mgw):
     with pytest.raises(RuntimeError):
         mgw.transformer(torch.zeros(1, 8, 8, 3), torch.zeros(1, 5, 5, 2))          # CPU tensors: no fallback

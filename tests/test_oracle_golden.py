@@ -197,3 +197,82 @@ def test_stream_golden_is_reference_output():
     import ref_loader
     blocks = ref_loader.deploy_stream_blocks()
     assert set(blocks) == {'assemble', 'refine', 'update'}
+
+
+def test_crop_oracle_matches_the_reference_loops():
+    """deploy_ref.crop_rect (run-length restatement) == `ans` of deploy_bundle.py:344-365 executed verbatim (fixture)"""
+    import deploy_ref
+    g = load_golden('deploy_crop')
+    names = sorted(k[:-4] for k in g if k.endswith('_ans'))
+    assert len(names) >= 6
+    for name in names:
+        ans = deploy_ref.crop_rect(g[name + '_all_black'])
+        assert ans == g[name + '_ans'].tolist(), name
+        if ans:
+            assert (ans[2] - ans[0] + 1) * (ans[3] - ans[1] + 1) == int(g[name + '_max_s'])
+            assert g[name + '_all_black'][ans[0]:ans[2] + 1, ans[1]:ans[3] + 1].sum() == 0
+    s = load_golden('deploy_stream')
+    ab = np.zeros(s['first'].shape, np.int64)
+    ref = deploy_ref.StreamStateRef(s['first'])
+    for k in range(s['cur_frames'].shape[0]):
+        in_x = ref.assemble(s['cur_frames'][k])
+        for _ in range(int(s['refine'])):
+            img, black = deploy_ref.stream_fake_net(in_x, k)
+            ab = deploy_ref.black_accumulate(ab, black)
+            in_x[..., -1] = ref.frame_of(img, black)
+        ref.push(img, black)
+    assert np.array_equal(ab, s['all_black'])
+
+
+@pytest.mark.reference
+def test_crop_golden_is_reference_output():
+    """regenerate one crop case from the reference's own statements"""
+    import math
+    import ref_loader
+    g = load_golden('deploy_crop')
+    ab = g['tie_all_black']
+    ns = dict(np=np, math=math, height=ab.shape[0], width=ab.shape[1], all_black=ab)
+    ref_loader.quiet(exec, ref_loader.deploy_crop_block(), ns)
+    assert ns['ans'] == g['tie_ans'].tolist() and ns['max_s'] == int(g['tie_max_s'])
+
+
+def test_vertex_loss_oracle_matches_the_reference_functions():
+    """oracle/vertex_loss_ref.py (closed forms, values + gradients) == the reference's get_black_pos / get_distortion_loss /
+    get_consistency_loss / id loss run on the shim (fixture), fp32 to rounding and fp64 to 1e-12"""
+    import vertex_loss_ref as V
+    g = load_golden('vertex_losses')
+
+    def rel(a, b):
+        a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+        return np.abs(a - b).max() / max(np.abs(b).max(), 1e-30) if np.abs(b).max() > 0 else np.abs(a).max()
+
+    assert len(g['grids']) >= 5
+    for gi, (gh, gw) in enumerate(g['grids']):
+        for tag, dt, tol in (('ref', np.float32, 2e-6), ('f64', np.float64, 1e-12)):
+            k = 'g%d_%s_' % (gi, tag)
+            head, raw = g['g%d_head' % gi].astype(dt), g['g%d_raw' % gi].astype(dt)
+            p1, p2 = g[k + 'pts1'].astype(dt), g[k + 'pts2'].astype(dt)
+            v, gr = V.id_loss(head)
+            assert rel(v, g[k + 'id']) <= tol and rel(gr, g[k + 'did_dhead']) <= tol
+            v, gr, err = V.black_pos_loss(raw)
+            assert rel(v, g[k + 'black']) <= tol and rel(gr, g[k + 'dblack_draw']) <= tol
+            assert rel(err.reshape(err.shape[0], -1), g[k + 'black_err']) <= tol
+            assert rel((err * err).reshape(err.shape[0], -1), g[k + 'black_pos']) <= tol
+            assert V.black_pos_loss(p1)[0] == 0 and g[k + 'black_clamped'] == 0
+            v, gr = V.distortion_loss(p1, int(gh), int(gw))
+            assert rel(v, g[k + 'dist']) <= tol and rel(gr, g[k + 'ddist_dpts1']) <= tol, (gh, gw, tag)
+            v, gr = V.consistency_loss(p2, int(gh), int(gw))
+            assert rel(v, g[k + 'cons']) <= tol and rel(gr, g[k + 'dcons_dpts2']) <= tol, (gh, gw, tag)
+
+
+@pytest.mark.reference
+def test_vertex_loss_golden_is_reference_output():
+    """regenerate one value from the reference's own function"""
+    import ref_loader
+    import torch
+    g = load_golden('vertex_losses')
+    gh, gw = (int(v) for v in g['grids'][1])
+    ns = ref_loader.s_net_regularisers(ref_loader.s_net_namespace(8, 8, gh, gw, 3, 1))
+    pts1, pts2 = ns['get_4_pts'](torch.as_tensor(g['g1_head']), 3)
+    assert np.allclose(ref_loader.quiet(ns['get_distortion_loss'], pts1).numpy(), g['g1_ref_dist'], rtol=1e-6)
+    assert np.allclose(ref_loader.quiet(ns['get_consistency_loss'], pts2).numpy(), g['g1_ref_cons'], rtol=1e-6)

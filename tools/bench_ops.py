@@ -55,4 +55,22 @@ timeit('feature_loss_fwd (3000 matches/sample)', lambda: ops.feature_loss_fwd(ma
 timeit('feature_loss_bwd', lambda: ops.feature_loss_bwd(matches, mask, img, 1.0), n * M * 28 + P * 8)
 head = torch.tensor(synth.randn((n, 50), 6, 0.05), device=dev)
 timeit('vertices_fwd (get_4_pts)', lambda: ops.vertices_fwd(head, 4, 4), n * 50 * 12)
+pts1, pts2 = ops.vertices_fwd(head, 4, 4)
+f4 = torch.ones(4, device=dev)
+timeit('vertex_losses_fwd (id+black_pos+distortion+consistency)', lambda: ops.vertex_losses_fwd(head, pts1, pts2, 4, 4), n * (50 + 128 + 50) * 4)
+timeit('vertex_losses_bwd', lambda: ops.vertex_losses_bwd(head, pts1, pts2, 4, 4, f4), n * (50 + 128 + 50) * 8)
+# deploy-side crop (deploy_bundle.py:291,344-365) at the network's frame size: accumulation per frame, search once per video
+blk = (torch.rand(H, W, device=dev) < 0.03).float()
+ab = torch.zeros(H, W, device=dev, dtype=torch.int32)
+timeit('black_accumulate 288x512', lambda: ops.black_accumulate(ab, blk), H * W * 12)
+yy, xx = np.mgrid[0:H, 0:W]
+border = ((yy < 12 + 8 * np.sin(xx / 37.0)) | (xx < 18 + 10 * np.cos(yy / 23.0)) | (yy > H - 14 - 6 * np.sin(xx / 51.0)) |
+          (xx > W - 16 + 8 * np.sin(yy / 29.0))).astype(np.int32)
+abv = torch.tensor(border, device=dev)
+timeit('crop_rect 288x512 (390 corners)', lambda: ops.crop_rect(abv), H * W * 8)
+import time, deploy_ref
+t0 = time.perf_counter(); want = deploy_ref.crop_rect(border.astype(np.int64)); t_np = time.perf_counter() - t0
+assert ops.crop_rect(abv).cpu().tolist() == want
+res['crop_rect 288x512 (390 corners)']['numpy_restatement_us'] = round(t_np * 1e6, 0)
+res['crop_rect 288x512 (390 corners)']['rect'] = want
 print(json.dumps(res))
