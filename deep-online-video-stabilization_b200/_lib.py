@@ -34,7 +34,7 @@ SIGNATURES = {
     'mgw_mesh_warp_bwd_acc': (c_i, [c_f, c_f, c_f, c_f, c_f] + [c_i] * 6 + [c_f, c_f, c_f, c_st]),
     'mgw_mesh_warp_img_loss_fwd': (c_i, [c_f, c_f, c_f] + [c_i] * 6 + [c_f, c_f, c_f, c_f, c_f, c_st]),
     'mgw_mesh_warp_img_loss_bwd_workspace_bytes': (ctypes.c_size_t, [c_i] * 6),
-    'mgw_mesh_warp_img_loss_bwd': (c_i, [c_f] * 7 + [c_fl, c_fl, c_f] + [c_i] * 6 + [c_f, c_f, c_f, c_st]),
+    'mgw_mesh_warp_img_loss_bwd': (c_i, [c_f] * 7 + [c_fl, c_f, c_fl, c_f] + [c_i] * 6 + [c_f, c_f, c_f, c_st]),
     'mgw_remap_bundle_u8_workspace_bytes': (ctypes.c_size_t, [c_i, c_i, c_i]),
     'mgw_remap_bundle_u8': (c_i, [c_f, c_f, c_i, c_i, c_i, c_i, c_f, c_f, c_st]),
     'mgw_stream_assemble': (c_i, [c_f, c_f, c_i, c_i, ctypes.POINTER(ctypes.c_int), c_i, c_i, c_f, c_i, c_i, c_f, c_st]),
@@ -49,11 +49,11 @@ SIGNATURES = {
     'mgw_homography_warp_fwd': (c_i, [c_f, c_f] + [c_i] * 6 + [c_f, c_f, c_f, c_st]),
     'mgw_homography_warp_bwd': (c_i, [c_f, c_f, c_f] + [c_i] * 6 + [c_f, c_f, c_st]),
     'mgw_img_loss_fwd': (c_i, [c_f, c_f, c_f] + [c_i] * 4 + [c_f, c_st]),
-    'mgw_img_loss_bwd': (c_i, [c_f, c_f, c_f, c_f, c_fl] + [c_i] * 4 + [c_f, c_st]),
+    'mgw_img_loss_bwd': (c_i, [c_f, c_f, c_f, c_f, c_fl, c_f] + [c_i] * 4 + [c_f, c_st]),
     'mgw_feature_loss_fwd': (c_i, [c_f, c_f, c_f] + [c_i] * 4 + [c_f, c_f, c_st]),
-    'mgw_feature_loss_bwd': (c_i, [c_f, c_f, c_f, c_fl] + [c_i] * 4 + [c_f, c_st]),
+    'mgw_feature_loss_bwd': (c_i, [c_f, c_f, c_f, c_fl, c_f] + [c_i] * 4 + [c_f, c_st]),
     'mgw_temp_loss_fwd': (c_i, [c_f] * 5 + [c_i] * 4 + [c_f, c_st]),
-    'mgw_temp_loss_bwd': (c_i, [c_f] * 6 + [c_fl] + [c_i] * 4 + [c_f, c_f, c_st]),
+    'mgw_temp_loss_bwd': (c_i, [c_f] * 6 + [c_fl, c_f] + [c_i] * 4 + [c_f, c_f, c_st]),
 }
 
 

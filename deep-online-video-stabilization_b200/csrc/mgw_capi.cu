@@ -181,7 +181,7 @@ static int warp_bwd_core(const float* U, const float* Hs, const float* d_out, co
     TRY(check_memset(cudaMemsetAsync(dHs_acc, 0, sizeof(float) * ncell * 9, st), "memset dHs"));
     if (fl) {       // generic path: materialise d_out of the fused loss first
         if (!d_out_scratch) return set_error(MGW_ERR_INVALID, "fused img_loss backward: workspace too small for the generic path");
-        TRY(launch_img_loss_bwd(fl->out, fl->y, fl->black, fl->sums, fl->kscale * 0.5f * (float)s.N, s.N, s.H, s.W, s.C, d_out_scratch, st));
+        TRY(launch_img_loss_bwd(fl->out, fl->y, fl->black, fl->sums, fl->kscale * 0.5f * (float)s.N, fl->kscale_dev, s.N, s.H, s.W, s.C, d_out_scratch, st));
         d_out = d_out_scratch;
     }
     TRY(launch_warp_bwd_generic(U, Hs, d_out, d_img, s, false, dU, dHs_acc, st));
@@ -289,8 +289,8 @@ size_t mgw_mesh_warp_img_loss_bwd_workspace_bytes(int N, int H, int W, int C, in
 }
 
 int mgw_mesh_warp_img_loss_bwd(const float* U, const float* theta, const float* Hs, const float* out, const float* y,
-                               const float* black, const float* sums, float upstream, float batch, const float* d_img, int N,
-                               int H, int W, int C, int gh, int gw, float* dU, float* dtheta, void* workspace, void* stream)
+                               const float* black, const float* sums, float upstream, const float* upstream_dev, float batch, const float* d_img,
+                               int N, int H, int W, int C, int gh, int gw, float* dU, float* dtheta, void* workspace, void* stream)
 {
     REQUIRE(U && theta && Hs && out && y && black && sums && dtheta && workspace, "mgw_mesh_warp_img_loss_bwd: null pointer");
     TRY(validate_mesh_shape("mgw_mesh_warp_img_loss_bwd", N, H, W, C, gh, gw));
@@ -303,7 +303,7 @@ int mgw_mesh_warp_img_loss_bwd(const float* U, const float* theta, const float* 
     void* tma_ws = tma_bytes ? (void*)((char*)workspace + off) : nullptr;
     const size_t base = align_up(mgw_mesh_warp_bwd_workspace_bytes(N, H, W, C, gh, gw), 256);
     float* scratch = (mgw_mesh_warp_img_loss_bwd_workspace_bytes(N, H, W, C, gh, gw) > base) ? (float*)((char*)workspace + base) : nullptr;
-    const FusedImgLoss fl{out, y, black, sums, upstream * 2.0f / batch};
+    const FusedImgLoss fl{out, y, black, sums, upstream * 2.0f / batch, upstream_dev};
     const float* parts; int np, ps;
     TRY(warp_bwd_core(U, Hs, nullptr, d_img, s, dU, dHs_acc, tma_ws, &parts, &np, &ps, st, &fl, scratch));
     return launch_solve_h_bwd(theta, Hs, parts, np, ps, N, gh, gw, dtheta, st);
@@ -427,12 +427,13 @@ int mgw_img_loss_fwd(const float* out, const float* y, const float* black, int N
     return launch_img_loss_fwd(out, y, black, N, H, W, C, sums, (cudaStream_t)stream);
 }
 
-int mgw_img_loss_bwd(const float* out, const float* y, const float* black, const float* sums, float upstream, int N,
+int mgw_img_loss_bwd(const float* out, const float* y, const float* black, const float* sums, float upstream,
+                     const float* upstream_dev, int N,
                      int H, int W, int C, float* d_out, void* stream)
 {
     REQUIRE(out && y && black && sums && d_out, "mgw_img_loss_bwd: null pointer");
     REQUIRE(N > 0 && H > 0 && W > 0 && C > 0, "mgw_img_loss_bwd: bad sizes");
-    return launch_img_loss_bwd(out, y, black, sums, upstream, N, H, W, C, d_out, (cudaStream_t)stream);
+    return launch_img_loss_bwd(out, y, black, sums, upstream, upstream_dev, N, H, W, C, d_out, (cudaStream_t)stream);
 }
 
 int mgw_feature_loss_fwd(const float* matches, const float* mask, const float* img, int N, int M, int H, int W,
@@ -444,13 +445,14 @@ int mgw_feature_loss_fwd(const float* matches, const float* mask, const float* i
     return launch_feature_loss_fwd(matches, mask, img, N, M, H, W, warpped, per_sample, (cudaStream_t)stream);
 }
 
-int mgw_feature_loss_bwd(const float* matches, const float* mask, const float* img, float upstream, int N, int M, int H,
+int mgw_feature_loss_bwd(const float* matches, const float* mask, const float* img, float upstream, const float* upstream_dev,
+                         int N, int M, int H,
                          int W, float* d_img, void* stream)
 {
     REQUIRE(matches && mask && img && d_img, "mgw_feature_loss_bwd: null pointer");
     REQUIRE(N > 0 && M > 0 && H > 0 && W > 0, "mgw_feature_loss_bwd: bad sizes");
     REQUIRE(aligned(matches, 16) && aligned(img, 8), "mgw_feature_loss_bwd: alignment");
-    return launch_feature_loss_bwd(matches, mask, img, upstream, N, M, H, W, d_img, (cudaStream_t)stream);
+    return launch_feature_loss_bwd(matches, mask, img, upstream, upstream_dev, N, M, H, W, d_img, (cudaStream_t)stream);
 }
 
 int mgw_temp_loss_fwd(const float* out1, const float* black1, const float* out2, const float* black2, const float* flow,
@@ -463,12 +465,13 @@ int mgw_temp_loss_fwd(const float* out1, const float* black1, const float* out2,
 }
 
 int mgw_temp_loss_bwd(const float* out1, const float* black1, const float* out2, const float* black2, const float* flow,
-                      const float* sums, float upstream, int N, int H, int W, int C, float* d_out1, float* d_out2, void* stream)
+                      const float* sums, float upstream, const float* upstream_dev, int N, int H, int W, int C, float* d_out1,
+                      float* d_out2, void* stream)
 {
     REQUIRE(out1 && black1 && out2 && black2 && flow && sums && d_out1 && d_out2, "mgw_temp_loss_bwd: null pointer");
     REQUIRE(N > 0 && H > 0 && W > 0 && C > 0, "mgw_temp_loss_bwd: bad sizes");
     REQUIRE(aligned(flow, 8), "mgw_temp_loss_bwd: flow must be 8-byte aligned");
-    return launch_temp_loss_bwd(out1, black1, out2, black2, flow, sums, upstream, N, H, W, C, d_out1, d_out2, (cudaStream_t)stream);
+    return launch_temp_loss_bwd(out1, black1, out2, black2, flow, sums, upstream, upstream_dev, N, H, W, C, d_out1, d_out2, (cudaStream_t)stream);
 }
 
 }  // extern "C"

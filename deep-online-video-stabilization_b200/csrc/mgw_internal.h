@@ -46,15 +46,15 @@ int launch_interp_bwd(const float* im, const float* x, const float* y, const flo
 // mgw_loss.cu
 int launch_img_loss_fwd(const float* out, const float* y, const float* black, int N, int H, int W, int C, float* sums, cudaStream_t st);
 int launch_img_loss_bwd(const float* out, const float* y, const float* black, const float* sums, float upstream,
-                        int N, int H, int W, int C, float* d_out, cudaStream_t st);
+                        const float* up_dev, int N, int H, int W, int C, float* d_out, cudaStream_t st);
 int launch_feature_loss_fwd(const float* matches, const float* mask, const float* img, int N, int M, int H, int W,
                             float* warpped, float* per_sample, cudaStream_t st);
-int launch_feature_loss_bwd(const float* matches, const float* mask, const float* img, float upstream, int N, int M,
+int launch_feature_loss_bwd(const float* matches, const float* mask, const float* img, float upstream, const float* up_dev, int N, int M,
                             int H, int W, float* d_img, cudaStream_t st);
 int launch_temp_loss_fwd(const float* out1, const float* black1, const float* out2, const float* black2,
                          const float* flow, int N, int H, int W, int C, float* sums, cudaStream_t st);
 int launch_temp_loss_bwd(const float* out1, const float* black1, const float* out2, const float* black2,
-                         const float* flow, const float* sums, float upstream, int N, int H, int W, int C,
+                         const float* flow, const float* sums, float upstream, const float* up_dev, int N, int H, int W, int C,
                          float* d_out1, float* d_out2, cudaStream_t st);
 
 // mgw_warp_tma.cu : TMA-staged tiles (fast path)
@@ -64,6 +64,7 @@ struct FusedImgLoss {            // img_loss fused onto the warp (s_net_bundle_n
     const float* black;          // backward: the forward's black_pix
     const float* sums;           // backward: [N,2] per-sample (sum e^2, sum (1-black)) from the fused forward
     float kscale;                // backward: upstream * 2 / batch
+    const float* kscale_dev;     // backward, nullable: device scalar multiplied onto kscale (the autograd upstream, no host sync)
 };
 bool tma_fwd_supported(const WarpShape& s);
 // y_tgt / sums nullable: when given, the img_loss partial sums are accumulated into sums[N,2] (must be zeroed)

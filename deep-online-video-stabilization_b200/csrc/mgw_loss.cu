@@ -44,11 +44,13 @@ img_loss_fwd_kernel(const float* __restrict__ out, const float* __restrict__ y, 
 
 __global__ void __launch_bounds__(256)
 img_loss_bwd_kernel(const float* __restrict__ out, const float* __restrict__ y, const float* __restrict__ black,
-                    const float* __restrict__ sums, float upstream, int N, int HW, int C, float* __restrict__ d_out)
+                    const float* __restrict__ sums, float upstream, const float* __restrict__ up_dev, int N, int HW, int C,
+                    float* __restrict__ d_out)
 {
     const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= (long long)N * HW) return;
     const int n = (int)(p / HW);
+    if (up_dev) upstream *= __ldg(up_dev);
     const float k = upstream * 2.0f / ((__ldg(sums + 2 * n + 1) + 1e-8f) * (float)N);
     const float nb = 1.0f - __ldg(black + p);
     for (int ch = 0; ch < C; ++ch)
@@ -87,7 +89,7 @@ feature_loss_fwd_kernel(const float* __restrict__ matches, const float* __restri
 
 __global__ void __launch_bounds__(256)
 feature_loss_bwd_kernel(const float* __restrict__ matches, const float* __restrict__ mask, const float* __restrict__ img,
-                        float upstream, int N, int M, int H, int W, float* __restrict__ d_img)
+                        float upstream, const float* __restrict__ up_dev, int N, int M, int H, int W, float* __restrict__ d_img)
 {
     __shared__ float sh[8];
     __shared__ float s_cnt;
@@ -97,6 +99,7 @@ feature_loss_bwd_kernel(const float* __restrict__ matches, const float* __restri
     cnt = block_sum(cnt, sh);
     if (threadIdx.x == 0) s_cnt = fmaxf(cnt, 1.0f);
     __syncthreads();
+    if (up_dev) upstream *= __ldg(up_dev);
     const float k = upstream / (s_cnt * (float)N);
     for (int m = threadIdx.x; m < M; m += blockDim.x) {
         const float mk = __ldg(mask + (size_t)n * M + m);
@@ -118,13 +121,15 @@ template <bool BWD>
 __global__ void __launch_bounds__(256)
 temp_loss_kernel(const float* __restrict__ out1, const float* __restrict__ black1, const float* __restrict__ out2,
                  const float* __restrict__ black2, const float* __restrict__ flow, const float* __restrict__ sums_in,
-                 float upstream, int N, int H, int W, int C, float* __restrict__ sums, float* __restrict__ d_out1,
+                 float upstream, const float* __restrict__ up_dev, int N, int H, int W, int C, float* __restrict__ sums,
+                 float* __restrict__ d_out1,
                  float* __restrict__ d_out2)
 {
     __shared__ float sh[8];
     const int n = blockIdx.y, HW = H * W;
     float se = 0.0f, sm = 0.0f;
     float k = 0.0f;
+    if (BWD && up_dev) upstream *= __ldg(up_dev);
     if (BWD) k = upstream * 2.0f / ((__ldg(sums_in + 2 * n + 1) + 1e-8f) * (float)N);
     for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < HW; q += gridDim.x * blockDim.x) {
         const size_t p = (size_t)n * HW + q;
@@ -182,10 +187,10 @@ int launch_img_loss_fwd(const float* out, const float* y, const float* black, in
 }
 
 int launch_img_loss_bwd(const float* out, const float* y, const float* black, const float* sums, float upstream,
-                        int N, int H, int W, int C, float* d_out, cudaStream_t st)
+                        const float* up_dev, int N, int H, int W, int C, float* d_out, cudaStream_t st)
 {
     const unsigned grid = (unsigned)(((long long)N * H * W + 255) / 256);
-    img_loss_bwd_kernel<<<grid, 256, 0, st>>>(out, y, black, sums, upstream, N, H * W, C, d_out);
+    img_loss_bwd_kernel<<<grid, 256, 0, st>>>(out, y, black, sums, upstream, up_dev, N, H * W, C, d_out);
     return check_launch("img_loss_bwd");
 }
 
@@ -196,10 +201,10 @@ int launch_feature_loss_fwd(const float* matches, const float* mask, const float
     return check_launch("feature_loss_fwd");
 }
 
-int launch_feature_loss_bwd(const float* matches, const float* mask, const float* img, float upstream, int N, int M,
+int launch_feature_loss_bwd(const float* matches, const float* mask, const float* img, float upstream, const float* up_dev, int N, int M,
                             int H, int W, float* d_img, cudaStream_t st)
 {
-    feature_loss_bwd_kernel<<<N, 256, 0, st>>>(matches, mask, img, upstream, N, M, H, W, d_img);
+    feature_loss_bwd_kernel<<<N, 256, 0, st>>>(matches, mask, img, upstream, up_dev, N, M, H, W, d_img);
     return check_launch("feature_loss_bwd");
 }
 
@@ -207,17 +212,17 @@ int launch_temp_loss_fwd(const float* out1, const float* black1, const float* ou
                          const float* flow, int N, int H, int W, int C, float* sums, cudaStream_t st)
 {
     cudaMemsetAsync(sums, 0, sizeof(float) * 2 * N, st);
-    temp_loss_kernel<false><<<dim3(blocks_for(H * W, N), N), 256, 0, st>>>(out1, black1, out2, black2, flow, nullptr, 0.0f,
+    temp_loss_kernel<false><<<dim3(blocks_for(H * W, N), N), 256, 0, st>>>(out1, black1, out2, black2, flow, nullptr, 0.0f, nullptr,
                                                                         N, H, W, C, sums, nullptr, nullptr);
     return check_launch("temp_loss_fwd");
 }
 
 int launch_temp_loss_bwd(const float* out1, const float* black1, const float* out2, const float* black2,
-                         const float* flow, const float* sums, float upstream, int N, int H, int W, int C,
+                         const float* flow, const float* sums, float upstream, const float* up_dev, int N, int H, int W, int C,
                          float* d_out1, float* d_out2, cudaStream_t st)
 {
     cudaMemsetAsync(d_out2, 0, sizeof(float) * (size_t)N * H * W * C, st);
-    temp_loss_kernel<true><<<dim3(blocks_for(H * W, N), N), 256, 0, st>>>(out1, black1, out2, black2, flow, sums, upstream,
+    temp_loss_kernel<true><<<dim3(blocks_for(H * W, N), N), 256, 0, st>>>(out1, black1, out2, black2, flow, sums, upstream, up_dev,
                                                                        N, H, W, C, nullptr, d_out1, d_out2);
     return check_launch("temp_loss_bwd");
 }

@@ -311,6 +311,7 @@ struct LossBwd {
     const float* black;     // forward black_pix
     const float* sums;      // [N,2] from the fused forward
     float kscale;           // upstream * 2 / batch
+    const float* kscale_dev;    // nullable device factor on kscale
 };
 
 #ifndef MGW_BWD_MINB
@@ -353,7 +354,7 @@ warp_bwd_tma_kernel(const __grid_constant__ CUtensorMap mapU, const __grid_const
     float gout[K][C], gimg[K][2];
     {
         size_t p = ((size_t)tl.n * cfg.H + tl.r0 + g * K) * cfg.W + col;
-        const float kn = LOSS ? loss.kscale / (__ldg(loss.sums + 2 * tl.n + 1) + 1e-8f) : 0.0f;
+        const float kn = LOSS ? (loss.kscale_dev ? loss.kscale * __ldg(loss.kscale_dev) : loss.kscale) / (__ldg(loss.sums + 2 * tl.n + 1) + 1e-8f) : 0.0f;
 #pragma unroll
         for (int k = 0; k < K; ++k, p += cfg.W) {
             if (LOSS) {
@@ -724,7 +725,7 @@ int launch_warp_bwd_tma(const float* U, const float* Hs, const float* d_out, con
 {
     LossBwd lb{};
     const LossBwd* loss = nullptr;
-    if (fl) { lb.out = fl->out; lb.y = fl->y; lb.black = fl->black; lb.sums = fl->sums; lb.kscale = fl->kscale; loss = &lb; }
+    if (fl) { lb.out = fl->out; lb.y = fl->y; lb.black = fl->black; lb.sums = fl->sums; lb.kscale = fl->kscale; lb.kscale_dev = fl->kscale_dev; loss = &lb; }
     Plan p;
     if (!plan(s, &p)) return set_error(MGW_ERR_UNSUPPORTED, "warp_bwd_tma: unsupported shape");
     *nparts = p.cfg.parts_y * p.cfg.parts_x;

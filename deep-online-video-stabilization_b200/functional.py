@@ -42,7 +42,7 @@ class MeshWarpImgLoss(torch.autograd.Function):
     def backward(ctx, g_loss, g_out, _g_black, g_img):
         U, theta, Hs, out, y, black, sums = ctx.saved_tensors
         g_img = None if g_img is None else g_img.contiguous()
-        up = 0.0 if g_loss is None else float(g_loss)
+        up = 0.0 if g_loss is None else g_loss                   # device scalar: read by the kernel, no host sync
         if g_out is None:
             dU, dtheta = ops.mesh_warp_img_loss_bwd(U, theta, Hs, out, y, black, sums, up, ctx.batch, g_img,
                                                     want_dU=ctx.needs_input_grad[0])
@@ -120,7 +120,7 @@ class ImgLoss(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g):
         out, y, black, sums = ctx.saved_tensors
-        d_out = ops.img_loss_bwd(out, y, black, sums, float(g) * out.shape[0] / ctx.batch)
+        d_out = ops.img_loss_bwd(out, y, black, sums, g * (out.shape[0] / ctx.batch))
         return d_out, (-d_out if ctx.needs_input_grad[1] else None), None, None
 
 
@@ -138,7 +138,7 @@ class FeatureLoss(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g, _gw):
         matches, mask, flow = ctx.saved_tensors
-        d_flow = ops.feature_loss_bwd(matches, mask, flow, float(g) * flow.shape[0] / ctx.batch)
+        d_flow = ops.feature_loss_bwd(matches, mask, flow, g * (flow.shape[0] / ctx.batch))
         return None, None, d_flow, None
 
 
@@ -156,7 +156,7 @@ class TempLoss(torch.autograd.Function):
     def backward(ctx, g):
         out1, black1, out2, black2, flow, sums = ctx.saved_tensors
         batch, use = ctx.cfg
-        d1, d2 = ops.temp_loss_bwd(out1, black1, out2, black2, flow, sums, float(g) * use * out1.shape[0] / batch)
+        d1, d2 = ops.temp_loss_bwd(out1, black1, out2, black2, flow, sums, g * (use * out1.shape[0] / batch))
         return d1, None, d2, None, None, None, None
 
 

@@ -22,6 +22,14 @@ def _p(t):
     return None if t is None else t.data_ptr()
 
 
+def _up(upstream):
+    """upstream gradient as (host factor, device pointer): a CUDA tensor is read by the kernel itself (no host sync)"""
+    if isinstance(upstream, torch.Tensor) and upstream.is_cuda:
+        t = upstream.detach().reshape(-1)[:1].to(torch.float32).contiguous()
+        return 1.0, t
+    return float(upstream), None
+
+
 def _st():
     return torch.cuda.current_stream().cuda_stream
 
@@ -179,13 +187,14 @@ def mesh_warp_img_loss_bwd(U, theta, Hs, out, y, black, sums, upstream, batch, d
     U, theta, Hs, out, y, black, sums = (_chk(t, nm) for t, nm in ((U, 'U'), (theta, 'theta'), (Hs, 'Hs'), (out, 'out'), (y, 'y'),
                                                                    (black, 'black'), (sums, 'sums')))
     d_img = None if d_img is None else _chk(d_img, 'd_img')
+    up = _up(upstream)
     n, h, w, c = _mesh_dims(U, theta, 'theta')
     gh, gw = Hs.shape[1:3]
     dU = torch.empty_like(U) if want_dU else None
     dtheta = torch.empty_like(theta)
     ws = _workspace(lib.mgw_mesh_warp_img_loss_bwd_workspace_bytes(n, h, w, c, gh, gw), U.device)
     with torch.cuda.device(U.device):
-        check(lib.mgw_mesh_warp_img_loss_bwd(_p(U), _p(theta), _p(Hs), _p(out), _p(y), _p(black), _p(sums), float(upstream),
+        check(lib.mgw_mesh_warp_img_loss_bwd(_p(U), _p(theta), _p(Hs), _p(out), _p(y), _p(black), _p(sums), up[0], _p(up[1]),
                                              float(batch), _p(d_img), n, h, w, c, gh, gw, _p(dU), _p(dtheta), _p(ws), _st()),
               'mgw_mesh_warp_img_loss_bwd')
     return dU, dtheta
@@ -256,8 +265,9 @@ def img_loss_bwd(out, y, black, sums, upstream):
     out, y, black, sums = _chk(out, 'out'), _chk(y, 'y'), _chk(black, 'black'), _chk(sums, 'sums')
     n, h, w, c = out.shape
     d_out = torch.empty_like(out)
+    up = _up(upstream)
     with torch.cuda.device(out.device):
-        check(lib.mgw_img_loss_bwd(_p(out), _p(y), _p(black), _p(sums), float(upstream), n, h, w, c, _p(d_out), _st()),
+        check(lib.mgw_img_loss_bwd(_p(out), _p(y), _p(black), _p(sums), up[0], _p(up[1]), n, h, w, c, _p(d_out), _st()),
               'mgw_img_loss_bwd')
     return d_out
 
@@ -280,8 +290,9 @@ def feature_loss_bwd(matches, mask, img, upstream, d_img=None):
     _, h, w, _ = img.shape
     if d_img is None:
         d_img = torch.zeros_like(img)
+    up = _up(upstream)
     with torch.cuda.device(img.device):
-        check(lib.mgw_feature_loss_bwd(_p(matches), _p(mask), _p(img), float(upstream), n, m, h, w, _p(d_img), _st()),
+        check(lib.mgw_feature_loss_bwd(_p(matches), _p(mask), _p(img), up[0], _p(up[1]), n, m, h, w, _p(d_img), _st()),
               'mgw_feature_loss_bwd')
     return d_img
 
@@ -302,8 +313,9 @@ def temp_loss_bwd(out1, black1, out2, black2, flow, sums, upstream):
                                                                            (black2, 'black2'), (flow, 'flow'), (sums, 'sums')))
     n, h, w, c = out1.shape
     d1, d2 = torch.empty_like(out1), torch.empty_like(out2)
+    up = _up(upstream)
     with torch.cuda.device(out1.device):
-        check(lib.mgw_temp_loss_bwd(_p(out1), _p(black1), _p(out2), _p(black2), _p(flow), _p(sums), float(upstream), n, h, w, c,
+        check(lib.mgw_temp_loss_bwd(_p(out1), _p(black1), _p(out2), _p(black2), _p(flow), _p(sums), up[0], _p(up[1]), n, h, w, c,
                                     _p(d1), _p(d2), _st()), 'mgw_temp_loss_bwd')
     return d1, d2
 

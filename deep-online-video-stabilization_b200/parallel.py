@@ -94,3 +94,30 @@ class MeshHeadGradReducer:
             self.work.wait()
             self.work = None
         return self.bufs[self.last]
+
+
+def allreduce_grads(params, bucket_bytes=32 << 20):
+    """Data-parallel training of the whole network (the carrier of SURVEY.md 8(f) rank 3): sums every parameter gradient over
+    the ranks in flat fp32 buckets (losses are already divided by the GLOBAL batch, so SUM is the reduction).  No-op for one rank."""
+    if not (dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1):
+        return
+    grads = [p.grad for p in params if p.grad is not None]
+    bucket, size = [], 0
+
+    def flush():
+        if not bucket:
+            return
+        flat = torch.cat([g.reshape(-1) for g in bucket])
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM)
+        off = 0
+        for g in bucket:
+            g.copy_(flat[off:off + g.numel()].view_as(g))
+            off += g.numel()
+
+    for g in grads:
+        bucket.append(g)
+        size += g.numel() * 4
+        if size >= bucket_bytes:
+            flush()
+            bucket, size = [], 0
+    flush()

@@ -101,6 +101,8 @@ MGW_API int mgw_mesh_warp_bwd_acc(const float* U, const float* theta, const floa
 /* ---- fused a1-a5 + a8: transformer(U, theta) with the img_loss epilogue (s_net_bundle_nobm.py:332,347-352) ----------
  * Forward: as mgw_mesh_warp_fwd (out, black required) plus sums [N,2] = per-sample (sum ((out-y)(1-black))^2,
  * sum (1-black)) accumulated inside the warp kernel -- no second pass over out / y / black.
+ * upstream_dev (here and in the other loss backwards): nullable DEVICE scalar multiplied onto `upstream` inside the kernel --
+ * the autograd upstream gradient without a host read, so that a whole training step can be enqueued / graph-captured.
  * Backward: the upstream gradient of out is the loss's, d_out = upstream*2/batch * (out-y)(1-black)^2/(sums[n][1]+1e-8),
  * formed in registers inside the backward kernel (no d_out tensor is written or read); d_img nullable as before.
  * loss = sum_n sums[n][0]/(sums[n][1]+1e-8)/batch is N scalars of arithmetic left to the caller. */
@@ -108,9 +110,9 @@ MGW_API int mgw_mesh_warp_img_loss_fwd(const float* U, const float* theta, const
                                int gw, float* Hs, float* out, float* black, float* img, float* sums, void* stream);
 MGW_API size_t mgw_mesh_warp_img_loss_bwd_workspace_bytes(int N, int H, int W, int C, int gh, int gw);
 MGW_API int mgw_mesh_warp_img_loss_bwd(const float* U, const float* theta, const float* Hs, const float* out, const float* y,
-                               const float* black, const float* sums, float upstream, float batch, const float* d_img,
-                               int N, int H, int W, int C, int gh, int gw, float* dU, float* dtheta, void* workspace,
-                               void* stream);
+                               const float* black, const float* sums, float upstream, const float* upstream_dev, float batch,
+                               const float* d_img, int N, int H, int W, int C, int gh, int gw, float* dU, float* dtheta,
+                               void* workspace, void* stream);
 
 /* ---- f1 (deploy side): warpRevBundle2(img, x_map, y_map), deploy_bundle.py:136-146 ---------------------------------
  * img [N,H,W,C] uint8 (the unstable frame at network size), xy [N,H,W,2] = the operator's x_map,y_map (the `img` output of
@@ -182,7 +184,7 @@ MGW_API int mgw_homography_warp_bwd(const float* U, const float* theta, const fl
 MGW_API int mgw_img_loss_fwd(const float* out, const float* y, const float* black, int N, int H, int W, int C,
                      float* sums, void* stream);
 MGW_API int mgw_img_loss_bwd(const float* out, const float* y, const float* black, const float* sums, float upstream,
-                     int N, int H, int W, int C, float* d_out, void* stream);
+                     const float* upstream_dev, int N, int H, int W, int C, float* d_out, void* stream);
 
 /* ---- a9: feature_loss / warp_pts, s_net_bundle_nobm.py:215-230,335-343 ---------------------------------
  * matches [N,M,4] (sx,sy,ux,uy), mask [N,M], img [N,H,W,2] -> warpped [N,M,2] nullable, per_sample [N]
@@ -190,8 +192,8 @@ MGW_API int mgw_img_loss_bwd(const float* out, const float* y, const float* blac
  * bwd: d_img [N,H,W,2] must be zeroed by the caller or carry a gradient to accumulate into (sparse +=). */
 MGW_API int mgw_feature_loss_fwd(const float* matches, const float* mask, const float* img, int N, int M, int H, int W,
                          float* warpped, float* per_sample, void* stream);
-MGW_API int mgw_feature_loss_bwd(const float* matches, const float* mask, const float* img, float upstream, int N, int M,
-                         int H, int W, float* d_img, void* stream);
+MGW_API int mgw_feature_loss_bwd(const float* matches, const float* mask, const float* img, float upstream,
+                         const float* upstream_dev, int N, int M, int H, int W, float* d_img, void* stream);
 
 /* ---- a10: temp_loss, train_bundle_nobm.py:115-125 -------------------------------------------------------
  * out1,out2 [N,H,W,C], black1,black2 [N,H,W], flow [N,H,W,2] -> sums [N,2] = (sum e^2, sum m),
@@ -200,8 +202,8 @@ MGW_API int mgw_feature_loss_bwd(const float* matches, const float* mask, const 
 MGW_API int mgw_temp_loss_fwd(const float* out1, const float* black1, const float* out2, const float* black2,
                       const float* flow, int N, int H, int W, int C, float* sums, void* stream);
 MGW_API int mgw_temp_loss_bwd(const float* out1, const float* black1, const float* out2, const float* black2,
-                      const float* flow, const float* sums, float upstream, int N, int H, int W, int C,
-                      float* d_out1, float* d_out2, void* stream);
+                      const float* flow, const float* sums, float upstream, const float* upstream_dev, int N, int H, int W,
+                      int C, float* d_out1, float* d_out2, void* stream);
 
 #ifdef __cplusplus
 }

@@ -564,6 +564,85 @@ def test_total_loss_and_schedule(mgw):
     assert abs(float(t1) - idl * m['id_mul'] * (m['theta_mul'] + m['grid_theta_mul'])) <= 1e-6 * float(t1)
 
 
+def test_stabnet_train_objective_flows_end_to_end(mgw):
+    """StabNet carrier + this library's path: two passes + temp loss (train_bundle_nobm.py:107-141); the objective is finite,
+    every parameter receives a gradient, and the image-side parts equal the standalone entry points."""
+    import synth
+    torch.manual_seed(1)
+    n, h, w = 2, 64, 96
+    net = mgw.StabNet(in_ch=13, grid=(4, 4)).cuda()
+
+    def batch(seed):
+        return dict(x=dev(synth.smooth_image(n, h, w, 13, seed)), y=dev(synth.smooth_image(n, h, w, 1, seed + 1)),
+                    matches=dev(synth.uniform((n, 30, 4), -1, 1, seed + 2)), mask=dev((synth.uniform((n, 30), 0, 1, seed + 3) < 0.5).astype(np.float32)))
+
+    b1, b2 = batch(10), batch(20)
+    flow = dev(synth.uniform((n, h, w, 2), -1, 1, 30))
+    total, ret1, ret2, t_loss = mgw.train_losses(net, b1, b2, flow, mgw.loss_gates(6000))
+    assert torch.isfinite(total) and ret1['output'].shape == (n, h, w, 1) and ret1['black_pix'].shape == (n, h, w, 1)
+    total.backward()
+    missing = [k for k, p in net.named_parameters() if p.grad is None or not torch.isfinite(p.grad).all()]
+    assert not missing, missing
+    assert float(net.backbone.conv1.weight.grad.abs().max()) > 0
+    # parts: the fused img_loss inside equals the standalone op on the same warped output
+    x = b1['x'][..., 12:13].contiguous()
+    out, black, _ = mgw.transformer(x, ret1['pts2'].detach())
+    il = mgw.img_loss(out, b1['y'], black)
+    assert abs(float(il) * mgw.losses.V2_93_MULS['img_mul'] - float(ret1['img_loss'])) <= 1e-5 * abs(float(ret1['img_loss']))
+    # theta_only (iterations <= 100): only the id terms reach the objective
+    t0, r1, _, _ = mgw.train_losses(net, b1, b2, flow, mgw.loss_gates(50))
+    want = float(r1['theta_loss'] + r1['grid_theta_loss']) * 1.0
+    assert torch.isfinite(t0) and float(t0) < float(total) and want > 0
+
+
+def test_loss_backwards_take_the_upstream_from_the_device(mgw):
+    """upstream_dev of the loss backwards: the same gradients as the by-value upstream, and a whole objective
+    (warp + img/feature/temp/vertex losses, forward and backward) enqueues without a single host synchronisation."""
+    import synth
+    n, h, w = 3, 48, 64
+    U, y = dev(synth.smooth_image(n, h, w, 1, 1)), dev(synth.smooth_image(n, h, w, 1, 2))
+    th = dev(synth.random_mesh(n, 4, 4, 0.05, 3))
+    out, black, img, Hs, sums = mgw.ops.mesh_warp_img_loss_fwd(U, th, y)
+    up = torch.tensor([0.37], device='cuda')
+    a = mgw.ops.img_loss_bwd(out, y, black, sums, 0.37)
+    b = mgw.ops.img_loss_bwd(out, y, black, sums, up)
+    assert torch.allclose(a, b, rtol=1e-6, atol=0)
+    a = mgw.ops.mesh_warp_img_loss_bwd(U, th, Hs, out, y, black, sums, 0.37, float(n))
+    b = mgw.ops.mesh_warp_img_loss_bwd(U, th, Hs, out, y, black, sums, up, float(n))
+    assert torch.allclose(a[1], b[1], rtol=1e-5, atol=1e-7) and torch.allclose(a[0], b[0], rtol=1e-5, atol=1e-7)
+    matches = dev(synth.uniform((n, 20, 4), -1, 1, 4)); mask = dev((synth.uniform((n, 20), 0, 1, 5) < 0.6).astype(np.float32))
+    assert torch.allclose(mgw.ops.feature_loss_bwd(matches, mask, img, 0.37), mgw.ops.feature_loss_bwd(matches, mask, img, up), rtol=1e-6, atol=0)
+    ts = mgw.ops.temp_loss_fwd(out, black, out, black, img)
+    a, b = mgw.ops.temp_loss_bwd(out, black, out, black, img, ts, 0.37), mgw.ops.temp_loss_bwd(out, black, out, black, img, ts, up)
+    assert torch.allclose(a[0], b[0], rtol=1e-6, atol=0) and torch.allclose(a[1], b[1], rtol=1e-5, atol=1e-9)
+
+    head = dev(synth.randn((n, 50), 6, 0.05)).requires_grad_(True)
+    flow = dev(synth.uniform((n, h, w, 2), -1, 1, 7))
+
+    def objective():
+        tot, rets = 0, []
+        for _ in range(2):
+            p1, p2 = mgw.get_4_pts(head, grid=(4, 4))
+            il, o, bl, fl = mgw.transformer_img_loss(U, p2, y)
+            ftl, _ = mgw.feature_loss(matches, mask, fl)
+            t, _ = mgw.total_loss(head, p1, p2, il, ftl)
+            tot = tot + t
+            rets.append((o, bl))
+        tot = tot + 500.0 * mgw.temp_loss(rets[0][0], rets[0][1], rets[1][0], rets[1][1], flow)
+        tot.backward()
+        return tot
+
+    objective()                                   # warm-up (allocations, lazy initialisation)
+    head.grad = None
+    torch.cuda.synchronize()
+    torch.cuda.set_sync_debug_mode('error')
+    try:
+        tot = objective()
+    finally:
+        torch.cuda.set_sync_debug_mode('default')
+    assert torch.isfinite(tot) and torch.isfinite(head.grad).all() and float(head.grad.abs().max()) > 0
+
+
 def test_deploy_crop_exact(mgw):
     """CropState (mgw_black_accumulate / mgw_crop_rect) == the reference's loops (fixture) and the restatement (larger sizes)."""
     import deploy_ref

@@ -83,3 +83,53 @@ def test_shard_bounds_cover_everything():
             b = [parallel.shard_bounds(n, r, world) for r in range(world)]
             assert b[0][0] == 0 and b[-1][1] == n and all(b[i][1] == b[i + 1][0] for i in range(world - 1))
             assert max(hi - lo for lo, hi in b) - min(hi - lo for lo, hi in b) <= 1
+
+
+def _grad_worker(rank, world, port, out_q):
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    parallel.init_from_env(backend='gloo')
+    torch.manual_seed(0)
+    lin = torch.nn.Sequential(torch.nn.Linear(5, 7), torch.nn.ReLU(), torch.nn.Linear(7, 3))
+    x = torch.arange(6 * 5, dtype=torch.float32).reshape(6, 5) / 10
+    xl = parallel.shard(x, rank, world)
+    (lin(xl).square().sum() / x.shape[0]).backward()                 # divided by the GLOBAL batch
+    parallel.allreduce_grads(lin.parameters(), bucket_bytes=64)      # several buckets
+    out_q.put((rank, [p.grad.numpy().copy() for p in lin.parameters()]))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def test_allreduce_grads_two_ranks_equal_one_rank():
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_grad_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=180) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    q1 = ctx.Queue()
+    p1 = ctx.Process(target=_grad_worker, args=(0, 1, _free_port(), q1))
+    p1.start()
+    single = q1.get(timeout=180)
+    p1.join(timeout=60)
+    for a, b, c in zip(res[0][1], res[1][1], single[1]):
+        assert np.array_equal(a, b) and np.allclose(a, c, rtol=1e-5, atol=1e-6)
+
+
+def test_stabnet_carrier_shapes_and_head_init():
+    """the backbone + head carrier (s_net_bundle_nobm.py:250-264) on CPU: theta shape, output_layer initialiser (resnet.py:50-53)"""
+    torch.manual_seed(0)
+    net = dovs_b200.StabNet(in_ch=13, grid=(4, 4)).eval()
+    with torch.no_grad():
+        f = net.backbone(torch.zeros(1, 13, 64, 96))
+        theta = net(torch.zeros(2, 64, 96, 13))
+    assert f.shape == (1, 2048, 2, 3)                                # output_stride 32
+    assert theta.shape == (2, 50)
+    assert float(net.head.weight.abs().max()) <= (3.0 / 512) ** 0.5 and float(net.head.bias.abs().max()) == 0.0
+    n_units = sum(1 for m in net.backbone.units)
+    assert n_units == 16
+    assert dovs_b200.StabNet(in_ch=13, grid=(2, 3)).head.out_features == 24

@@ -157,51 +157,17 @@ res['deploy_frame_288x512'] = {
     'note': '1x288x512: H2D gray fp32 + colour u8, K1 + K2 (C=1) + maps/4 + remap, D2H colour u8; CPU = the same three cv2 calls'}
 
 
-# ---- config #3: StabNet-shaped forward, batch 16, 13-channel 288x512 input (configs/v2_93.py:19-22,40)
-def bottleneck(cin, mid, stride):
-    return nn.ModuleDict(dict(
-        pre=nn.Sequential(nn.BatchNorm2d(cin), nn.ReLU(inplace=True)),
-        short=nn.Conv2d(cin, mid * 4, 1, stride) if (stride != 1 or cin != mid * 4) else nn.Identity(),
-        body=nn.Sequential(nn.Conv2d(cin, mid, 1), nn.BatchNorm2d(mid), nn.ReLU(inplace=True),
-                           nn.Conv2d(mid, mid, 3, stride, 1), nn.BatchNorm2d(mid), nn.ReLU(inplace=True),
-                           nn.Conv2d(mid, mid * 4, 1))))
-
-
-class ResNet50v2Head(nn.Module):
-    """resnet_v2_50(global_pool=False, output_stride=32) -> mean pool -> fc 2048/1024/512/50 (s_net_bundle_nobm.py:250-264)."""
-
-    def __init__(self, cin=13, nout=50):
-        super().__init__()
-        self.stem = nn.Sequential(nn.Conv2d(cin, 64, 7, 2, 3), nn.MaxPool2d(3, 2, 1))
-        blocks, c = [], 64
-        for mid, n, stride in ((64, 3, 2), (128, 4, 2), (256, 6, 2), (512, 3, 1)):
-            for i in range(n):
-                blocks.append(bottleneck(c, mid, stride if i == n - 1 else 1))
-                c = mid * 4
-        self.blocks = nn.ModuleList(blocks)
-        self.post = nn.Sequential(nn.BatchNorm2d(c), nn.ReLU(inplace=True))
-        self.fc = nn.Sequential(nn.Linear(2048, 2048), nn.ReLU(), nn.Linear(2048, 1024), nn.ReLU(), nn.Linear(1024, 512), nn.ReLU(),
-                                nn.Linear(512, nout))
-        nn.init.zeros_(self.fc[-1].weight); nn.init.zeros_(self.fc[-1].bias)
-
-    def forward(self, x):
-        x = self.stem(x)
-        for b in self.blocks:
-            y = b['pre'](x)
-            x = b['short'](y if not isinstance(b['short'], nn.Identity) else x) + b['body'](y)
-        return self.fc(self.post(x).mean((2, 3)))
-
-
+# ---- config #3: StabNet forward, batch 16, 13-channel 288x512 input (configs/v2_93.py:19-22,40): the package's carrier
 torch.backends.cudnn.benchmark = True
-net = ResNet50v2Head().to(dev).eval().to(memory_format=torch.channels_last)
+torch.manual_seed(0)
+net = mgw.StabNet(in_ch=13, grid=(4, 4)).to(dev).eval().to(memory_format=torch.channels_last)
 n = 16
 x_nhwc = torch.tensor(synth.noise_image(n, 288, 512, 13, 5), device=dev)
 with torch.no_grad():
     def backbone():
-        return net(x_nhwc.permute(0, 3, 1, 2))          # NHWC storage viewed as channels_last NCHW: no copy
+        return net(x_nhwc)
 
     def warp_stage(head):
-        head = head + 0.01 * torch.randn_like(head)       # random-init head outputs zeros: jitter so the mesh is not the identity
         _, pts2 = mgw.get_4_pts(head, n, (4, 4))
         cur = x_nhwc[..., 12:13].contiguous()             # the current frame, channel 12 (s_net_bundle_nobm.py:281)
         return mgw.transformer(cur, pts2)
@@ -212,6 +178,78 @@ with torch.no_grad():
     t_total = dev_time(lambda: warp_stage(backbone()), 20)
 res['config3_stabnet_fwd_b16'] = {'us_backbone_torch_fp32': t_backbone, 'us_warp_stage_C1': t_warp, 'us_total': t_total,
                                   'warp_share_pct': 100 * t_warp / t_total,
-                                  'note': 'backbone = torch/cuDNN ResNet-50-v2-shaped carrier at random init (not a kernel-writing target); '
-                                          'warp stage = get_4_pts + slice + K1 + K2 on the 1-channel current frame'}
+                                  'note': 'backbone = dovs_b200.StabNet (torch/cuDNN ResNet-50-v2 carrier, random init; not a kernel-writing '
+                                          'target); warp stage = get_4_pts + slice + K1 + K2 on the 1-channel current frame'}
+
+# ---- config #5, one rank's share: the training objective of train_bundle_nobm.py:107-141 at 32 clips per GPU (256 over 8)
+net.train()
+nb = 32
+
+
+def clip_batch(seed):
+    return dict(x=torch.tensor(synth.noise_image(nb, 288, 512, 13, seed), device=dev),
+                y=torch.tensor(synth.noise_image(nb, 288, 512, 1, seed + 1), device=dev),
+                matches=torch.tensor(synth.uniform((nb, 3000, 4), -1, 1, seed + 2), device=dev),
+                mask=(torch.rand(nb, 3000, device=dev) < 0.3).float())
+
+
+b1, b2 = clip_batch(40), clip_batch(50)
+flow = torch.tensor(synth.uniform((nb, 288, 512, 2), -1, 1, 60), device=dev)
+gates = mgw.loss_gates(6000)
+opt = torch.optim.Adam(net.parameters(), lr=2e-5)
+
+
+def train_step():
+    opt.zero_grad(set_to_none=True)
+    total, _, _, _ = mgw.train_losses(net, b1, b2, flow, gates, batch_size=256)
+    total.backward()
+    opt.step()
+    return total
+
+
+l0 = mgw.launch_count()
+train_step()
+ours = mgw.launch_count() - l0
+t_step = dev_time(train_step, 10, flush_l2=False)
+
+
+def path_only():
+    # the same step with the backbone cut out: theta is a leaf
+    th = theta_leaf.detach().requires_grad_(True)
+    tot = 0
+    rets = []
+    for b in (b1, b2):
+        p1, p2 = mgw.get_4_pts(th, grid=(4, 4))
+        il, out, black, fl = mgw.transformer_img_loss(b['x'][..., 12:13].contiguous(), p2, b['y'], batch_size=256)
+        ftl, _ = mgw.feature_loss(b['matches'], b['mask'], fl, batch_size=256)
+        t, _ = mgw.total_loss(th, p1, p2, il, ftl, batch_size=256)
+        tot = tot + t
+        rets.append((out, black))
+    tot = tot + 500.0 * mgw.temp_loss(rets[0][0], rets[0][1], rets[1][0], rets[1][1], flow, batch_size=256)
+    tot.backward()
+    return tot
+
+
+with torch.no_grad():
+    theta_leaf = net(b1['x'])
+t_path = dev_time(path_only, 10, flush_l2=False)
+# the same objective captured once in a CUDA graph (no host synchronisation anywhere in it: the loss backwards read their
+# upstream gradient on the device), replayed
+side = torch.cuda.Stream()
+side.wait_stream(torch.cuda.current_stream())
+with torch.cuda.stream(side):
+    for _ in range(3):
+        path_only()
+torch.cuda.current_stream().wait_stream(side)
+torch.cuda.synchronize()
+graph = torch.cuda.CUDAGraph()
+with torch.cuda.graph(graph):
+    path_only()
+t_path_graph = dev_time(graph.replay, 20, flush_l2=False)
+res['config5_train_step_32_clips_per_gpu'] = {
+    'us_step_backbone_plus_path_plus_adam': t_step, 'us_path_only_fwd_bwd_all_losses_eager': t_path, 'us_path_only_graph_replay': t_path_graph,
+    'path_share_pct_eager': 100 * t_path / t_step,
+    'launches_of_this_library_per_step': ours,
+    'note': 'two passes (shared weights) + temp_loss, every loss term of the reference objective, Adam; backbone = torch fp32 carrier; '
+            'the path = get_4_pts + fused warp/img_loss fwd+bwd + feature/temp/vertex losses on the 1-channel current frame'}
 print(json.dumps(res, indent=1))
