@@ -643,6 +643,50 @@ def test_loss_backwards_take_the_upstream_from_the_device(mgw):
     assert torch.isfinite(tot) and torch.isfinite(head.grad).all() and float(head.grad.abs().max()) > 0
 
 
+@pytest.mark.parametrize('impl', ['auto', 'generic'])
+def test_no_kernel_writes_outside_its_buffers(mgw, impl):
+    """Every output and the workspace of the warp calls sit between guard bands filled with a NaN pattern inside one big
+    allocation; after forward + backward (TMA stores, TMA reduce-adds, red.v4 drains, fixed-point scatter) the guards are
+    intact and nothing inside the buffers was left unwritten.  (compute-sanitizer is not available on this pool.)"""
+    import synth
+    from dovs_b200._lib import lib, check
+    mgw.set_impl(impl)
+    try:
+        for (n, h, w, c, gh, gw) in [(2, 48, 64, 3, 4, 4), (1, 288, 512, 3, 4, 4), (3, 50, 70, 1, 2, 3), (2, 96, 128, 4, 4, 4),
+                                     (2, 72, 96, 1, 4, 4), (1, 40, 36, 2, 1, 1)]:
+            G = 8192                                            # guard floats (32 KB) around every buffer
+            sizes = dict(Hs=n * gh * gw * 9, out=n * h * w * c, black=n * h * w, img=n * h * w * 2, dU=n * h * w * c,
+                         dtheta=n * (gh + 1) * (gw + 1) * 2,
+                         ws=(lib.mgw_mesh_warp_bwd_workspace_bytes(n, h, w, c, gh, gw) + 3) // 4 + 64)
+            offs, total = {}, G
+            for k, v in sizes.items():
+                offs[k] = total
+                total += (v + 63) // 64 * 64 + G                 # 256-byte aligned starts
+            pool = torch.full((total,), float('nan'), device='cuda')
+            pool.view(torch.int32).fill_(0x7fc0dead)            # a recognisable quiet NaN
+            view = {k: pool[offs[k]:offs[k] + sizes[k]] for k in sizes}
+            U = dev(synth.noise_image(n, h, w, c, 1)); th = dev(synth.random_mesh(n, gh, gw, 0.06, 2))
+            d_out = dev(synth.randn((n, h, w, c), 3)); d_img = dev(synth.randn((n, h, w, 2), 4))
+            st = torch.cuda.current_stream().cuda_stream
+            P = lambda t: t.data_ptr()
+            check(lib.mgw_mesh_warp_fwd(P(U), P(th), n, h, w, c, gh, gw, P(view['Hs']), P(view['out']), P(view['black']), P(view['img']), st), 'fwd')
+            check(lib.mgw_mesh_warp_bwd(P(U), P(th), P(view['Hs']), P(d_out), P(d_img), n, h, w, c, gh, gw, P(view['dU']), P(view['dtheta']),
+                                        P(view['ws']), st), 'bwd')
+            torch.cuda.synchronize()
+            raw = pool.view(torch.int32)
+            mask = torch.ones(total, dtype=torch.bool, device='cuda')
+            for k in sizes:
+                mask[offs[k]:offs[k] + sizes[k]] = False
+            assert bool((raw[mask] == 0x7fc0dead).all()), ('guard band overwritten', impl, (n, h, w, c, gh, gw))
+            for k in ('Hs', 'out', 'black', 'img', 'dU', 'dtheta'):
+                assert not bool((view[k].view(torch.int32) == 0x7fc0dead).any()), ('unwritten output', k, impl, (n, h, w, c))
+            # and the guarded results are the ordinary ones
+            o, b, i, Hs = mgw.ops.mesh_warp_fwd(U, th)
+            assert torch.equal(o.reshape(-1), view['out']) and torch.equal(b.reshape(-1), view['black']) and torch.equal(i.reshape(-1), view['img'])
+    finally:
+        mgw.set_impl('auto')
+
+
 def test_deploy_crop_exact(mgw):
     """CropState (mgw_black_accumulate / mgw_crop_rect) == the reference's loops (fixture) and the restatement (larger sizes)."""
     import deploy_ref
