@@ -171,10 +171,13 @@ def main():
         side.wait_stream(cur)
         with torch.cuda.stream(side):
             dU_buf.zero_()
-        if world > 1:
-            # head gradient (features^T . dtheta) and all-reduce of the PREVIOUS step, on a side stream under this step's kernels
-            reducer.launch(slot=(i - 1) % R, features=feats, dtheta=dth_slots[(i - 1) % R])
         out, black, img, Hs = ops.mesh_warp_fwd(s['U'], s['theta'])
+        if world > 1:
+            # head gradient (features^T . dtheta) and all-reduce of the PREVIOUS step on a high-priority side stream, forked
+            # AFTER the forward: the persistent forward kernel owns every SM with a static tile schedule (a CTA displaced by
+            # the NCCL kernel would finish late), the backward's 3072 one-tile CTAs are placed by the hardware scheduler and
+            # absorb it
+            reducer.launch(slot=(i - 1) % R, features=feats, dtheta=dth_slots[(i - 1) % R])
         cur.wait_stream(side)
         dU, dtheta = ops.mesh_warp_bwd(s['U'], s['theta'], Hs, s['d_out'], s['d_img'], accumulate_into=dU_buf,
                                        dtheta_out=dth_slots[i % R])

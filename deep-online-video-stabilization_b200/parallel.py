@@ -52,7 +52,8 @@ class MeshHeadGradReducer:
     def __init__(self, n_features, n_out, device, nbuf=1):
         self.bufs = [torch.zeros(n_features * n_out + n_out, device=device, dtype=torch.float32) for _ in range(nbuf)]
         self.nf, self.no = n_features, n_out
-        self.side = torch.cuda.Stream(device=device) if torch.device(device).type == 'cuda' else None
+        # high priority: the few CTAs of the reduction are placed ahead of the queued CTAs of the warp kernels it overlaps
+        self.side = torch.cuda.Stream(device=device, priority=-1) if torch.device(device).type == 'cuda' else None
         self.work = None
         self.last = 0
 
