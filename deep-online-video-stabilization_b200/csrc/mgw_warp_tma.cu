@@ -374,13 +374,8 @@ warp_bwd_tma_kernel(const __grid_constant__ CUtensorMap mapU, const __grid_const
             }
         }
     }
-    if (DU) {
-        int4* a4 = reinterpret_cast<int4*>(s_acc);
-#pragma unroll
-        for (int i = 0; i < (G::kBoxF / 4 + NT - 1) / NT; ++i)
-            if (i * NT + tid < G::kBoxF / 4) a4[i * NT + tid] = make_int4(0, 0, 0, 0);
-    }
-    __syncthreads();                                  // barrier initialised
+    // warp 0 issues the TMA load of the source box first (thread 0 initialised the barrier itself; everybody else meets it
+    // after the __syncthreads below), then everyone zeroes the accumulator under the load's latency
     if (tid < 32) {
         int bx0, by0, interior, area_ok;
         source_box<C, TW, K, NT>(cfg, tl, Hc, stepx, stepy, bx0, by0, interior, area_ok);
@@ -389,6 +384,12 @@ warp_bwd_tma_kernel(const __grid_constant__ CUtensorMap mapU, const __grid_const
             tma::mbar_expect_tx(bar, (uint32_t)(G::kBoxF * sizeof(float)));
             tma::load_3d(s_src, &mapU, bar, bx0 * C, by0, tl.n);
         }
+    }
+    if (DU) {
+        int4* a4 = reinterpret_cast<int4*>(s_acc);
+#pragma unroll
+        for (int i = 0; i < (G::kBoxF / 4 + NT - 1) / NT; ++i)
+            if (i * NT + tid < G::kBoxF / 4) a4[i * NT + tid] = make_int4(0, 0, 0, 0);
     }
     // ---- per-tile fixed-point scale from max|d_out| (Inf/NaN anywhere in the tile disables the fixed-point path)
     if (DU) {
