@@ -74,7 +74,7 @@ __device__ __forceinline__ Tile this_tile(const TileCfg& cfg)
 // to global memory for the ones outside the box.
 template <int C, int TW, int K, int NT>
 __device__ __forceinline__ void source_box(const TileCfg& cfg, const Tile& tl, const float (&Hc)[9], float stepx, float stepy,
-                                           int& bx0, int& by0, int& interior, int& area_ok)
+                                           int& bx0, int& by0, int& interior, int& area_ok, int* complete = nullptr)
 {
     using G = Geo<C, TW, K, NT>;
     const int k4 = threadIdx.x & 3;
@@ -95,6 +95,7 @@ __device__ __forceinline__ void source_box(const TileCfg& cfg, const Tile& tl, c
     }
     ok = ok && (sgn == 4 || sgn == -4);
     bx0 = 0; by0 = 0; interior = 0; area_ok = 0;
+    if (complete) *complete = 0;
     if (ok) {
         const int ux0 = (int)floorf(xmin) - 1, ux1 = (int)floorf(xmax) + 2;      // unclipped tap range, 1 px of slack
         const int uy0 = (int)floorf(ymin) - 1, uy1 = (int)floorf(ymax) + 2;
@@ -108,6 +109,8 @@ __device__ __forceinline__ void source_box(const TileCfg& cfg, const Tile& tl, c
         bx0 -= bx0 % G::kXalign;
         interior = (ux0 >= 0 && ux1 <= cfg.W - 1 && uy0 >= 0 && uy1 <= cfg.H - 1 &&
                     ux1 - bx0 < G::SBW && uy1 - by0 < G::SBH) ? 1 : 0;
+        // every tap that survives clipping lies inside the box (the backward skips pixels with a clipped tap, see below)
+        if (complete) *complete = (ix0 >= bx0 && ix1 - bx0 < G::SBW && iy0 >= by0 && iy1 - by0 < G::SBH) ? 1 : 0;
         // magnification guard for the fixed-point accumulator: bbox area >= 1/16 of the tile area
         area_ok = ((xmax - xmin + 1.0f) * (ymax - ymin + 1.0f) * 16.0f >= (float)(G::TH * TW)) ? 1 : 0;
     }
@@ -377,10 +380,10 @@ warp_bwd_tma_kernel(const __grid_constant__ CUtensorMap mapU, const __grid_const
     // warp 0 issues the TMA load of the source box first (thread 0 initialised the barrier itself; everybody else meets it
     // after the __syncthreads below), then everyone zeroes the accumulator under the load's latency
     if (tid < 32) {
-        int bx0, by0, interior, area_ok;
-        source_box<C, TW, K, NT>(cfg, tl, Hc, stepx, stepy, bx0, by0, interior, area_ok);
+        int bx0, by0, interior, area_ok, complete;
+        source_box<C, TW, K, NT>(cfg, tl, Hc, stepx, stepy, bx0, by0, interior, area_ok, &complete);
         if (tid == 0) {
-            ti->bx0 = bx0; ti->by0 = by0; ti->interior = interior; ti->area_ok = area_ok;
+            ti->bx0 = bx0; ti->by0 = by0; ti->interior = complete; ti->area_ok = area_ok;      // backward: "interior" = complete
             tma::mbar_expect_tx(bar, (uint32_t)(G::kBoxF * sizeof(float)));
             tma::load_3d(s_src, &mapU, bar, bx0 * C, by0, tl.n);
         }
@@ -429,7 +432,12 @@ warp_bwd_tma_kernel(const __grid_constant__ CUtensorMap mapU, const __grid_const
 
     tma::mbar_wait(bar, 0);
     if (ti->interior && (fixed || !DU)) {
-        // ---- fast path: every tap unclipped and inside the box; shared-memory offsets are compile-time constants
+        // ---- fast path: every UNCLIPPED tap lies inside the box; shared-memory offsets are compile-time constants.
+        // A pixel with a clipped tap (its sample point is outside the image) contributes nothing but its d_img term: clipping
+        // collapses a tap pair onto one pixel with weights that are exact negatives (mgw_device.cuh, taps_scatter), so its
+        // dU terms cancel and gx = sum_c g_c (Ic-Ia)(ay+by) = 0, gy likewise -- the reference keeps only the rounding residue
+        // of those cancellations (~1e-8 relative), far below the gradient tolerance.  Border tiles therefore run this loop
+        // too, with the gather / scatter of such pixels predicated off, instead of the general per-tap loop below.
 #pragma unroll
         for (int k = 0; k < K; ++k) {
             const int row = tl.r0 + g * K + k;
@@ -442,27 +450,30 @@ warp_bwd_tma_kernel(const __grid_constant__ CUtensorMap mapU, const __grid_const
                 float xn, yn;
                 const float rz = div2_rn(xs, ys, zs, xn, yn);
                 const FastTaps t = make_taps_interior(xn, yn, cfg.H, cfg.W);
-                const int ia = ((t.y0 - by0) * G::kRowF + (t.x0 - bx0) * C);
-                const float* pa = s_src + ia;
-                int* qa = s_acc + ia;
-                const float wa = t.ax * t.ay, wb = t.ax * t.by, wc = t.bx * t.ay, wd = t.bx * t.by;
-                // gx = sum_c g_c [(Ic-Ia) ay + (Id-Ib) by], gy = sum_c g_c [(Ib-Ia) ax + (Id-Ic) bx], with the channel sums taken
-                // per tap first (4 FMAs per channel instead of 10 operations)
-                float sa = 0.0f, sb = 0.0f, sc = 0.0f, sd = 0.0f;
+                float gx = 0.0f, gy = 0.0f;
+                if ((unsigned)t.x0 < (unsigned)(cfg.W - 1) && (unsigned)t.y0 < (unsigned)(cfg.H - 1)) {      // no tap clipped
+                    const int ia = ((t.y0 - by0) * G::kRowF + (t.x0 - bx0) * C);
+                    const float* pa = s_src + ia;
+                    int* qa = s_acc + ia;
+                    const float wa = t.ax * t.ay, wb = t.ax * t.by, wc = t.bx * t.ay, wd = t.bx * t.by;
+                    // gx = sum_c g_c [(Ic-Ia) ay + (Id-Ib) by], gy = sum_c g_c [(Ib-Ia) ax + (Id-Ic) bx], with the channel sums
+                    // taken per tap first (4 FMAs per channel instead of 10 operations)
+                    float sa = 0.0f, sb = 0.0f, sc = 0.0f, sd = 0.0f;
 #pragma unroll
-                for (int ch = 0; ch < C; ++ch) {
-                    const float gch = gout[k][ch];
-                    sa = fmaf(gch, pa[ch], sa); sb = fmaf(gch, pa[G::kRowF + ch], sb);
-                    sc = fmaf(gch, pa[C + ch], sc); sd = fmaf(gch, pa[G::kRowF + C + ch], sd);
-                    if (DU) {
-                        const float gs = gch * scale;
-                        atomicAdd(qa + ch, fixed_of(wa, gs));
-                        atomicAdd(qa + G::kRowF + ch, fixed_of(wb, gs));
-                        atomicAdd(qa + C + ch, fixed_of(wc, gs));
-                        atomicAdd(qa + G::kRowF + C + ch, fixed_of(wd, gs));
+                    for (int ch = 0; ch < C; ++ch) {
+                        const float gch = gout[k][ch];
+                        sa = fmaf(gch, pa[ch], sa); sb = fmaf(gch, pa[G::kRowF + ch], sb);
+                        sc = fmaf(gch, pa[C + ch], sc); sd = fmaf(gch, pa[G::kRowF + C + ch], sd);
+                        if (DU) {
+                            const float gs = gch * scale;
+                            atomicAdd(qa + ch, fixed_of(wa, gs));
+                            atomicAdd(qa + G::kRowF + ch, fixed_of(wb, gs));
+                            atomicAdd(qa + C + ch, fixed_of(wc, gs));
+                            atomicAdd(qa + G::kRowF + C + ch, fixed_of(wd, gs));
+                        }
                     }
+                    gx = fmaf(sc - sa, t.ay, (sd - sb) * t.by); gy = fmaf(sb - sa, t.ax, (sd - sc) * t.bx);
                 }
-                const float gx = fmaf(sc - sa, t.ay, (sd - sb) * t.by), gy = fmaf(sb - sa, t.ax, (sd - sc) * t.bx);
                 accumulate_dh_r(dh, fmaf(gx, halfW, gimg[k][0]), fmaf(gy, halfH, gimg[k][1]), xn, yn, rz, xt, yt);
             }
         }
