@@ -52,3 +52,24 @@ def test_fails_loudly_without_a_gpu():
     # and the raw ABI reports a CUDA error instead of computing anything
     rc = dovs_b200._lib.lib.mgw_solve_h_fwd(1, 1, 4, 4, 1, None)
     assert rc < 0 and dovs_b200._lib.lib.mgw_last_error()
+
+
+def test_reference_import_lines_work_unchanged():
+    """s_net_bundle_nobm.py:16 and train_bundle_nobm.py:16 import the operator by these exact statements; with the dropin/
+    directory first on sys.path they resolve to this library ("a module pair importable under those names")."""
+    import subprocess
+    import sys
+    code = (
+        "import sys; sys.path.insert(0, %r)\n"
+        "from spatial_transformer3 import transformer\n"
+        "t3 = transformer\n"
+        "from spatial_transformer import *\n"
+        "import dovs_b200, inspect\n"
+        "assert t3 is dovs_b200.spatial_transformer3.transformer\n"
+        "assert transformer is dovs_b200.spatial_transformer.transformer and interpolate is dovs_b200.spatial_transformer.interpolate\n"
+        "assert list(inspect.signature(t3).parameters)[:2] == ['U', 'theta']\n"
+        "assert list(inspect.signature(transformer).parameters)[:3] == ['U', 'theta', 'out_size']\n"
+        "assert list(inspect.signature(interpolate).parameters)[:4] == ['im', 'x', 'y', 'out_size']\n"
+        "print('ok')\n") % os.path.join(ROOT, 'deep-online-video-stabilization_b200', 'dropin')
+    r = subprocess.run([sys.executable, '-c', code], capture_output=True, text=True, cwd='/tmp', timeout=300)
+    assert r.returncode == 0 and r.stdout.strip().endswith('ok'), r.stderr[-2000:]
