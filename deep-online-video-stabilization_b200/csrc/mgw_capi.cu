@@ -382,6 +382,15 @@ int mgw_stream_push(float* frames, float* masks, int depth, int slot, const floa
     return launch_stream_push(frames, masks, depth, slot, img, black, H, W, frame_out, out_stride, (cudaStream_t)stream);
 }
 
+int mgw_warp_rev_bundle_u8(const uint8_t* img, const double* Hs_cvt, int N, int H, int W, int C, int gh, int gw, uint8_t* dst,
+                           void* stream)
+{
+    REQUIRE(img && Hs_cvt && dst, "mgw_warp_rev_bundle_u8: null pointer");
+    REQUIRE(N > 0 && H > 0 && W > 0 && gh > 0 && gw > 0 && gh <= H && gw <= W && (long long)N * H * W < (1LL << 31),
+            "mgw_warp_rev_bundle_u8: bad sizes");
+    return launch_warp_rev_bundle_u8(img, Hs_cvt, N, H, W, C, gh, gw, dst, (cudaStream_t)stream);
+}
+
 int mgw_vertex_losses_fwd(const float* theta, const float* pts1, const float* pts2, int N, int gh, int gw, float do_crop_rate,
                           float* sums, float* black_err, void* stream)
 {

@@ -73,28 +73,17 @@ __device__ __forceinline__ int cv_round(float v)
     return (fabsf(v) < 2147483648.0f) ? __float2int_rn(v) : (int)0x80000000;
 }
 
+// remapBilinear on 1/32-pixel fixed-point source coordinates: taps clamped to int16, 15-bit integer weights summing to 2^15,
+// constant border 0 (imgwarp.cpp); shared by cv2.remap (float maps) and cv2.warpPerspective (its own fixed-point maps)
 template <int C>
-__global__ void __launch_bounds__(256)
-remap_up_kernel(const uint8_t* __restrict__ img, const float2* __restrict__ small, int N, int H, int W, int h4, int w4,
-                uint8_t* __restrict__ dst)
+__device__ __forceinline__ void bilinear_fixed_u8(const uint8_t* __restrict__ base, int H, int W, int sx, int sy, uint8_t* __restrict__ o)
 {
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= N * H * W) return;
-    const int c = t % W, r = (t / W) % H, n = t / (W * H);
-    const Lin h = hcoef(c, W, w4), v = vcoef(r, H, h4);
-    const float2 m = resize_sample(small + (size_t)n * h4 * w4, w4, h, v);
-    // (map + 1) / 2 * size in fp32 (deploy_bundle.py:142-143)
-    const float xp = __fmul_rn(__fmul_rn(__fadd_rn(m.x, 1.0f), 0.5f), (float)W);
-    const float yp = __fmul_rn(__fmul_rn(__fadd_rn(m.y, 1.0f), 0.5f), (float)H);
-    // remapBilinear: 1/32-pixel fixed point, taps clamped to int16, 15-bit weights, constant border 0
-    const int sx = cv_round(__fmul_rn(xp, 32.0f)), sy = cv_round(__fmul_rn(yp, 32.0f));
     const int ix = min(max(sx >> 5, -32768), 32767), iy = min(max(sy >> 5, -32768), 32767);
     const int fx = sx & 31, fy = sy & 31;
     const int w00 = (32 - fx) * (32 - fy) * 32, w01 = fx * (32 - fy) * 32, w10 = (32 - fx) * fy * 32, w11 = fx * fy * 32;
     const bool x0 = (unsigned)ix < (unsigned)W, x1 = (unsigned)(ix + 1) < (unsigned)W;
     const bool y0 = (unsigned)iy < (unsigned)H, y1 = (unsigned)(iy + 1) < (unsigned)H;
-    const uint8_t* base = img + (size_t)n * H * W * C;
-    const uint8_t* p00 = base + ((size_t)iy * W + ix) * C;
+    const uint8_t* p00 = base + ((long long)iy * W + ix) * C;
     int acc[C];
 #pragma unroll
     for (int ch = 0; ch < C; ++ch) acc[ch] = 1 << 14;
@@ -108,15 +97,64 @@ remap_up_kernel(const uint8_t* __restrict__ img, const float2* __restrict__ smal
     }
     if (y1 && x0) {
 #pragma unroll
-        for (int ch = 0; ch < C; ++ch) acc[ch] += w10 * (int)__ldg(p00 + (size_t)W * C + ch);
+        for (int ch = 0; ch < C; ++ch) acc[ch] += w10 * (int)__ldg(p00 + (long long)W * C + ch);
     }
     if (y1 && x1) {
 #pragma unroll
-        for (int ch = 0; ch < C; ++ch) acc[ch] += w11 * (int)__ldg(p00 + (size_t)W * C + C + ch);
+        for (int ch = 0; ch < C; ++ch) acc[ch] += w11 * (int)__ldg(p00 + (long long)W * C + C + ch);
     }
-    uint8_t* o = dst + (size_t)t * C;
 #pragma unroll
     for (int ch = 0; ch < C; ++ch) o[ch] = (uint8_t)min(max(acc[ch] >> 15, 0), 255);
+}
+
+// warpRevBundle (deploy_bundle.py:148-173): output cell (i, j) = that region of cv2.warpPerspective(img, Hs_cvt[i][j],
+// WARP_INVERSE_MAP | INTER_LINEAR).  OpenCV walks the destination in blocks of bw columns and evaluates, in double,
+//   X0 = M0*bx + M1*y + M2 (left to right), W = W0 + M6*x1, W = W ? 32/W : 0, fX = clamp((X0 + M0*x1)*W), X = cvRound(fX)
+// with bx the block's first column and x1 = x - bx; restated operation by operation (no contraction: __dmul_rn / __dadd_rn).
+__device__ __forceinline__ int persp_fixed(double a, double b, double c, double bx, double y, double x1, double Wq)
+{
+    const double X0 = __dadd_rn(__dadd_rn(__dmul_rn(a, bx), __dmul_rn(b, y)), c);
+    double f = __dmul_rn(__dadd_rn(X0, __dmul_rn(a, x1)), Wq);
+    f = (f < 2147483647.0) ? f : 2147483647.0;                    // std::min((double)INT_MAX, f)
+    f = (-2147483648.0 < f) ? f : -2147483648.0;                  // std::max((double)INT_MIN, f)
+    return __double2int_rn(f);                                    // cvRound: round half to even
+}
+
+template <int C>
+__global__ void __launch_bounds__(256)
+warp_rev_bundle_kernel(const uint8_t* __restrict__ img, const double* __restrict__ Hc, int N, int H, int W, int gh, int gw, int bw,
+                       uint8_t* __restrict__ dst)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= N * H * W) return;
+    const int x = t % W, y = (t / W) % H, n = t / (W * H);
+    const int ci = min(y / (H / gh), gh - 1), cj = min(x / (W / gw), gw - 1);       // the last cell takes the remainder (:162-165)
+    const double* M = Hc + ((size_t)(n * gh + ci) * gw + cj) * 9;
+    const int bxi = (x / bw) * bw;
+    const double bx = (double)bxi, x1 = (double)(x - bxi), yd = (double)y;
+    const double W0 = __dadd_rn(__dadd_rn(__dmul_rn(__ldg(M + 6), bx), __dmul_rn(__ldg(M + 7), yd)), __ldg(M + 8));
+    double Wq = __dadd_rn(W0, __dmul_rn(__ldg(M + 6), x1));
+    Wq = (Wq != 0.0) ? __ddiv_rn(32.0, Wq) : 0.0;
+    const int sx = persp_fixed(__ldg(M + 0), __ldg(M + 1), __ldg(M + 2), bx, yd, x1, Wq);
+    const int sy = persp_fixed(__ldg(M + 3), __ldg(M + 4), __ldg(M + 5), bx, yd, x1, Wq);
+    bilinear_fixed_u8<C>(img + (size_t)n * H * W * C, H, W, sx, sy, dst + (size_t)t * C);
+}
+
+template <int C>
+__global__ void __launch_bounds__(256)
+remap_up_kernel(const uint8_t* __restrict__ img, const float2* __restrict__ small, int N, int H, int W, int h4, int w4,
+                uint8_t* __restrict__ dst)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= N * H * W) return;
+    const int c = t % W, r = (t / W) % H, n = t / (W * H);
+    const Lin h = hcoef(c, W, w4), v = vcoef(r, H, h4);
+    const float2 m = resize_sample(small + (size_t)n * h4 * w4, w4, h, v);
+    // (map + 1) / 2 * size in fp32 (deploy_bundle.py:142-143)
+    const float xp = __fmul_rn(__fmul_rn(__fadd_rn(m.x, 1.0f), 0.5f), (float)W);
+    const float yp = __fmul_rn(__fmul_rn(__fadd_rn(m.y, 1.0f), 0.5f), (float)H);
+    const int sx = cv_round(__fmul_rn(xp, 32.0f)), sy = cv_round(__fmul_rn(yp, 32.0f));
+    bilinear_fixed_u8<C>(img + (size_t)n * H * W * C, H, W, sx, sy, dst + (size_t)t * C);
 }
 
 }  // namespace
@@ -140,6 +178,22 @@ int launch_remap_bundle_u8(const uint8_t* img, const float* xy, int N, int H, in
     default: return set_error(MGW_ERR_UNSUPPORTED, "remap_bundle_u8: C must be 1, 3 or 4 (got %d)", C);
     }
     return check_launch("remap_up");
+}
+
+int launch_warp_rev_bundle_u8(const uint8_t* img, const double* Hs_cvt, int N, int H, int W, int C, int gh, int gw, uint8_t* dst,
+                              cudaStream_t st)
+{
+    // WarpPerspectiveInvoker's block width: bh0 = min(16, H); bw0 = min(1024 / bh0, W)
+    const int bh0 = H < 16 ? H : 16;
+    const int bw = (1024 / bh0) < W ? (1024 / bh0) : W;
+    const int t = N * H * W, grid = (t + 255) / 256;
+    switch (C) {
+    case 1: warp_rev_bundle_kernel<1><<<grid, 256, 0, st>>>(img, Hs_cvt, N, H, W, gh, gw, bw, dst); break;
+    case 3: warp_rev_bundle_kernel<3><<<grid, 256, 0, st>>>(img, Hs_cvt, N, H, W, gh, gw, bw, dst); break;
+    case 4: warp_rev_bundle_kernel<4><<<grid, 256, 0, st>>>(img, Hs_cvt, N, H, W, gh, gw, bw, dst); break;
+    default: return set_error(MGW_ERR_UNSUPPORTED, "warp_rev_bundle_u8: C must be 1, 3 or 4 (got %d)", C);
+    }
+    return check_launch("warp_rev_bundle");
 }
 
 }  // namespace mgw

@@ -86,6 +86,9 @@ size_t remap_bundle_workspace_bytes(int N, int H, int W);
 int launch_remap_bundle_u8(const uint8_t* img, const float* xy, int N, int H, int W, int C, uint8_t* dst, void* workspace,
                            cudaStream_t st);
 
+int launch_warp_rev_bundle_u8(const uint8_t* img, const double* Hs_cvt, int N, int H, int W, int C, int gh, int gw, uint8_t* dst,
+                              cudaStream_t st);
+
 // mgw_vertex_loss.cu : vertex regularisers (s_net_bundle_nobm.py:139-210,246-247)
 int launch_vertex_losses_fwd(const float* theta, const float* pts1, const float* pts2, int N, int gh, int gw, float do_crop_rate,
                              float* sums, float* black_err, cudaStream_t st);

@@ -11,7 +11,7 @@ import torch
 
 from . import ops
 
-__all__ = ['warpRevBundle2', 'StreamState', 'CropState']
+__all__ = ['warpRevBundle2', 'warpRevBundle', 'cvt_theta_mat_bundle', 'StreamState', 'CropState']
 
 
 def warpRevBundle2(img, x_map, y_map, device=None):
@@ -31,6 +31,34 @@ def warpRevBundle2(img, x_map, y_map, device=None):
     dst = ops.remap_bundle_u8(im, xy)
     if single:
         dst = dst[0]
+    return dst.cpu().numpy() if as_numpy else dst
+
+
+def cvt_theta_mat_bundle(Hs, height, width, grid_h, grid_w):
+    """reference deploy_bundle.py:121-134 with its own numpy expressions (float64 on the host: 16 3x3 products), so that the
+    pixel-space homographies the kernel receives are the reference's bit for bit; height / width / grid are its config globals."""
+    from numpy.linalg import inv
+    scale_mat = np.eye(3)
+    scale_mat[0, 0] = width / 2.
+    scale_mat[0, 2] = width / 2.
+    scale_mat[1, 1] = height / 2.
+    scale_mat[1, 2] = height / 2.
+    Hs = np.asarray(Hs).reshape((grid_h, grid_w, 3, 3))
+    return np.matmul(np.matmul(scale_mat, Hs), inv(scale_mat))
+
+
+def warpRevBundle(img, Hs, grid=(4, 4), device=None):
+    """reference deploy_bundle.py:148-173: one uint8 frame [H,W,3] and the operator's Hs ([gh,gw,9] or anything that reshapes to
+    it, as `Hs[0]` of the reference's fetch) -> the frame with every mesh cell warped by its own homography
+    (cv2.warpPerspective, WARP_INVERSE_MAP | INTER_LINEAR, byte-exact).  numpy in -> numpy out; a CUDA frame stays on the device."""
+    as_numpy = isinstance(img, np.ndarray)
+    dev = torch.device(device) if device is not None else (torch.device('cuda') if as_numpy else img.device)
+    im = (torch.as_tensor(np.ascontiguousarray(img)) if as_numpy else img).to(device=dev, dtype=torch.uint8)
+    h, w = im.shape[-3], im.shape[-2]
+    gh, gw = int(grid[0]), int(grid[1])
+    Hs_np = Hs.detach().cpu().numpy() if isinstance(Hs, torch.Tensor) else np.asarray(Hs)
+    Hc = torch.as_tensor(np.ascontiguousarray(cvt_theta_mat_bundle(Hs_np, h, w, gh, gw), dtype=np.float64)).to(dev)
+    dst = ops.warp_rev_bundle_u8(im.reshape(1, h, w, -1).contiguous(), Hc.reshape(1, gh, gw, 9), gh, gw)[0]
     return dst.cpu().numpy() if as_numpy else dst
 
 

@@ -414,3 +414,16 @@ def vertex_losses_bwd(theta, pts1, pts2, gh, gw, f, do_crop_rate=0.8, need=(True
         check(lib.mgw_vertex_losses_bwd(_p(theta), _p(pts1), _p(pts2), ref.shape[0], gh, gw, do_crop_rate, _p(f),
                                         _p(outs[0]), _p(outs[1]), _p(outs[2]), _st()), 'mgw_vertex_losses_bwd')
     return tuple(outs)
+
+
+def warp_rev_bundle_u8(img, Hs_cvt, gh, gw):
+    """deploy_bundle.py:148-173 on the device: img [N,H,W,C] uint8, Hs_cvt [N,gh,gw,9] float64 (pixel-space homographies of
+    cvt_theta_mat_bundle) -> [N,H,W,C] uint8, every cell cut from the frame warped by its own homography."""
+    img, Hs_cvt = _chk(img, 'img', torch.uint8), _chk(Hs_cvt, 'Hs_cvt', torch.float64)
+    n, h, w, c = img.shape
+    if Hs_cvt.numel() != n * gh * gw * 9:
+        raise ValueError('Hs_cvt has %d elements for batch %d and a %dx%d grid' % (Hs_cvt.numel(), n, gh, gw))
+    dst = torch.empty_like(img)
+    with torch.cuda.device(img.device):
+        check(lib.mgw_warp_rev_bundle_u8(_p(img), _p(Hs_cvt), n, h, w, c, gh, gw, _p(dst), _st()), 'mgw_warp_rev_bundle_u8')
+    return dst

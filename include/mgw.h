@@ -123,6 +123,13 @@ MGW_API size_t mgw_remap_bundle_u8_workspace_bytes(int N, int H, int W);
 MGW_API int mgw_remap_bundle_u8(const uint8_t* img, const float* xy, int N, int H, int W, int C, uint8_t* dst, void* workspace,
                         void* stream);
 
+/* warpRevBundle(img, Hs), deploy_bundle.py:148-173 (the per-cell cv2.warpPerspective variant; its call at :300 is commented
+ * out in the reference): Hs_cvt [N,gh,gw,9] DOUBLE on the device = cvt_theta_mat_bundle(Hs) (:121-134: scale_mat . H .
+ * inv(scale_mat), computed by the host binding with the reference's own numpy expressions); dst cell (i, j) = that region of
+ * cv2.warpPerspective(img, Hs_cvt[i][j], dsize=(W,H), WARP_INVERSE_MAP | INTER_LINEAR), byte-exact with OpenCV 4.x. */
+MGW_API int mgw_warp_rev_bundle_u8(const uint8_t* img, const double* Hs_cvt, int N, int H, int W, int C, int gh, int gw,
+                           uint8_t* dst, void* stream);
+
 /* ---- f2 (deploy side): the streaming state of deploy_bundle.py:204-232,259-295,319-327 -----------------------------
  * frames, masks: device rings [depth][H][W] (the reference's before_frames / before_masks lists, depth = before_ch = 32);
  * `head` = slot of the newest entry, so that list[-i] is slot (head - (i-1)) mod depth.

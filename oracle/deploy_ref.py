@@ -180,3 +180,77 @@ def crop_rect(all_black, step=10):
             if area[k] > max_s:
                 max_s, ans = int(area[k]), [i, j, i + k, j + int(w[k]) - 1]
     return ans
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# warpRevBundle(img, Hs) of deploy_bundle.py:148-173 (the per-cell cv2.warpPerspective variant; its call at :300 is commented
+# out in the reference, warpRevBundle2 is the live one) with cvt_theta_mat_bundle :121-134.
+def _bilinear_fixed_u8(img, sx, sy):
+    """remapBilinear on 1/32-pixel fixed-point coordinates (int64 arrays), constant border 0 -- shared with cv2.remap"""
+    H, W = img.shape[:2]
+    ix = np.clip(sx >> 5, -32768, 32767)
+    iy = np.clip(sy >> 5, -32768, 32767)
+    fx, fy = sx & 31, sy & 31
+    w = [(32 - fx) * (32 - fy) * 32, fx * (32 - fy) * 32, (32 - fx) * fy * 32, fx * fy * 32]
+
+    def tap(yy, xx):
+        ok = (xx >= 0) & (xx < W) & (yy >= 0) & (yy < H)
+        v = img[np.clip(yy, 0, H - 1), np.clip(xx, 0, W - 1)].astype(np.int64)
+        return v * ok[..., None]
+
+    s = (tap(iy, ix) * w[0][..., None] + tap(iy, ix + 1) * w[1][..., None] + tap(iy + 1, ix) * w[2][..., None] +
+         tap(iy + 1, ix + 1) * w[3][..., None])
+    return np.clip((s + (1 << 14)) >> 15, 0, 255).astype(np.uint8)
+
+
+def warp_perspective_fixed_coords(M, out_w, out_h):
+    """cv2.warpPerspective(..., flags=WARP_INVERSE_MAP|INTER_LINEAR), imgwarp.cpp WarpPerspectiveInvoker: the destination is
+    walked in blocks (bh0 = min(16, h), bw0 = min(1024 / bh0, w), bh0 = min(1024 / bw0, h)); in a block starting at column bx,
+        X0 = M0*bx + M1*y + M2, Y0 = M3*bx + M4*y + M5, W0 = M6*bx + M7*y + M8          (double, left to right)
+        W = W0 + M6*x1; W = W ? 32/W : 0; fX = clamp((X0 + M0*x1)*W, INT_MIN, INT_MAX), X = cvRound(fX)   (x1 = x - bx)
+    -> 1/32-pixel fixed-point source coordinates (int64 [out_h,out_w] each)."""
+    M = np.asarray(M, np.float64).reshape(9)
+    bh0 = min(16, out_h)
+    bw0 = min(1024 // bh0, out_w)
+    x = np.arange(out_w)
+    bx = (x // bw0) * bw0
+    x1 = (x - bx).astype(np.float64)
+    bxf = bx.astype(np.float64)
+    y = np.arange(out_h, dtype=np.float64)[:, None]
+    X0 = M[0] * bxf[None, :] + M[1] * y + M[2]
+    Y0 = M[3] * bxf[None, :] + M[4] * y + M[5]
+    W0 = M[6] * bxf[None, :] + M[7] * y + M[8]
+    Wv = W0 + M[6] * x1[None, :]
+    with np.errstate(divide='ignore', invalid='ignore'):
+        Wv = np.where(Wv != 0, 32.0 / Wv, 0.0)
+        fX = np.maximum(-2147483648.0, np.minimum(2147483647.0, (X0 + M[0] * x1[None, :]) * Wv))
+        fY = np.maximum(-2147483648.0, np.minimum(2147483647.0, (Y0 + M[3] * x1[None, :]) * Wv))
+    return np.rint(fX).astype(np.int64), np.rint(fY).astype(np.int64)
+
+
+def cvt_theta_mat_bundle(Hs, height, width, grid_h, grid_w):
+    """deploy_bundle.py:121-134, the same numpy expressions"""
+    from numpy.linalg import inv
+    scale_mat = np.eye(3)
+    scale_mat[0, 0] = width / 2.
+    scale_mat[0, 2] = width / 2.
+    scale_mat[1, 1] = height / 2.
+    scale_mat[1, 2] = height / 2.
+    Hs = np.asarray(Hs).reshape((grid_h, grid_w, 3, 3))
+    return np.matmul(np.matmul(scale_mat, Hs), inv(scale_mat))
+
+
+def warp_rev_bundle(img, Hs, grid_h, grid_w):
+    """deploy_bundle.py:148-173: every cell of the output is cut from the frame warped by that cell's homography"""
+    height, width = img.shape[:2]
+    Hc = cvt_theta_mat_bundle(Hs, height, width, grid_h, grid_w)
+    gh, gw = height // grid_h, width // grid_w
+    out = np.zeros_like(img)
+    for i in range(grid_h):
+        for j in range(grid_w):
+            sx, sy = warp_perspective_fixed_coords(Hc[i, j], width, height)
+            full = _bilinear_fixed_u8(img, sx, sy)
+            r0, r1 = i * gh, (height if i == grid_h - 1 else (i + 1) * gh)
+            c0, c1 = j * gw, (width if j == grid_w - 1 else (j + 1) * gw)
+            out[r0:r1, c0:c1] = full[r0:r1, c0:c1]
+    return out

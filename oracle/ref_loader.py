@@ -179,6 +179,19 @@ def deploy_warp_rev_bundle2(height, width):
     return _exec_nodes(fn, ns, 'deploy_bundle.py')['warpRevBundle2']
 
 
+def deploy_warp_rev_bundle(height, width, grid_h, grid_w):
+    """warpRevBundle and cvt_theta_mat_bundle of deploy_bundle.py:121-134,148-173 as callables (needs cv2)."""
+    import math
+    import cv2
+    import numpy as np
+    tree = _parse('deploy_bundle.py')
+    fns = [n for n in tree.body if isinstance(n, ast.FunctionDef) and n.name in ('warpRevBundle', 'cvt_theta_mat_bundle')]
+    assert len(fns) == 2
+    ns = dict(cv2=cv2, np=np, math=math, width=width, height=height, grid_h=grid_h, grid_w=grid_w)
+    ns = _exec_nodes(fns, ns, 'deploy_bundle.py')
+    return ns['warpRevBundle'], ns['cvt_theta_mat_bundle']
+
+
 def deploy_stream_blocks():
     """The per-frame state handling of deploy_bundle.py as three code objects compiled from the reference's own statements
     (picked out of the `while(True)` loop by line range; the script cannot be imported):

@@ -32,7 +32,7 @@ def test_header_and_library_agree():
 def test_no_torch_types_in_the_abi():
     for name, args in header_functions().items():
         for a in args:
-            assert re.match(r'^(const\s+)?(float|int32_t|uint8_t|void|int|size_t)\s*\*?\s*\w+$', a) or a.startswith('float '), (name, a)
+            assert re.match(r'^(const\s+)?(float|double|int32_t|uint8_t|void|int|size_t)\s*\*?\s*\w+$', a) or a.startswith('float '), (name, a)
 
 
 def test_product_never_imports_the_oracle():

@@ -479,6 +479,31 @@ def test_deploy_remap_byte_exact(mgw, tag):
     assert np.array_equal(g1[0].cpu().numpy(), want)
 
 
+def test_deploy_warp_rev_bundle_byte_exact(mgw):
+    """warpRevBundle (mgw_warp_rev_bundle_u8) == the reference's function on OpenCV (fixture), and C = 1 / 4, batched, against
+    the restatement"""
+    import deploy_ref
+    g = load_golden('deploy_warp_rev_bundle')
+    for n in sorted(k[:-4] for k in g if k.endswith('_dst')):
+        gh, gw = (int(v) for v in g[n + '_grid'])
+        got = mgw.warpRevBundle(g[n + '_img'], g[n + '_Hs'], grid=(gh, gw))
+        assert isinstance(got, np.ndarray) and np.array_equal(got, g[n + '_dst']), n
+    # CUDA tensors in -> CUDA tensor out
+    got = mgw.warpRevBundle(torch.as_tensor(g['ragged_img']).cuda(), torch.as_tensor(g['ragged_Hs']).cuda(), grid=(3, 4))
+    assert got.is_cuda and np.array_equal(got.cpu().numpy(), g['ragged_dst'])
+    # other channel counts and a batch through the op
+    r = np.random.RandomState(9)
+    for c in (1, 4):
+        h, w, gh, gw = 60, 88, 2, 4
+        imgs = r.randint(0, 256, (2, h, w, c)).astype(np.uint8)
+        Hs = [g['strong_Hs'].reshape(2, 2, 9)[[0, 1]][:, [0, 1, 0, 1]], g['ragged_Hs'].reshape(3, 4, 9)[:2]]
+        Hc = np.stack([deploy_ref.cvt_theta_mat_bundle(Hs[k], h, w, gh, gw) for k in range(2)])
+        got = mgw.ops.warp_rev_bundle_u8(torch.as_tensor(imgs).cuda(), torch.as_tensor(Hc).cuda(), gh, gw).cpu().numpy()
+        for k in range(2):
+            want = deploy_ref.warp_rev_bundle(np.repeat(imgs[k], 3, -1)[..., :3] if c == 1 else imgs[k][..., :3], Hs[k], gh, gw)
+            assert np.array_equal(got[k][..., 0], want[..., 0]), (c, k)
+
+
 def test_deploy_stream_state_exact(mgw):
     """StreamState (device rings, mgw_stream_assemble / mgw_stream_push) == the reference's per-frame list handling."""
     import deploy_ref

@@ -276,3 +276,33 @@ def test_vertex_loss_golden_is_reference_output():
     pts1, pts2 = ns['get_4_pts'](torch.as_tensor(g['g1_head']), 3)
     assert np.allclose(ref_loader.quiet(ns['get_distortion_loss'], pts1).numpy(), g['g1_ref_dist'], rtol=1e-6)
     assert np.allclose(ref_loader.quiet(ns['get_consistency_loss'], pts2).numpy(), g['g1_ref_cons'], rtol=1e-6)
+
+
+def test_warp_rev_bundle_oracle_matches_the_reference():
+    """deploy_ref.warp_rev_bundle (cv2.warpPerspective restated: double-precision block walk, 1/32-px fixed point) ==
+    warpRevBundle of deploy_bundle.py:148-173 run from the reference source on OpenCV (fixture), byte for byte"""
+    import deploy_ref
+    g = load_golden('deploy_warp_rev_bundle')
+    names = sorted(k[:-4] for k in g if k.endswith('_dst'))
+    assert len(names) >= 5
+    for n in names:
+        gh, gw = (int(v) for v in g[n + '_grid'])
+        h, w = g[n + '_img'].shape[:2]
+        assert np.array_equal(deploy_ref.cvt_theta_mat_bundle(g[n + '_Hs'], h, w, gh, gw), g[n + '_Hs_cvt']), n
+        assert np.array_equal(deploy_ref.warp_rev_bundle(g[n + '_img'], g[n + '_Hs'], gh, gw), g[n + '_dst']), n
+        assert int(g[n + '_optimized_differs']) == 0          # OpenCV's two code paths agree on this one
+
+
+@pytest.mark.reference
+def test_warp_rev_bundle_golden_is_reference_output():
+    cv2 = pytest.importorskip('cv2')
+    import ref_loader
+    g = load_golden('deploy_warp_rev_bundle')
+    gh, gw = (int(v) for v in g['ragged_grid'])
+    h, w = g['ragged_img'].shape[:2]
+    warp, _ = ref_loader.deploy_warp_rev_bundle(h, w, gh, gw)
+    cv2.setUseOptimized(False)
+    try:
+        assert np.array_equal(warp(g['ragged_img'], g['ragged_Hs']), g['ragged_dst'])
+    finally:
+        cv2.setUseOptimized(True)

@@ -109,6 +109,33 @@ with torch.cuda.stream(s):
         dst_h.copy_(dst_d, non_blocking=True)
         s.synchronize()
         lat3.append((time.perf_counter() - t0) * 1e6)
+# the other deploy warp, warpRevBundle (deploy_bundle.py:148-173): 16 cv2.warpPerspective calls + stitching on the CPU
+dev_wrb = cpu_wrb = None
+try:
+    import cv2
+    Hs_np = Hs1.cpu().numpy()[0]                      # the operator's Hs of the frame above
+    Hc_np = mgw.deploy.cvt_theta_mat_bundle(Hs_np, hn, wn, 4, 4)
+    Hc_d = torch.as_tensor(np.ascontiguousarray(Hc_np)).cuda().reshape(1, 4, 4, 9)
+    with torch.cuda.stream(s):
+        dev_wrb = dev_time(lambda: ops.warp_rev_bundle_u8(col_d, Hc_d, 4, 4), 200, flush_l2=False)
+    col_np = col_h.numpy()[0]
+    def cpu_wrb_fn():
+        parts = []
+        for i in range(4):
+            row = []
+            for j in range(4):
+                tmp = cv2.warpPerspective(col_np, Hc_np[i, j], dsize=(wn, hn), flags=cv2.WARP_INVERSE_MAP | cv2.INTER_LINEAR)
+                row.append(tmp[i * 72:(i + 1) * 72, j * 128:(j + 1) * 128])
+            parts.append(np.concatenate(row, 1))
+        return np.concatenate(parts, 0)
+    want = cpu_wrb_fn()
+    assert np.array_equal(ops.warp_rev_bundle_u8(col_d, Hc_d, 4, 4).cpu().numpy()[0], want)
+    tt = []
+    for _ in range(20):
+        t0 = time.perf_counter(); cpu_wrb_fn(); tt.append((time.perf_counter() - t0) * 1e6)
+    cpu_wrb = float(np.median(tt))
+except Exception as e:      # noqa: BLE001
+    cpu_wrb = str(e)
 # the streaming state around it (deploy_bundle.py:259-274,319-328): input assembly from the history rings + push of the new frame
 state = mgw.StreamState(gray_h[0, ..., 0])
 cur2d = gray_d[0, ..., 0].contiguous()
@@ -153,6 +180,7 @@ res['deploy_frame_288x512'] = {
     'us_device_graph_replay_warp_plus_remap': dev_frame, 'us_device_remap_only': dev_remap,
     'us_p50_host_to_host_u8_frames': float(np.percentile(lat3, 50)), 'us_p99_host_to_host': float(np.percentile(lat3, 99)),
     'us_cpu_opencv_remap_only': cpu_us, 'cpu_threads': os.cpu_count(),
+    'us_device_warp_rev_bundle': dev_wrb, 'us_cpu_opencv_warp_rev_bundle': cpu_wrb,
     'us_device_stream_state_assemble_plus_push': dev_state, 'us_cpu_numpy_stream_state': cpu_state_us,
     'note': '1x288x512: H2D gray fp32 + colour u8, K1 + K2 (C=1) + maps/4 + remap, D2H colour u8; CPU = the same three cv2 calls'}
 
