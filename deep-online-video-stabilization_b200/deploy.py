@@ -11,7 +11,7 @@ import torch
 
 from . import ops
 
-__all__ = ['warpRevBundle2', 'warpRevBundle', 'cvt_theta_mat_bundle', 'StreamState', 'CropState']
+__all__ = ['warpRevBundle2', 'warpRevBundle', 'warpRev', 'cvt_theta_mat_bundle', 'StreamState', 'CropState']
 
 
 def warpRevBundle2(img, x_map, y_map, device=None):
@@ -60,6 +60,13 @@ def warpRevBundle(img, Hs, grid=(4, 4), device=None):
     Hc = torch.as_tensor(np.ascontiguousarray(cvt_theta_mat_bundle(Hs_np, h, w, gh, gw), dtype=np.float64)).to(dev)
     dst = ops.warp_rev_bundle_u8(im.reshape(1, h, w, -1).contiguous(), Hc.reshape(1, gh, gw, 9), gh, gw)[0]
     return dst.cpu().numpy() if as_numpy else dst
+
+
+def warpRev(img, theta, device=None):
+    """reference deploy_bundle.py:100-118: cv2.warpPerspective(img, cvt_theta_mat(theta), WARP_INVERSE_MAP | INTER_LINEAR) for one
+    3x3 homography in normalised coordinates -- the 1x1-grid case of warpRevBundle."""
+    return warpRevBundle(img, np.asarray(theta.detach().cpu() if isinstance(theta, torch.Tensor) else theta).reshape(1, 1, 9),
+                         grid=(1, 1), device=device)
 
 
 class StreamState:

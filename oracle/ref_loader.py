@@ -185,10 +185,11 @@ def deploy_warp_rev_bundle(height, width, grid_h, grid_w):
     import cv2
     import numpy as np
     tree = _parse('deploy_bundle.py')
-    fns = [n for n in tree.body if isinstance(n, ast.FunctionDef) and n.name in ('warpRevBundle', 'cvt_theta_mat_bundle')]
-    assert len(fns) == 2
+    fns = [n for n in tree.body if isinstance(n, ast.FunctionDef) and n.name in ('warpRevBundle', 'cvt_theta_mat_bundle', 'warpRev', 'cvt_theta_mat')]
+    assert len(fns) == 4
     ns = dict(cv2=cv2, np=np, math=math, width=width, height=height, grid_h=grid_h, grid_w=grid_w)
     ns = _exec_nodes(fns, ns, 'deploy_bundle.py')
+    ns['warpRevBundle'].warpRev = ns['warpRev']              # the single-homography variant (:100-118) rides along
     return ns['warpRevBundle'], ns['cvt_theta_mat_bundle']
 
 

@@ -488,6 +488,7 @@ def test_deploy_warp_rev_bundle_byte_exact(mgw):
         gh, gw = (int(v) for v in g[n + '_grid'])
         got = mgw.warpRevBundle(g[n + '_img'], g[n + '_Hs'], grid=(gh, gw))
         assert isinstance(got, np.ndarray) and np.array_equal(got, g[n + '_dst']), n
+    assert np.array_equal(mgw.deploy.warpRev(g['strong_img'], g['warprev_theta']), g['warprev_out'])       # warpRev (:113-117)
     # CUDA tensors in -> CUDA tensor out
     got = mgw.warpRevBundle(torch.as_tensor(g['ragged_img']).cuda(), torch.as_tensor(g['ragged_Hs']).cuda(), grid=(3, 4))
     assert got.is_cuda and np.array_equal(got.cpu().numpy(), g['ragged_dst'])

@@ -291,6 +291,7 @@ def test_warp_rev_bundle_oracle_matches_the_reference():
         assert np.array_equal(deploy_ref.cvt_theta_mat_bundle(g[n + '_Hs'], h, w, gh, gw), g[n + '_Hs_cvt']), n
         assert np.array_equal(deploy_ref.warp_rev_bundle(g[n + '_img'], g[n + '_Hs'], gh, gw), g[n + '_dst']), n
         assert int(g[n + '_optimized_differs']) == 0          # OpenCV's two code paths agree on this one
+    assert np.array_equal(deploy_ref.warp_rev_bundle(g['strong_img'], g['warprev_theta'].reshape(1, 1, 9), 1, 1), g['warprev_out'])
 
 
 @pytest.mark.reference
