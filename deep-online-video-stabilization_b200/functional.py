@@ -4,6 +4,15 @@ import torch
 from . import ops
 
 
+def empty_batch(U, theta, oh, ow):
+    """N = 0 (an empty shard of a ragged batch split): nothing to launch; empty outputs that still hang off U and theta in
+    the autograd graph, as the reference's graph would produce"""
+    if not (U.is_cuda and theta.is_cuda):
+        raise RuntimeError('U and theta must live on a CUDA device: this library has no CPU path')
+    z = (U.sum() + theta.sum()) * 0
+    return U.new_zeros((0, oh, ow, U.shape[3])) + z, U.new_zeros((0, oh, ow)), U.new_zeros((0, oh, ow, 2)) + z
+
+
 class MeshWarp(torch.autograd.Function):
     """spatial_transformer3.transformer(U, theta) (reference spatial_transformer3.py:19-365)."""
 

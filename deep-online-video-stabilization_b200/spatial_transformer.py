@@ -15,6 +15,9 @@ __all__ = ['transformer', 'interpolate']
 
 def transformer(U, theta, out_size, name='SpatialTransformer', **kwargs):
     n = U.shape[0]
+    if n == 0 and theta.shape[0] == 0:
+        out, black, img = F.empty_batch(U, theta, int(out_size[0]), int(out_size[1]))
+        return (out, black, img) if (theta.dim() == 4 and theta.shape[-1] == 2) else (out, U.new_zeros((0, U.shape[1], U.shape[2])))
     if theta.dim() == 4 and theta.shape[-1] == 2:
         if tuple(int(v) for v in out_size) != (U.shape[1], U.shape[2]):
             raise ValueError('the multi-grid warp produces an output of the input size (reference spatial_transformer3.py:289)')
@@ -27,4 +30,6 @@ def transformer(U, theta, out_size, name='SpatialTransformer', **kwargs):
 
 def interpolate(im, x, y, out_size, name='SpatialInterpolate', **kwargs):
     """im [N,IH,IW,C]; x, y [N,out_h,out_w,1] normalised coordinates -> [N,out_h,out_w,C]."""
+    if im.shape[0] == 0 and x.shape[0] == 0:
+        return F.empty_batch(im, x, int(out_size[0]), int(out_size[1]))[0] + y.sum() * 0
     return F.Interpolate.apply(im, x, y, (int(out_size[0]), int(out_size[1])))

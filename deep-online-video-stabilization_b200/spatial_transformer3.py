@@ -16,6 +16,8 @@ NAMED = {}      # 'output_img', 'black_pix', 'Hs', 'x_map', 'y_map' of the most 
 
 def transformer(U, theta, name='SpatialTransformer', **kwargs):
     """-> (output [N,H,W,C], black_pix [N,H,W], img [N,H,W,2]); differentiable w.r.t. U and theta."""
+    if U.shape[0] == 0 and theta.shape[0] == 0:
+        return F.empty_batch(U, theta, U.shape[1], U.shape[2])
     out, black, img, Hs = F.MeshWarp.apply(U, theta)
     NAMED.update(output_img=out, black_pix=black, Hs=Hs, x_map=img[..., 0:1], y_map=img[..., 1:2])
     return out, black, img

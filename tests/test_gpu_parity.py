@@ -754,6 +754,24 @@ def test_deploy_crop_exact(mgw):
             assert torch.equal(c.cut(frame, step), frame[want[0]:want[2] + 1, want[1]:want[3] + 1, :])
 
 
+def test_empty_batch_is_a_no_op(mgw):
+    """N = 0 (an empty shard): empty outputs of the right shapes, no launch, and backward through them works"""
+    l0 = mgw.launch_count()
+    U = torch.zeros(0, 48, 64, 3, device='cuda', requires_grad=True)
+    th = torch.zeros(0, 5, 5, 2, device='cuda', requires_grad=True)
+    out, black, img = mgw.transformer(U, th)
+    assert out.shape == (0, 48, 64, 3) and black.shape == (0, 48, 64) and img.shape == (0, 48, 64, 2)
+    (out.sum() + img.sum()).backward()
+    assert th.grad.shape == th.shape and U.grad.shape == U.shape
+    o2, b2 = mgw.spatial_transformer.transformer(U, torch.zeros(0, 9, device='cuda'), (24, 32))
+    assert o2.shape == (0, 24, 32, 3) and b2.shape == (0, 48, 64)
+    o3 = mgw.interpolate(U, torch.zeros(0, 24, 32, 1, device='cuda'), torch.zeros(0, 24, 32, 1, device='cuda'), (24, 32))
+    assert o3.shape == (0, 24, 32, 3)
+    assert mgw.launch_count() == l0
+    with pytest.raises(RuntimeError):
+        mgw.transformer(torch.zeros(0, 8, 8, 3), torch.zeros(0, 5, 5, 2))          # still no CPU path
+
+
 def test_errors_are_loud(mgw):
     with pytest.raises(RuntimeError):
         mgw.transformer(torch.zeros(1, 8, 8, 3), torch.zeros(1, 5, 5, 2))          # CPU tensors: no fallback
