@@ -382,6 +382,16 @@ int mgw_stream_push(float* frames, float* masks, int depth, int slot, const floa
     return launch_stream_push(frames, masks, depth, slot, img, black, H, W, frame_out, out_stride, (cudaStream_t)stream);
 }
 
+int mgw_cvt_img2train_u8(const uint8_t* bgr, int H, int W, const int32_t* kx, const int32_t* x0, const int32_t* xn, int ksx,
+                         const int32_t* ky, const int32_t* y0, const int32_t* yn, int ksy, int out_h, int out_w, uint8_t* tmp,
+                         float* out, void* stream)
+{
+    REQUIRE(bgr && kx && x0 && xn && ky && y0 && yn && tmp && out, "mgw_cvt_img2train_u8: null pointer");
+    REQUIRE(H > 0 && W > 0 && out_h > 0 && out_w > 0 && ksx > 0 && ksy > 0 && (long long)H * out_w < (1LL << 31) &&
+            (long long)H * W < (1LL << 29), "mgw_cvt_img2train_u8: bad sizes");
+    return launch_cvt_img2train_u8(bgr, H, W, kx, x0, xn, ksx, ky, y0, yn, ksy, out_h, out_w, tmp, out, (cudaStream_t)stream);
+}
+
 int mgw_warp_rev_bundle_u8(const uint8_t* img, const double* Hs_cvt, int N, int H, int W, int C, int gh, int gw, uint8_t* dst,
                            void* stream)
 {

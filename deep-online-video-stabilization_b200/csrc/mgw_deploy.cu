@@ -180,6 +180,58 @@ int launch_remap_bundle_u8(const uint8_t* img, const float* xy, int N, int H, in
     return check_launch("remap_up");
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// cvt_img2train (config.py:6-21): BGR uint8 frame -> cv2 BGR2GRAY -> Pillow resize(BILINEAR) [-> crop] -> v*(1/255) - 0.5.
+// The host binding computes Pillow's 22-bit fixed-point coefficient tables (double arithmetic, Resample.c) once per shape
+// and slices them for the crop; the two passes below are Pillow's: horizontal first into a uint8 image, then vertical.
+namespace {
+
+__global__ void __launch_bounds__(256)
+gray_hpass_kernel(const uint8_t* __restrict__ bgr, int H, int W, const int32_t* __restrict__ kx, const int32_t* __restrict__ x0,
+                  const int32_t* __restrict__ xn, int ks, int out_w, uint8_t* __restrict__ tmp)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= H * out_w) return;
+    const int xx = t % out_w, row = t / out_w;
+    const uint8_t* p = bgr + ((size_t)row * W + __ldg(x0 + xx)) * 3;
+    const int n = __ldg(xn + xx);
+    int acc = 1 << 21;
+    for (int k = 0; k < n; ++k, p += 3) {
+        // RGB2Gray<uchar>: (B*3735 + G*19235 + R*9798 + 2^14) >> 15
+        const int g = ((int)__ldg(p) * 3735 + (int)__ldg(p + 1) * 19235 + (int)__ldg(p + 2) * 9798 + (1 << 14)) >> 15;
+        acc += g * __ldg(kx + (size_t)xx * ks + k);
+    }
+    tmp[t] = (uint8_t)min(max(acc >> 22, 0), 255);
+}
+
+__global__ void __launch_bounds__(256)
+vpass_norm_kernel(const uint8_t* __restrict__ tmp, int out_w, const int32_t* __restrict__ ky, const int32_t* __restrict__ y0,
+                  const int32_t* __restrict__ yn, int ks, int out_h, float* __restrict__ out)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= out_h * out_w) return;
+    const int xx = t % out_w, yy = t / out_w;
+    const uint8_t* p = tmp + (size_t)__ldg(y0 + yy) * out_w + xx;
+    const int n = __ldg(yn + yy);
+    int acc = 1 << 21;
+    for (int k = 0; k < n; ++k, p += out_w) acc += (int)__ldg(p) * __ldg(ky + (size_t)yy * ks + k);
+    const int v = min(max(acc >> 22, 0), 255);
+    // img * (1. / 255) - 0.5 in double (numpy), then the float32 cast of the network's placeholder
+    out[t] = (float)__dadd_rn(__dmul_rn((double)v, 1.0 / 255), -0.5);
+}
+
+}  // namespace
+
+int launch_cvt_img2train_u8(const uint8_t* bgr, int H, int W, const int32_t* kx, const int32_t* x0, const int32_t* xn, int ksx,
+                            const int32_t* ky, const int32_t* y0, const int32_t* yn, int ksy, int out_h, int out_w, uint8_t* tmp,
+                            float* out, cudaStream_t st)
+{
+    gray_hpass_kernel<<<(H * out_w + 255) / 256, 256, 0, st>>>(bgr, H, W, kx, x0, xn, ksx, out_w, tmp);
+    if (int rc = check_launch("gray_hpass")) return rc;
+    vpass_norm_kernel<<<(out_h * out_w + 255) / 256, 256, 0, st>>>(tmp, out_w, ky, y0, yn, ksy, out_h, out);
+    return check_launch("vpass_norm");
+}
+
 int launch_warp_rev_bundle_u8(const uint8_t* img, const double* Hs_cvt, int N, int H, int W, int C, int gh, int gw, uint8_t* dst,
                               cudaStream_t st)
 {

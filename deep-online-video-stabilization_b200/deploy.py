@@ -11,7 +11,7 @@ import torch
 
 from . import ops
 
-__all__ = ['warpRevBundle2', 'warpRevBundle', 'warpRev', 'cvt_theta_mat_bundle', 'StreamState', 'CropState']
+__all__ = ['warpRevBundle2', 'warpRevBundle', 'warpRev', 'cvt_theta_mat_bundle', 'cvt_img2train', 'StreamState', 'CropState']
 
 
 def warpRevBundle2(img, x_map, y_map, device=None):
@@ -32,6 +32,62 @@ def warpRevBundle2(img, x_map, y_map, device=None):
     if single:
         dst = dst[0]
     return dst.cpu().numpy() if as_numpy else dst
+
+
+def _pil_bilinear_windows(in_size, out_size):
+    """Pillow's precompute_coeffs + normalize_coeffs_8bpc (src/libImaging/Resample.c) for BILINEAR, in the same double
+    arithmetic: per output sample the first source index, the window length and the 22-bit fixed-point weights."""
+    import math
+    scale = in_size / float(out_size)
+    filterscale = max(scale, 1.0)
+    support = 1.0 * filterscale
+    ksize = int(math.ceil(support)) * 2 + 1
+    first = np.zeros(out_size, np.int32)
+    count = np.zeros(out_size, np.int32)
+    kk = np.zeros((out_size, ksize), np.int32)
+    ss = 1.0 / filterscale
+    for xx in range(out_size):
+        center = (xx + 0.5) * scale
+        xmin = max(int(center - support + 0.5), 0)
+        xmax = min(int(center + support + 0.5), in_size) - xmin
+        w = [max(1.0 - abs((x + xmin - center + 0.5) * ss), 0.0) for x in range(xmax)]
+        ww = 0.0
+        for v in w:
+            ww += v
+        for x, v in enumerate(w):
+            v = v / ww if ww != 0.0 else v
+            kk[xx, x] = int(v * (1 << 22) + 0.5)
+        first[xx], count[xx] = xmin, xmax
+    return kk, first, count
+
+
+_CVT_TABLES = {}
+
+
+def cvt_img2train(img, crop_rate=1, height=288, width=512, device='cuda', as_numpy=False):
+    """reference config.py:6-21 (`height`, `width` are its config globals): one BGR uint8 frame [H,W,3] -> the network's frame
+    format, exact: cv2 BGR2GRAY, Pillow resize(BILINEAR) (to (width, height), or to the 1/crop_rate larger size followed by
+    the centre crop), v * (1/255) - 0.5.  Returns a CUDA fp32 tensor [1,height,width,1]; as_numpy=True gives the reference's
+    float64 numpy array (same values: the network's placeholder casts to fp32).  The coefficient tables are built once per
+    shape on the host and kept on the device."""
+    im = (torch.as_tensor(np.ascontiguousarray(img)) if isinstance(img, np.ndarray) else img).to(device=device, dtype=torch.uint8)
+    H, W = int(im.shape[0]), int(im.shape[1])
+    key = (H, W, height, width, float(crop_rate), str(im.device))
+    if key not in _CVT_TABLES:
+        if crop_rate != 1:
+            h = int(height / crop_rate); dh = int((h - height) / 2)
+            w = int(width / crop_rate); dw = int((w - width) / 2)
+        else:
+            h, w, dh, dw = height, width, 0, 0
+        kx, x0, xn = _pil_bilinear_windows(W, w)
+        ky, y0, yn = _pil_bilinear_windows(H, h)
+        tabs = (kx[dw:dw + width], x0[dw:dw + width], xn[dw:dw + width], ky[dh:dh + height], y0[dh:dh + height], yn[dh:dh + height])
+        _CVT_TABLES[key] = tuple(torch.as_tensor(np.ascontiguousarray(t)).to(im.device) for t in tabs)
+    out = ops.cvt_img2train_u8(im.contiguous(), _CVT_TABLES[key], height, width).reshape(1, height, width, 1)
+    if not as_numpy:
+        return out
+    v = np.rint((out.cpu().numpy().astype(np.float64) + 0.5) * 255)          # the resampled byte, recovered exactly
+    return v * (1. / 255) - 0.5
 
 
 def cvt_theta_mat_bundle(Hs, height, width, grid_h, grid_w):

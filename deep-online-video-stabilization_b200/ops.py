@@ -427,3 +427,19 @@ def warp_rev_bundle_u8(img, Hs_cvt, gh, gw):
     with torch.cuda.device(img.device):
         check(lib.mgw_warp_rev_bundle_u8(_p(img), _p(Hs_cvt), n, h, w, c, gh, gw, _p(dst), _st()), 'mgw_warp_rev_bundle_u8')
     return dst
+
+
+def cvt_img2train_u8(bgr, tables, out_h, out_w):
+    """config.py:6-21 on the device: bgr [H,W,3] uint8, tables = (kx, x0, xn, ky, y0, yn) int32 device tensors (Pillow's
+    coefficient windows, see deploy.cvt_img2train) -> [out_h,out_w] fp32 in [-0.5, 0.5]."""
+    bgr = _chk(bgr, 'bgr', torch.uint8)
+    kx, x0, xn, ky, y0, yn = (_chk(t, 'table', torch.int32) for t in tables)
+    h, w, c = bgr.shape
+    if c != 3 or kx.shape[0] != out_w or ky.shape[0] != out_h:
+        raise ValueError('bgr must be [H,W,3] and the tables must cover the %dx%d output' % (out_h, out_w))
+    tmp = torch.empty((h, out_w), device=bgr.device, dtype=torch.uint8)
+    out = torch.empty((out_h, out_w), device=bgr.device, dtype=torch.float32)
+    with torch.cuda.device(bgr.device):
+        check(lib.mgw_cvt_img2train_u8(_p(bgr), h, w, _p(kx), _p(x0), _p(xn), kx.shape[1], _p(ky), _p(y0), _p(yn), ky.shape[1],
+                                       out_h, out_w, _p(tmp), _p(out), _st()), 'mgw_cvt_img2train_u8')
+    return out

@@ -123,6 +123,15 @@ MGW_API size_t mgw_remap_bundle_u8_workspace_bytes(int N, int H, int W);
 MGW_API int mgw_remap_bundle_u8(const uint8_t* img, const float* xy, int N, int H, int W, int C, uint8_t* dst, void* workspace,
                         void* stream);
 
+/* cvt_img2train(img, crop_rate), config.py:6-21 (the producer of every frame the network and the warp see): bgr [H,W,3] uint8 ->
+ * cv2 BGR2GRAY -> Pillow resize(BILINEAR) [-> centre crop] -> v*(1/255) - 0.5 -> out [out_h,out_w] fp32, exact.
+ * kx [out_w,ksx] / ky [out_h,ksy]: Pillow's 22-bit fixed-point weights of each output column / row, x0 / y0 the first source
+ * column / row of its window, xn / yn the window length (device int32 tables; the host binding computes them in double as
+ * Resample.c does and slices them for the crop).  tmp: device scratch of H*out_w bytes (the horizontally resampled image). */
+MGW_API int mgw_cvt_img2train_u8(const uint8_t* bgr, int H, int W, const int32_t* kx, const int32_t* x0, const int32_t* xn, int ksx,
+                         const int32_t* ky, const int32_t* y0, const int32_t* yn, int ksy, int out_h, int out_w, uint8_t* tmp,
+                         float* out, void* stream);
+
 /* warpRevBundle(img, Hs), deploy_bundle.py:148-173 (the per-cell cv2.warpPerspective variant; its call at :300 is commented
  * out in the reference): Hs_cvt [N,gh,gw,9] DOUBLE on the device = cvt_theta_mat_bundle(Hs) (:121-134: scale_mat . H .
  * inv(scale_mat), computed by the host binding with the reference's own numpy expressions); dst cell (i, j) = that region of

@@ -254,3 +254,83 @@ def warp_rev_bundle(img, Hs, grid_h, grid_w):
             c0, c1 = j * gw, (width if j == grid_w - 1 else (j + 1) * gw)
             out[r0:r1, c0:c1] = full[r0:r1, c0:c1]
     return out
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# cvt_img2train(img, crop_rate) of config.py:6-21: BGR uint8 frame -> cv2.cvtColor(BGR2GRAY) -> PIL resize(BILINEAR) [-> centre
+# crop] -> v * (1/255) - 0.5.  Third-party arithmetic (OpenCV 4.13, Pillow 12.2 here; neither pinned by the reference), restated
+# from the published algorithms and pinned against the libraries themselves (tests/golden/deploy_cvt_img2train.npz):
+#   BGR2GRAY (color_rgb.simd.hpp, RGB2Gray<uchar>): (B*3735 + G*19235 + R*9798 + 2^14) >> 15
+#   Pillow ImagingResample (src/libImaging/Resample.c), 8 bits per channel: per output sample a window of
+#   ceil(support)*2+1 taps, support = max(scale, 1) for BILINEAR, triangle weights normalised to 1 in double, converted to
+#   22-bit fixed point (round half away from zero); horizontal pass first, each pass = clip8((2^21 + sum v*k) >> 22).
+def bgr2gray_u8(img):
+    b, g, r = (img[..., k].astype(np.int64) for k in range(3))
+    return ((b * 3735 + g * 19235 + r * 9798 + (1 << 14)) >> 15).astype(np.uint8)
+
+
+def pil_bilinear_coeffs(in_size, out_size):
+    """precompute_coeffs + normalize_coeffs_8bpc of Resample.c -> (xmin [out], count [out], k int32 [out, ksize])"""
+    import math
+    scale = in_size / float(out_size)
+    filterscale = max(scale, 1.0)
+    support = 1.0 * filterscale
+    ksize = int(math.ceil(support)) * 2 + 1
+    xmin_a = np.zeros(out_size, np.int32); cnt_a = np.zeros(out_size, np.int32); kk = np.zeros((out_size, ksize), np.int32)
+    ss = 1.0 / filterscale
+    for xx in range(out_size):
+        center = (xx + 0.5) * scale
+        xmin = int(center - support + 0.5)
+        if xmin < 0:
+            xmin = 0
+        xmax = int(center + support + 0.5)
+        if xmax > in_size:
+            xmax = in_size
+        xmax -= xmin
+        w = []
+        ww = 0.0
+        for x in range(xmax):
+            t = (x + xmin - center + 0.5) * ss
+            t = -t if t < 0.0 else t
+            v = 1.0 - t if t < 1.0 else 0.0
+            w.append(v)
+            ww += v
+        for x in range(xmax):
+            v = w[x] / ww if ww != 0.0 else w[x]
+            kk[xx, x] = int(v * (1 << 22) - 0.5) if v < 0 else int(v * (1 << 22) + 0.5)
+        xmin_a[xx], cnt_a[xx] = xmin, xmax
+    return xmin_a, cnt_a, kk
+
+
+def _pil_pass(src, xmin, cnt, kk, axis):
+    """one resampling pass along `axis` of a uint8 2-D array"""
+    s = np.moveaxis(src.astype(np.int64), axis, 1)           # [other, in]
+    out = np.zeros((s.shape[0], len(xmin)), np.int64)
+    for xx in range(len(xmin)):
+        acc = np.full(s.shape[0], 1 << 21, np.int64)
+        for x in range(cnt[xx]):
+            acc += s[:, xmin[xx] + x] * int(kk[xx, x])
+        out[:, xx] = np.clip(acc >> 22, 0, 255)
+    return np.moveaxis(out.astype(np.uint8), 1, axis)
+
+
+def pil_resize_bilinear_u8(gray, out_w, out_h):
+    h, w = gray.shape
+    t = gray
+    if out_w != w:
+        t = _pil_pass(t, *pil_bilinear_coeffs(w, out_w), axis=1)
+    if out_h != h:
+        t = _pil_pass(t, *pil_bilinear_coeffs(h, out_h), axis=0)
+    return t
+
+
+def cvt_img2train(img, height, width, crop_rate=1):
+    """config.py:6-21 -> float64 [1,height,width,1] as the reference returns it"""
+    g = bgr2gray_u8(img)
+    if crop_rate != 1:
+        h = int(height / crop_rate); dh = int((h - height) / 2)
+        w = int(width / crop_rate); dw = int((w - width) / 2)
+        g = pil_resize_bilinear_u8(g, w, h)[dh:dh + height, dw:dw + width]
+    else:
+        g = pil_resize_bilinear_u8(g, width, height)
+    return (g * (1. / 255) - 0.5).reshape((1, height, width, 1))

@@ -179,6 +179,13 @@ def deploy_warp_rev_bundle2(height, width):
     return _exec_nodes(fn, ns, 'deploy_bundle.py')['warpRevBundle2']
 
 
+def config_cvt_img2train(height, width):
+    """cvt_img2train of config.py:6-21 with the config globals height / width set (needs cv2 and Pillow)."""
+    m = _import('config')
+    m.height, m.width = height, width
+    return m.cvt_img2train
+
+
 def deploy_warp_rev_bundle(height, width, grid_h, grid_w):
     """warpRevBundle and cvt_theta_mat_bundle of deploy_bundle.py:121-134,148-173 as callables (needs cv2)."""
     import math

@@ -505,6 +505,23 @@ def test_deploy_warp_rev_bundle_byte_exact(mgw):
             assert np.array_equal(got[k][..., 0], want[..., 0]), (c, k)
 
 
+def test_cvt_img2train_exact(mgw):
+    """deploy.cvt_img2train (mgw_cvt_img2train_u8) == the reference's config.py function on OpenCV + Pillow (fixture), and a
+    1080p frame against the restatement"""
+    import deploy_ref
+    g = load_golden('deploy_cvt_img2train')
+    for n in sorted(k[:-4] for k in g if k.endswith('_out')):
+        h, w, cr = g[n + '_cfg']
+        cr = 1 if cr == 1 else float(cr)
+        out = mgw.deploy.cvt_img2train(g[n + '_img'], cr, height=int(h), width=int(w))
+        assert out.is_cuda and out.dtype == torch.float32 and out.shape == (1, int(h), int(w), 1)
+        assert np.array_equal(out.cpu().numpy(), g[n + '_out'].astype(np.float32)), n
+        assert np.array_equal(mgw.deploy.cvt_img2train(g[n + '_img'], cr, height=int(h), width=int(w), as_numpy=True), g[n + '_out']), n
+    img = np.random.RandomState(4).randint(0, 256, (1080, 1920, 3)).astype(np.uint8)
+    want = deploy_ref.cvt_img2train(img, 288, 512).astype(np.float32)
+    assert np.array_equal(mgw.deploy.cvt_img2train(img).cpu().numpy(), want)
+
+
 def test_deploy_stream_state_exact(mgw):
     """StreamState (device rings, mgw_stream_assemble / mgw_stream_push) == the reference's per-frame list handling."""
     import deploy_ref

@@ -307,3 +307,25 @@ def test_warp_rev_bundle_golden_is_reference_output():
         assert np.array_equal(warp(g['ragged_img'], g['ragged_Hs']), g['ragged_dst'])
     finally:
         cv2.setUseOptimized(True)
+
+
+def test_cvt_img2train_oracle_matches_the_reference():
+    """deploy_ref.cvt_img2train (cv2 BGR2GRAY + Pillow BILINEAR resize restated) == config.py:6-21 run from the reference
+    source on OpenCV and Pillow (fixture), exactly (float64 values)"""
+    import deploy_ref
+    g = load_golden('deploy_cvt_img2train')
+    names = sorted(k[:-4] for k in g if k.endswith('_out'))
+    assert len(names) >= 6
+    for n in names:
+        h, w, cr = g[n + '_cfg']
+        got = deploy_ref.cvt_img2train(g[n + '_img'], int(h), int(w), 1 if cr == 1 else float(cr))
+        assert got.dtype == np.float64 and np.array_equal(got, g[n + '_out']), n
+
+
+@pytest.mark.reference
+def test_cvt_img2train_golden_is_reference_output():
+    pytest.importorskip('cv2'); pytest.importorskip('PIL')
+    import ref_loader
+    g = load_golden('deploy_cvt_img2train')
+    f = ref_loader.config_cvt_img2train(72, 128)
+    assert np.array_equal(f(g['crop_img'], 0.9), g['crop_out'])

@@ -136,6 +136,26 @@ try:
     cpu_wrb = float(np.median(tt))
 except Exception as e:      # noqa: BLE001
     cpu_wrb = str(e)
+# the frame producer, cvt_img2train (config.py:6-21): 1080p BGR uint8 -> gray -> Pillow bilinear to 288x512 -> fp32
+dev_cvt = cpu_cvt = None
+try:
+    import cv2
+    from PIL import Image
+    bgr_np = np.random.RandomState(8).randint(0, 256, (1080, 1920, 3)).astype(np.uint8)
+    bgr_d = torch.as_tensor(bgr_np).cuda()
+    mgw.deploy.cvt_img2train(bgr_d)
+    with torch.cuda.stream(s):
+        dev_cvt = dev_time(lambda: mgw.deploy.cvt_img2train(bgr_d), 200, flush_l2=False)
+    def cpu_cvt_fn():
+        im = Image.fromarray(cv2.cvtColor(bgr_np, cv2.COLOR_BGR2GRAY)).resize((wn, hn), Image.BILINEAR)
+        return (np.array(im) * (1. / 255) - 0.5).reshape((1, hn, wn, 1))
+    assert np.array_equal(mgw.deploy.cvt_img2train(bgr_d).cpu().numpy(), cpu_cvt_fn().astype(np.float32))
+    tt = []
+    for _ in range(30):
+        t0 = time.perf_counter(); cpu_cvt_fn(); tt.append((time.perf_counter() - t0) * 1e6)
+    cpu_cvt = float(np.median(tt))
+except Exception as e:      # noqa: BLE001
+    cpu_cvt = str(e)
 # the streaming state around it (deploy_bundle.py:259-274,319-328): input assembly from the history rings + push of the new frame
 state = mgw.StreamState(gray_h[0, ..., 0])
 cur2d = gray_d[0, ..., 0].contiguous()
@@ -180,6 +200,7 @@ res['deploy_frame_288x512'] = {
     'us_device_graph_replay_warp_plus_remap': dev_frame, 'us_device_remap_only': dev_remap,
     'us_p50_host_to_host_u8_frames': float(np.percentile(lat3, 50)), 'us_p99_host_to_host': float(np.percentile(lat3, 99)),
     'us_cpu_opencv_remap_only': cpu_us, 'cpu_threads': os.cpu_count(),
+    'us_device_cvt_img2train_1080p': dev_cvt, 'us_cpu_cv2_pil_cvt_img2train_1080p': cpu_cvt,
     'us_device_warp_rev_bundle': dev_wrb, 'us_cpu_opencv_warp_rev_bundle': cpu_wrb,
     'us_device_stream_state_assemble_plus_push': dev_state, 'us_cpu_numpy_stream_state': cpu_state_us,
     'note': '1x288x512: H2D gray fp32 + colour u8, K1 + K2 (C=1) + maps/4 + remap, D2H colour u8; CPU = the same three cv2 calls'}
