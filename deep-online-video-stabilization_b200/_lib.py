@@ -37,6 +37,7 @@ SIGNATURES = {
     'mgw_mesh_warp_img_loss_bwd': (c_i, [c_f] * 7 + [c_fl, c_f, c_fl, c_f] + [c_i] * 6 + [c_f, c_f, c_f, c_st]),
     'mgw_remap_bundle_u8_workspace_bytes': (ctypes.c_size_t, [c_i, c_i, c_i]),
     'mgw_remap_bundle_u8': (c_i, [c_f, c_f, c_i, c_i, c_i, c_i, c_f, c_f, c_st]),
+    'mgw_resize_linear_u8': (c_i, [c_f, c_i, c_i, c_i, c_f, c_f, c_i, c_i, c_f, c_st]),
     'mgw_cvt_img2train_u8': (c_i, [c_f, c_i, c_i, c_f, c_f, c_f, c_i, c_f, c_f, c_f, c_i, c_i, c_i, c_f, c_f, c_st]),
     'mgw_warp_rev_bundle_u8': (c_i, [c_f, c_f, c_i, c_i, c_i, c_i, c_i, c_i, c_f, c_st]),
     'mgw_stream_assemble': (c_i, [c_f, c_f, c_i, c_i, ctypes.POINTER(ctypes.c_int), c_i, c_i, c_f, c_i, c_i, c_f, c_st]),

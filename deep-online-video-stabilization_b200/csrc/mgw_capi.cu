@@ -382,6 +382,16 @@ int mgw_stream_push(float* frames, float* masks, int depth, int slot, const floa
     return launch_stream_push(frames, masks, depth, slot, img, black, H, W, frame_out, out_stride, (cudaStream_t)stream);
 }
 
+int mgw_resize_linear_u8(const uint8_t* img, int H, int W, int C, const int32_t* xtab, const int32_t* ytab, int out_h, int out_w,
+                         uint8_t* dst, void* stream)
+{
+    REQUIRE(img && dst, "mgw_resize_linear_u8: null pointer");
+    REQUIRE(H > 0 && W > 0 && out_h > 0 && out_w > 0 && (long long)H * W * 4 < (1LL << 31) && (long long)out_h * out_w < (1LL << 29),
+            "mgw_resize_linear_u8: bad sizes");
+    REQUIRE((!xtab || aligned(xtab, 16)) && (!ytab || aligned(ytab, 16)), "mgw_resize_linear_u8: tables must be 16-byte aligned");
+    return launch_resize_linear_u8(img, H, W, C, xtab, ytab, out_h, out_w, dst, (cudaStream_t)stream);
+}
+
 int mgw_cvt_img2train_u8(const uint8_t* bgr, int H, int W, const int32_t* kx, const int32_t* x0, const int32_t* xn, int ksx,
                          const int32_t* ky, const int32_t* y0, const int32_t* yn, int ksy, int out_h, int out_w, uint8_t* tmp,
                          float* out, void* stream)

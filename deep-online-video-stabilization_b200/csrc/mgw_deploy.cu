@@ -232,6 +232,60 @@ int launch_cvt_img2train_u8(const uint8_t* bgr, int H, int W, const int32_t* kx,
     return check_launch("vpass_norm");
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// cv2.resize(frame, (width, height)) of the uint8 colour frame (deploy_bundle.py:301; INTER_LINEAR): OpenCV's 8-bit path --
+// 11-bit fixed-point weights (tables from the host binding: x0, x1, a0, a1 per output column / row), int32 horizontal sums,
+// ((b0*(S0>>4))>>16) + ((b1*(S1>>4))>>16) + 2) >> 2 vertically; an exact 2x2 decimation is OpenCV's INTER_AREA shortcut.
+namespace {
+
+template <int C>
+__global__ void __launch_bounds__(256)
+resize_u8_kernel(const uint8_t* __restrict__ img, int H, int W, const int4* __restrict__ xtab, const int4* __restrict__ ytab,
+                 int out_h, int out_w, int area2, uint8_t* __restrict__ dst)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= out_h * out_w) return;
+    const int x = t % out_w, y = t / out_w;
+    uint8_t* o = dst + (size_t)t * C;
+    if (area2) {
+        const uint8_t* p = img + ((size_t)(2 * y) * W + 2 * x) * C;
+#pragma unroll
+        for (int ch = 0; ch < C; ++ch)
+            o[ch] = (uint8_t)(((int)__ldg(p + ch) + (int)__ldg(p + C + ch) + (int)__ldg(p + (size_t)W * C + ch) +
+                               (int)__ldg(p + (size_t)W * C + C + ch) + 2) >> 2);
+        return;
+    }
+    const int4 xt = __ldg(xtab + x), yt = __ldg(ytab + y);            // {i0, i1, a0, a1}
+    const uint8_t* r0 = img + (size_t)yt.x * W * C;
+    const uint8_t* r1 = img + (size_t)yt.y * W * C;
+#pragma unroll
+    for (int ch = 0; ch < C; ++ch) {
+        const int h0 = (int)__ldg(r0 + xt.x * C + ch) * xt.z + (int)__ldg(r0 + xt.y * C + ch) * xt.w;
+        const int h1 = (int)__ldg(r1 + xt.x * C + ch) * xt.z + (int)__ldg(r1 + xt.y * C + ch) * xt.w;
+        const int v = (((yt.z * (h0 >> 4)) >> 16) + ((yt.w * (h1 >> 4)) >> 16) + 2) >> 2;
+        o[ch] = (uint8_t)min(max(v, 0), 255);
+    }
+}
+
+}  // namespace
+
+int launch_resize_linear_u8(const uint8_t* img, int H, int W, int C, const int32_t* xtab, const int32_t* ytab, int out_h, int out_w,
+                            uint8_t* dst, cudaStream_t st)
+{
+    const int area2 = (W == 2 * out_w && H == 2 * out_h) ? 1 : 0;
+    if (!area2 && (!xtab || !ytab)) return set_error(MGW_ERR_INVALID, "resize_linear_u8: coefficient tables are required");
+    const int grid = (out_h * out_w + 255) / 256;
+    const int4* xt = reinterpret_cast<const int4*>(xtab);
+    const int4* yt = reinterpret_cast<const int4*>(ytab);
+    switch (C) {
+    case 1: resize_u8_kernel<1><<<grid, 256, 0, st>>>(img, H, W, xt, yt, out_h, out_w, area2, dst); break;
+    case 3: resize_u8_kernel<3><<<grid, 256, 0, st>>>(img, H, W, xt, yt, out_h, out_w, area2, dst); break;
+    case 4: resize_u8_kernel<4><<<grid, 256, 0, st>>>(img, H, W, xt, yt, out_h, out_w, area2, dst); break;
+    default: return set_error(MGW_ERR_UNSUPPORTED, "resize_linear_u8: C must be 1, 3 or 4 (got %d)", C);
+    }
+    return check_launch("resize_u8");
+}
+
 int launch_warp_rev_bundle_u8(const uint8_t* img, const double* Hs_cvt, int N, int H, int W, int C, int gh, int gw, uint8_t* dst,
                               cudaStream_t st)
 {

@@ -11,7 +11,7 @@ import torch
 
 from . import ops
 
-__all__ = ['warpRevBundle2', 'warpRevBundle', 'warpRev', 'cvt_theta_mat_bundle', 'cvt_img2train', 'StreamState', 'CropState']
+__all__ = ['warpRevBundle2', 'warpRevBundle', 'warpRev', 'cvt_theta_mat_bundle', 'cvt_img2train', 'cv2_resize', 'StreamState', 'CropState']
 
 
 def warpRevBundle2(img, x_map, y_map, device=None):
@@ -61,7 +61,49 @@ def _pil_bilinear_windows(in_size, out_size):
     return kk, first, count
 
 
+def _cv_linear_table(n_out, n_in, horizontal):
+    """resize.cpp: fx = (float)((d + 0.5) * scale - 0.5), s = floor(fx), fx -= s; horizontally a tap outside the row is folded
+    onto the border with weight 0, vertically the row indices are clamped and the weights kept; 11-bit weights cvRound(w*2048)"""
+    f32 = np.float32
+    scale = 1.0 / (n_out / float(n_in))
+    tab = np.zeros((n_out, 4), np.int32)
+    for d in range(n_out):
+        f = f32((d + 0.5) * scale - 0.5)
+        s0 = int(np.floor(f))
+        f = f32(f - f32(s0))
+        if horizontal:
+            if s0 < 0:
+                s0, f = 0, f32(0)
+            if s0 >= n_in - 1:
+                s0, f = n_in - 1, f32(0)
+            i0, i1 = s0, min(s0 + 1, n_in - 1)
+        else:
+            i0, i1 = min(max(s0, 0), n_in - 1), min(max(s0 + 1, 0), n_in - 1)
+        tab[d] = (i0, i1, int(np.rint(f32(f32(1) - f) * f32(2048))), int(np.rint(f * f32(2048))))
+    return tab
+
+
 _CVT_TABLES = {}
+_RESIZE_TABLES = {}
+
+
+def cv2_resize(img, dsize, device='cuda'):
+    """cv2.resize(img, dsize) for a uint8 frame [H,W,C] (reference deploy_bundle.py:301 resizes the unstable colour frame to the
+    network size before warpRevBundle2), byte-exact with OpenCV's INTER_LINEAR; dsize = (width, height) as in OpenCV.
+    numpy in -> numpy out; a CUDA frame stays on the device."""
+    as_numpy = isinstance(img, np.ndarray)
+    im = (torch.as_tensor(np.ascontiguousarray(img)) if as_numpy else img).to(device=device if as_numpy else img.device, dtype=torch.uint8)
+    H, W = int(im.shape[0]), int(im.shape[1])
+    ow, oh = int(dsize[0]), int(dsize[1])
+    key = (H, W, oh, ow, str(im.device))
+    if key not in _RESIZE_TABLES:
+        if W == 2 * ow and H == 2 * oh:
+            _RESIZE_TABLES[key] = (None, None)
+        else:
+            _RESIZE_TABLES[key] = (torch.as_tensor(_cv_linear_table(ow, W, True)).to(im.device),
+                                   torch.as_tensor(_cv_linear_table(oh, H, False)).to(im.device))
+    dst = ops.resize_linear_u8(im.contiguous(), _RESIZE_TABLES[key][0], _RESIZE_TABLES[key][1], oh, ow)
+    return dst.cpu().numpy() if as_numpy else dst
 
 
 def cvt_img2train(img, crop_rate=1, height=288, width=512, device='cuda', as_numpy=False):

@@ -443,3 +443,16 @@ def cvt_img2train_u8(bgr, tables, out_h, out_w):
         check(lib.mgw_cvt_img2train_u8(_p(bgr), h, w, _p(kx), _p(x0), _p(xn), kx.shape[1], _p(ky), _p(y0), _p(yn), ky.shape[1],
                                        out_h, out_w, _p(tmp), _p(out), _st()), 'mgw_cvt_img2train_u8')
     return out
+
+
+def resize_linear_u8(img, xtab, ytab, out_h, out_w):
+    """cv2.resize(img, (out_w, out_h)) for a uint8 [H,W,C] frame on the device; xtab / ytab: int32 [out,4] tables
+    {i0, i1, a0, a1} (see deploy.cv2_resize), None for the exact 2x2 decimation."""
+    img = _chk(img, 'img', torch.uint8)
+    h, w, c = img.shape
+    xtab = None if xtab is None else _chk(xtab, 'xtab', torch.int32)
+    ytab = None if ytab is None else _chk(ytab, 'ytab', torch.int32)
+    dst = torch.empty((out_h, out_w, c), device=img.device, dtype=torch.uint8)
+    with torch.cuda.device(img.device):
+        check(lib.mgw_resize_linear_u8(_p(img), h, w, c, _p(xtab), _p(ytab), out_h, out_w, _p(dst), _st()), 'mgw_resize_linear_u8')
+    return dst

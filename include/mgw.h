@@ -123,6 +123,13 @@ MGW_API size_t mgw_remap_bundle_u8_workspace_bytes(int N, int H, int W);
 MGW_API int mgw_remap_bundle_u8(const uint8_t* img, const float* xy, int N, int H, int W, int C, uint8_t* dst, void* workspace,
                         void* stream);
 
+/* cv2.resize(frame, (width, height)) of the uint8 colour frame, deploy_bundle.py:301 (INTER_LINEAR, OpenCV's 8-bit fixed-point
+ * path, byte-exact; an exact 2x2 decimation takes OpenCV's INTER_AREA shortcut and needs no tables).  img [H,W,C] -> dst
+ * [out_h,out_w,C]; xtab [out_w][4], ytab [out_h][4] = {i0, i1, a0, a1}: the two source indices and their 11-bit weights
+ * (device int32, 16-byte aligned; computed by the host binding as resize.cpp does). */
+MGW_API int mgw_resize_linear_u8(const uint8_t* img, int H, int W, int C, const int32_t* xtab, const int32_t* ytab, int out_h,
+                         int out_w, uint8_t* dst, void* stream);
+
 /* cvt_img2train(img, crop_rate), config.py:6-21 (the producer of every frame the network and the warp see): bgr [H,W,3] uint8 ->
  * cv2 BGR2GRAY -> Pillow resize(BILINEAR) [-> centre crop] -> v*(1/255) - 0.5 -> out [out_h,out_w] fp32, exact.
  * kx [out_w,ksx] / ky [out_h,ksy]: Pillow's 22-bit fixed-point weights of each output column / row, x0 / y0 the first source

@@ -334,3 +334,43 @@ def cvt_img2train(img, height, width, crop_rate=1):
     else:
         g = pil_resize_bilinear_u8(g, width, height)
     return (g * (1. / 255) - 0.5).reshape((1, height, width, 1))
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# cv2.resize(frame, (width, height)) of the uint8 colour frame (deploy_bundle.py:301, default INTER_LINEAR), resize.cpp:
+#   coefficients as for float (fx = (dx+0.5)*scale - 0.5, border taps folded with weight 0) but in 11-bit fixed point
+#   (cvRound(w * 2048)); horizontal pass in int32: S[sx]*a0 + S[sx+1]*a1; vertical pass of the 8-bit specialisation:
+#   ((b0 * (S0 >> 4)) >> 16) + ((b1 * (S1 >> 4)) >> 16) + 2) >> 2.  An exact 2x2 decimation is rerouted by OpenCV to INTER_AREA
+#   (mean of the 2x2 block, (sum + 2) >> 2).  Plain C++ path (cv2.setUseOptimized(False)); the dispatched path (IPP) may differ.
+def resize_linear_u8(img, out_w, out_h):
+    H, W = img.shape[:2]
+    src = img.astype(np.int64).reshape(H, W, -1)
+    if W == 2 * out_w and H == 2 * out_h:
+        s = src[0::2, 0::2] + src[0::2, 1::2] + src[1::2, 0::2] + src[1::2, 1::2]
+        return ((s + 2) >> 2).astype(np.uint8).reshape((out_h, out_w) + img.shape[2:])
+
+    def coeffs(n_out, n_in, clamp_weights):
+        scale = _scale(n_out, n_in)
+        i0 = np.zeros(n_out, np.int64); i1 = np.zeros(n_out, np.int64); a = np.zeros((n_out, 2), np.int64)
+        for d in range(n_out):
+            f = f32((d + 0.5) * scale - 0.5)
+            s0 = int(np.floor(f))
+            f = f32(f - f32(s0))
+            if clamp_weights:                       # horizontal: fold the outside tap onto the border with weight 0
+                if s0 < 0:
+                    s0, f = 0, f32(0)
+                if s0 >= n_in - 1:
+                    s0, f = n_in - 1, f32(0)
+                i0[d], i1[d] = s0, min(s0 + 1, n_in - 1)
+            else:                                   # vertical: clamp the row indices, keep the weights
+                i0[d], i1[d] = min(max(s0, 0), n_in - 1), min(max(s0 + 1, 0), n_in - 1)
+            a[d] = (int(np.rint(f32(f32(1) - f) * f32(2048))), int(np.rint(f * f32(2048))))
+        return i0, i1, a
+
+    x0, x1, ax = coeffs(out_w, W, True)
+    y0, y1, ay = coeffs(out_h, H, False)
+    hp = src[:, x0] * ax[:, 0][None, :, None] + src[:, x1] * ax[:, 1][None, :, None]          # [H, out_w, C] int
+    r0, r1 = hp[y0], hp[y1]
+    b0, b1 = ay[:, 0][:, None, None], ay[:, 1][:, None, None]
+    out = (((b0 * (r0 >> 4)) >> 16) + ((b1 * (r1 >> 4)) >> 16) + 2) >> 2
+    return np.clip(out, 0, 255).astype(np.uint8).reshape((out_h, out_w) + img.shape[2:])

@@ -522,6 +522,21 @@ def test_cvt_img2train_exact(mgw):
     assert np.array_equal(mgw.deploy.cvt_img2train(img).cpu().numpy(), want)
 
 
+def test_cv2_resize_byte_exact(mgw):
+    """deploy.cv2_resize (mgw_resize_linear_u8) == cv2.resize of the uint8 frame (fixture made by OpenCV), and the deploy loop's
+    own size (1080p -> 512x288) against the restatement"""
+    import deploy_ref
+    g = load_golden('deploy_cv2_resize')
+    for n in sorted(k[:-4] for k in g if k.endswith('_dst')):
+        want = g[n + '_dst']
+        img = g[n + '_img']
+        got = mgw.deploy.cv2_resize(img if img.ndim == 3 else img[..., None], (want.shape[1], want.shape[0]))
+        assert np.array_equal(got.reshape(want.shape), want), n
+    img = np.random.RandomState(6).randint(0, 256, (1080, 1920, 3)).astype(np.uint8)
+    got = mgw.deploy.cv2_resize(torch.as_tensor(img).cuda(), (512, 288))
+    assert got.is_cuda and np.array_equal(got.cpu().numpy(), deploy_ref.resize_linear_u8(img, 512, 288))
+
+
 def test_deploy_stream_state_exact(mgw):
     """StreamState (device rings, mgw_stream_assemble / mgw_stream_push) == the reference's per-frame list handling."""
     import deploy_ref

@@ -329,3 +329,15 @@ def test_cvt_img2train_golden_is_reference_output():
     g = load_golden('deploy_cvt_img2train')
     f = ref_loader.config_cvt_img2train(72, 128)
     assert np.array_equal(f(g['crop_img'], 0.9), g['crop_out'])
+
+
+def test_cv2_resize_oracle_matches_opencv():
+    """deploy_ref.resize_linear_u8 == cv2.resize(uint8 frame, dsize) (fixture made by OpenCV itself), byte for byte"""
+    import deploy_ref
+    g = load_golden('deploy_cv2_resize')
+    names = sorted(k[:-4] for k in g if k.endswith('_dst'))
+    assert len(names) >= 6
+    for n in names:
+        want = g[n + '_dst']
+        assert np.array_equal(deploy_ref.resize_linear_u8(g[n + '_img'], want.shape[1], want.shape[0]), want), n
+        assert int(g[n + '_optimized_differs']) == 0

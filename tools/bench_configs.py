@@ -156,6 +156,36 @@ try:
     cpu_cvt = float(np.median(tt))
 except Exception as e:      # noqa: BLE001
     cpu_cvt = str(e)
+# the whole per-frame deploy loop on the device (deploy_bundle.py:259-328 minus the network, whose output is a fixed mesh here):
+# H2D of the raw 1080p BGR frame -> cvt_img2train -> input assembly from the rings -> K1 + K2 on the gray frame -> ring push +
+# black accumulation -> cv2.resize of the colour frame -> warpRevBundle2 -> D2H of the stabilised 512x288 colour frame
+loop_p50 = loop_p99 = None
+try:
+    raw_h = torch.as_tensor(np.random.RandomState(9).randint(0, 256, (1080, 1920, 3)).astype(np.uint8)).pin_memory()
+    raw_d = torch.empty((1080, 1920, 3), device=dev, dtype=torch.uint8)
+    out_hh = torch.empty((hn, wn, 3), dtype=torch.uint8).pin_memory()
+    st_loop = mgw.StreamState(gray_h[0, ..., 0])
+    crop = mgw.CropState(hn, wn)
+    with torch.cuda.stream(s):
+        def loop_frame():
+            raw_d.copy_(raw_h, non_blocking=True)
+            cur = mgw.deploy.cvt_img2train(raw_d)                               # [1,288,512,1] fp32
+            in_x = st_loop.assemble(cur.reshape(hn, wn))                        # the network's input (unused: no network here)
+            out, black, img = mgw.transformer(cur, th)
+            st_loop.push(out.reshape(hn, wn), black.reshape(hn, wn))
+            crop.add(black)
+            small = mgw.deploy.cv2_resize(raw_d, (wn, hn))
+            dst = ops.remap_bundle_u8(small.reshape(1, hn, wn, 3), img)
+            out_hh.copy_(dst[0], non_blocking=True)
+            s.synchronize()
+        for _ in range(20):
+            loop_frame()
+        lat = []
+        for _ in range(500):
+            t0 = time.perf_counter(); loop_frame(); lat.append((time.perf_counter() - t0) * 1e6)
+    loop_p50, loop_p99 = float(np.percentile(lat, 50)), float(np.percentile(lat, 99))
+except Exception as e:      # noqa: BLE001
+    loop_p50 = str(e)
 # the streaming state around it (deploy_bundle.py:259-274,319-328): input assembly from the history rings + push of the new frame
 state = mgw.StreamState(gray_h[0, ..., 0])
 cur2d = gray_d[0, ..., 0].contiguous()
@@ -200,6 +230,7 @@ res['deploy_frame_288x512'] = {
     'us_device_graph_replay_warp_plus_remap': dev_frame, 'us_device_remap_only': dev_remap,
     'us_p50_host_to_host_u8_frames': float(np.percentile(lat3, 50)), 'us_p99_host_to_host': float(np.percentile(lat3, 99)),
     'us_cpu_opencv_remap_only': cpu_us, 'cpu_threads': os.cpu_count(),
+    'us_p50_whole_deploy_loop_1080p_bgr_in_288x512_bgr_out_host_to_host': loop_p50, 'us_p99_whole_deploy_loop': loop_p99,
     'us_device_cvt_img2train_1080p': dev_cvt, 'us_cpu_cv2_pil_cvt_img2train_1080p': cpu_cvt,
     'us_device_warp_rev_bundle': dev_wrb, 'us_cpu_opencv_warp_rev_bundle': cpu_wrb,
     'us_device_stream_state_assemble_plus_push': dev_state, 'us_cpu_numpy_stream_state': cpu_state_us,
