@@ -488,7 +488,7 @@ int mgw_temp_loss_fwd(const float* out1, const float* black1, const float* out2,
                       int N, int H, int W, int C, float* sums, void* stream)
 {
     REQUIRE(out1 && black1 && out2 && black2 && flow && sums, "mgw_temp_loss_fwd: null pointer");
-    REQUIRE(N > 0 && H > 0 && W > 0 && C > 0, "mgw_temp_loss_fwd: bad sizes");
+    REQUIRE(N > 0 && H > 0 && W > 0 && C > 0 && (long long)H * W * C < (1LL << 31), "mgw_temp_loss_fwd: bad sizes");
     REQUIRE(aligned(flow, 8), "mgw_temp_loss_fwd: flow must be 8-byte aligned");
     return launch_temp_loss_fwd(out1, black1, out2, black2, flow, N, H, W, C, sums, (cudaStream_t)stream);
 }
@@ -498,7 +498,7 @@ int mgw_temp_loss_bwd(const float* out1, const float* black1, const float* out2,
                       float* d_out2, void* stream)
 {
     REQUIRE(out1 && black1 && out2 && black2 && flow && sums && d_out1 && d_out2, "mgw_temp_loss_bwd: null pointer");
-    REQUIRE(N > 0 && H > 0 && W > 0 && C > 0, "mgw_temp_loss_bwd: bad sizes");
+    REQUIRE(N > 0 && H > 0 && W > 0 && C > 0 && (long long)H * W * C < (1LL << 31), "mgw_temp_loss_bwd: bad sizes");
     REQUIRE(aligned(flow, 8), "mgw_temp_loss_bwd: flow must be 8-byte aligned");
     return launch_temp_loss_bwd(out1, black1, out2, black2, flow, sums, upstream, upstream_dev, N, H, W, C, d_out1, d_out2, (cudaStream_t)stream);
 }

@@ -117,46 +117,63 @@ feature_loss_bwd_kernel(const float* __restrict__ matches, const float* __restri
 }
 
 // ---------------------------------------------------------------- temp_loss
-template <bool BWD>
-__global__ void __launch_bounds__(256)
+// CC = compile-time channel count (1, 3, 4) or 0 = run-time C.  Per-sample base pointers and 32-bit offsets inside a sample
+// (H*W*C < 2^31 is checked by the C ABI): the 64-bit index arithmetic of the first version cost 74 registers (3 blocks per SM).
+template <bool BWD, int CC>
+__global__ void __launch_bounds__(256, BWD ? 4 : 5)
 temp_loss_kernel(const float* __restrict__ out1, const float* __restrict__ black1, const float* __restrict__ out2,
                  const float* __restrict__ black2, const float* __restrict__ flow, const float* __restrict__ sums_in,
-                 float upstream, const float* __restrict__ up_dev, int N, int H, int W, int C, float* __restrict__ sums,
+                 float upstream, const float* __restrict__ up_dev, int N, int H, int W, int Crt, float* __restrict__ sums,
                  float* __restrict__ d_out1,
                  float* __restrict__ d_out2)
 {
     __shared__ float sh[8];
+    const int C = CC ? CC : Crt;
     const int n = blockIdx.y, HW = H * W;
     float se = 0.0f, sm = 0.0f;
     float k = 0.0f;
     if (BWD && up_dev) upstream *= __ldg(up_dev);
     if (BWD) k = upstream * 2.0f / ((__ldg(sums_in + 2 * n + 1) + 1e-8f) * (float)N);
-    for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < HW; q += gridDim.x * blockDim.x) {
-        const size_t p = (size_t)n * HW + q;
-        const float2 f = __ldg(reinterpret_cast<const float2*>(flow) + p);
+    const size_t sbase = (size_t)n * HW;
+    const float* b2 = black2 + sbase;
+    const float* o2 = out2 + sbase * C;
+    const float* o1 = out1 + sbase * C;
+    const float* b1 = black1 + sbase;
+    const float2* fl = reinterpret_cast<const float2*>(flow) + sbase;
+    float* g1p = BWD ? d_out1 + sbase * C : nullptr;
+    float* d2 = BWD ? d_out2 + sbase * C : nullptr;
+    // each iteration is two dependent round trips to memory (the flow sample, then the taps it points at): the next
+    // iteration's flow sample is fetched one iteration ahead, and the grid is sized for ~8 iterations per thread
+    const int stride = gridDim.x * blockDim.x;
+    int q = blockIdx.x * blockDim.x + threadIdx.x;
+    float2 f_next = (q < HW) ? __ldg(fl + q) : make_float2(0.0f, 0.0f);
+    for (; q < HW; q += stride) {
+        const float2 f = f_next;
+        if (q + stride < HW) f_next = __ldg(fl + q + stride);
         const Taps t = make_taps(f.x, f.y, H, W);                                   // train_bundle_nobm.py:117-118
-        const size_t ia = (size_t)t.y0 * W + t.x0, ib = (size_t)t.y1 * W + t.x0;
-        const size_t ic = (size_t)t.y0 * W + t.x1, id = (size_t)t.y1 * W + t.x1;
-        const float* b2 = black2 + (size_t)n * HW;
+        const int ia = t.y0 * W + t.x0, ib = t.y1 * W + t.x0, ic = t.y0 * W + t.x1, id = t.y1 * W + t.x1;
         const float nb2 = blend(t, 1.0f - __ldg(b2 + ia), 1.0f - __ldg(b2 + ib), 1.0f - __ldg(b2 + ic), 1.0f - __ldg(b2 + id));
-        const float m = (1.0f - __ldg(black1 + p)) * nb2;                           // :121
-        const float* o2 = out2 + (size_t)n * HW * C;
+        const float m = (1.0f - __ldg(b1 + q)) * nb2;                               // :121
         sm += m;
         const float wa = t.ax * t.ay, wb = t.ax * t.by, wc = t.bx * t.ay, wd = t.bx * t.by;
-        for (int ch = 0; ch < C; ++ch) {
-            const float v2 = blend(t, __ldg(o2 + ia * C + ch), __ldg(o2 + ib * C + ch), __ldg(o2 + ic * C + ch), __ldg(o2 + id * C + ch));
-            const float e = (__ldg(out1 + p * C + ch) - v2) * m;                    // :120,:122
-            if (!BWD) {
-                se = fmaf(e, e, se);
-            } else {
-                const float g1 = k * e * m;
-                d_out1[p * C + ch] = g1;
-                if (!taps_scatter(t)) continue;
-                float* d2 = d_out2 + (size_t)n * HW * C;
-                atomicAdd(d2 + ia * C + ch, -g1 * wa);
-                atomicAdd(d2 + ib * C + ch, -g1 * wb);
-                atomicAdd(d2 + ic * C + ch, -g1 * wc);
-                atomicAdd(d2 + id * C + ch, -g1 * wd);
+        const bool scatter = BWD && taps_scatter(t);
+#pragma unroll
+        for (int ch = 0; ch < (CC ? CC : 1); ++ch) {
+            for (int c2 = ch; c2 < C; c2 += (CC ? C : 1)) {                         // run-time C: the inner loop walks the channels
+                const float v2 = blend(t, __ldg(o2 + ia * C + c2), __ldg(o2 + ib * C + c2), __ldg(o2 + ic * C + c2), __ldg(o2 + id * C + c2));
+                const float e = (__ldg(o1 + q * C + c2) - v2) * m;                  // :120,:122
+                if (!BWD) {
+                    se = fmaf(e, e, se);
+                } else {
+                    const float g1 = k * e * m;
+                    g1p[q * C + c2] = g1;
+                    if (scatter) {
+                        atomicAdd(d2 + ia * C + c2, -g1 * wa);
+                        atomicAdd(d2 + ib * C + c2, -g1 * wb);
+                        atomicAdd(d2 + ic * C + c2, -g1 * wc);
+                        atomicAdd(d2 + id * C + c2, -g1 * wd);
+                    }
+                }
             }
         }
     }
@@ -167,22 +184,48 @@ temp_loss_kernel(const float* __restrict__ out1, const float* __restrict__ black
     }
 }
 
+template <bool BWD>
+static void launch_temp_loss(int C, dim3 grid, cudaStream_t st, const float* out1, const float* black1, const float* out2,
+                             const float* black2, const float* flow, const float* sums_in, float upstream, const float* up_dev, int N,
+                             int H, int W, float* sums, float* d_out1, float* d_out2)
+{
+#define MGW_TL(CC) temp_loss_kernel<BWD, CC><<<grid, 256, 0, st>>>(out1, black1, out2, black2, flow, sums_in, upstream, up_dev, N, H, W, C, \
+                                                                   sums, d_out1, d_out2)
+    switch (C) {
+    case 1: MGW_TL(1); break;
+    case 3: MGW_TL(3); break;
+    case 4: MGW_TL(4); break;
+    default: MGW_TL(0); break;
+    }
+#undef MGW_TL
+}
+
 // ---------------------------------------------------------------- launchers
 // blocks per sample of the grid-stride reductions: about 8 resident blocks per SM over the whole batch (148 SMs), so that a
 // block amortises its two block-wide reductions and its two atomics over many pixels (one pixel per thread made these
 // kernels latency-bound: 58 us for 132 MB)
-static unsigned blocks_for(int HW, int N)
+static unsigned blocks_for(int HW, int N, int resident_per_sm = 8)
 {
     const unsigned full = (unsigned)((HW + 255) / 256);
-    unsigned per = (unsigned)((148 * 8 + N - 1) / N);
+    unsigned per = (unsigned)((148 * resident_per_sm + N - 1) / N);
     if (per < 1) per = 1;
     return per < full ? per : full;
+}
+
+#ifndef MGW_LOSS_ITERS
+#define MGW_LOSS_ITERS 4
+#endif
+// the same, but never more than `iters` grid-stride iterations per thread (kernels whose iterations are dependent memory round trips)
+static unsigned blocks_iters(int HW, int N, int resident_per_sm, int iters)
+{
+    const unsigned a = blocks_for(HW, N, resident_per_sm), b = (unsigned)((HW + 256 * iters - 1) / (256 * iters));
+    return a > b ? a : b;
 }
 
 int launch_img_loss_fwd(const float* out, const float* y, const float* black, int N, int H, int W, int C, float* sums, cudaStream_t st)
 {
     cudaMemsetAsync(sums, 0, sizeof(float) * 2 * N, st);
-    img_loss_fwd_kernel<<<dim3(blocks_for(H * W, N), N), 256, 0, st>>>(out, y, black, H * W, C, sums);
+    img_loss_fwd_kernel<<<dim3(blocks_iters(H * W, N, 8, MGW_LOSS_ITERS), N), 256, 0, st>>>(out, y, black, H * W, C, sums);
     return check_launch("img_loss_fwd");
 }
 
@@ -212,8 +255,8 @@ int launch_temp_loss_fwd(const float* out1, const float* black1, const float* ou
                          const float* flow, int N, int H, int W, int C, float* sums, cudaStream_t st)
 {
     cudaMemsetAsync(sums, 0, sizeof(float) * 2 * N, st);
-    temp_loss_kernel<false><<<dim3(blocks_for(H * W, N), N), 256, 0, st>>>(out1, black1, out2, black2, flow, nullptr, 0.0f, nullptr,
-                                                                        N, H, W, C, sums, nullptr, nullptr);
+    launch_temp_loss<false>(C, dim3(blocks_iters(H * W, N, 5, MGW_LOSS_ITERS), N), st, out1, black1, out2, black2, flow, nullptr, 0.0f, nullptr, N, H, W,
+                            sums, nullptr, nullptr);
     return check_launch("temp_loss_fwd");
 }
 
@@ -222,8 +265,8 @@ int launch_temp_loss_bwd(const float* out1, const float* black1, const float* ou
                          float* d_out1, float* d_out2, cudaStream_t st)
 {
     cudaMemsetAsync(d_out2, 0, sizeof(float) * (size_t)N * H * W * C, st);
-    temp_loss_kernel<true><<<dim3(blocks_for(H * W, N), N), 256, 0, st>>>(out1, black1, out2, black2, flow, sums, upstream, up_dev,
-                                                                       N, H, W, C, nullptr, d_out1, d_out2);
+    launch_temp_loss<true>(C, dim3(blocks_iters(H * W, N, 4, MGW_LOSS_ITERS), N), st, out1, black1, out2, black2, flow, sums, upstream, up_dev, N, H, W,
+                           nullptr, d_out1, d_out2);
     return check_launch("temp_loss_bwd");
 }
 

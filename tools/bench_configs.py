@@ -274,7 +274,10 @@ def clip_batch(seed):
 
 
 b1, b2 = clip_batch(40), clip_batch(50)
-flow = torch.tensor(synth.uniform((nb, 288, 512, 2), -1, 1, 60), device=dev)
+# optical flow between the two clips as sampling coordinates: identity grid + a smooth displacement of a few pixels (a flow of
+# independent uniform samples would make every gather and every atomic of temp_loss a random access, which no video does)
+_ys, _xs = torch.meshgrid(torch.linspace(-1, 1, 288, device=dev), torch.linspace(-1, 1, 512, device=dev), indexing='ij')
+flow = torch.stack([_xs + 0.03 * torch.sin(3 * _ys), _ys + 0.03 * torch.cos(2 * _xs)], -1).expand(nb, 288, 512, 2).contiguous()
 gates = mgw.loss_gates(6000)
 opt = torch.optim.Adam(net.parameters(), lr=2e-5)
 
