@@ -2,7 +2,9 @@
 
 Layout: csrc/ (CUDA kernels + C ABI, built into libmgw_b200.so), _lib.py (ctypes), ops.py (tensor carriers),
 functional.py (autograd), spatial_transformer3.py / spatial_transformer.py (reference-named operator modules),
-losses.py (vertex builder + fused loss epilogue), deploy.py (deploy-side colour-frame warp), parallel.py (batch sharding + NCCL all-reduce).
+losses.py (vertex builder, loss epilogues, vertex regularisers, schedule, total loss), deploy.py (the deploy loop's pieces: frame
+producer, colour-frame warps, history rings, crop), stabnet.py (torch backbone carrier + the reference's objective),
+parallel.py (batch sharding + NCCL all-reduce), dropin/ (top-level module names of the reference).
 """
 from . import _lib, deploy, functional, losses, ops, parallel, spatial_transformer, spatial_transformer3, stabnet  # noqa: F401
 from ._lib import MgwError, launch_count, set_impl  # noqa: F401

@@ -93,5 +93,6 @@ def launch_count():
 
 
 def set_impl(mode):
-    """'auto' | 'generic' | 'tma'"""
+    """'auto' (pipeline / TMA tiles when the shape allows, else generic) | 'generic' | 'tma' (one TMA tile per CTA, error if the
+    shape does not fit) | 'pipe' (the persistent forward pipeline; the backward then takes the TMA tiles)"""
     check(lib.mgw_set_impl({'auto': 0, 'generic': 1, 'tma': 2, 'pipe': 3}[mode]), 'mgw_set_impl')
