@@ -47,6 +47,8 @@ SIGNATURES = {
     'mgw_black_accumulate': (c_i, [c_f, c_f, c_i, c_st]),
     'mgw_crop_rect_workspace_bytes': (ctypes.c_size_t, [c_i, c_i]),
     'mgw_crop_rect': (c_i, [c_f, c_i, c_i, c_i, c_f, c_f, c_st]),
+    'mgw_stream_assemble_dev': (c_i, [c_f, c_f, c_i, c_f, ctypes.POINTER(ctypes.c_int), c_i, c_i, c_f, c_i, c_i, c_f, c_st]),
+    'mgw_stream_push_dev': (c_i, [c_f, c_f, c_i, c_f, c_f, c_f, c_i, c_i, c_st]),
     'mgw_interp_fwd': (c_i, [c_f, c_f, c_f] + [c_i] * 6 + [c_f, c_st]),
     'mgw_interp_bwd': (c_i, [c_f, c_f, c_f, c_f] + [c_i] * 6 + [c_f, c_f, c_f, c_st]),
     'mgw_homography_warp_fwd': (c_i, [c_f, c_f] + [c_i] * 6 + [c_f, c_f, c_f, c_st]),

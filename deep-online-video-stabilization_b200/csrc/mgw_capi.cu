@@ -449,6 +449,24 @@ int mgw_crop_rect(const int32_t* all_black, int H, int W, int step, void* worksp
     return launch_crop_rect(all_black, H, W, step, workspace, rect, (cudaStream_t)stream);
 }
 
+int mgw_stream_assemble_dev(const float* frames, const float* masks, int depth, const int32_t* head_dev, const int* taps, int ntaps,
+                            int use_masks, const float* cur, int H, int W, float* in_x, void* stream)
+{
+    REQUIRE(frames && cur && in_x && taps && head_dev && (masks || !use_masks), "mgw_stream_assemble_dev: null pointer");
+    REQUIRE(depth > 0 && H > 0 && W > 0 && (long long)H * W < (1LL << 31), "mgw_stream_assemble_dev: bad sizes");
+    return launch_stream_assemble(frames, masks, depth, 0, taps, ntaps, use_masks, cur, H, W, in_x, (cudaStream_t)stream,
+                                  reinterpret_cast<const int*>(head_dev));
+}
+
+int mgw_stream_push_dev(float* frames, float* masks, int depth, int32_t* head_dev, const float* img, const float* black, int H, int W,
+                        void* stream)
+{
+    REQUIRE(img && black && frames && head_dev, "mgw_stream_push_dev: null pointer");
+    REQUIRE(depth > 0 && H > 0 && W > 0 && (long long)H * W < (1LL << 31), "mgw_stream_push_dev: bad sizes");
+    TRY(launch_stream_push(frames, masks, depth, 0, img, black, H, W, nullptr, 1, (cudaStream_t)stream, reinterpret_cast<const int*>(head_dev)));
+    return launch_stream_advance(reinterpret_cast<int*>(head_dev), depth, (cudaStream_t)stream);
+}
+
 int mgw_img_loss_fwd(const float* out, const float* y, const float* black, int N, int H, int W, int C, float* sums, void* stream)
 {
     REQUIRE(out && y && black && sums, "mgw_img_loss_fwd: null pointer");

@@ -108,8 +108,9 @@ int launch_crop_rect(const int32_t* all_black, int H, int W, int step, void* wor
 
 // mgw_stream.cu : deploy-side streaming state (device-resident history rings, deploy_bundle.py:204-232,259-295,319-327)
 int launch_stream_assemble(const float* frames, const float* masks, int depth, int head, const int* taps_host, int ntaps, int use_masks,
-                           const float* cur, int H, int W, float* in_x, cudaStream_t st);
+                           const float* cur, int H, int W, float* in_x, cudaStream_t st, const int* head_dev = nullptr);
 int launch_stream_push(float* frames, float* masks, int depth, int slot, const float* img, const float* black, int H, int W,
-                       float* frame_out, int out_stride, cudaStream_t st);
+                       float* frame_out, int out_stride, cudaStream_t st, const int* head_dev = nullptr);
+int launch_stream_advance(int* head_dev, int depth, cudaStream_t st);
 
 }  // namespace mgw

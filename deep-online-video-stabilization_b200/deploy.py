@@ -181,15 +181,20 @@ class StreamState:
             st.push(img, black)
     """
 
-    def __init__(self, first_frame, depth=32, taps=(1, 2, 4, 8, 16, 32), use_masks=True, device='cuda'):
+    def __init__(self, first_frame, depth=32, taps=(1, 2, 4, 8, 16, 32), use_masks=True, device='cuda', device_head=False):
+        """device_head=True keeps the ring head in device memory: assemble / push then take no per-frame launch parameter, so the
+        whole frame loop can be captured in one CUDA graph and replayed (the host-side `head` is not maintained in that mode)."""
         f = torch.as_tensor(first_frame, dtype=torch.float32).to(device)
         h, w = f.shape
         self.frames = f.reshape(1, h, w).repeat(depth, 1, 1).contiguous()
         self.masks = torch.zeros((depth, h, w), device=f.device, dtype=torch.float32)
         self.depth, self.taps, self.use_masks, self.head = depth, tuple(int(t) for t in taps), use_masks, depth - 1
+        self.head_dev = torch.full((1,), depth - 1, device=f.device, dtype=torch.int32) if device_head else None
 
-    def assemble(self, cur):
+    def assemble(self, cur, out=None):
         cur = torch.as_tensor(cur, dtype=torch.float32).to(self.frames.device).reshape(self.frames.shape[1:]).contiguous()
+        if self.head_dev is not None:
+            return ops.stream_assemble_dev(self.frames, self.masks, self.head_dev, self.taps, cur, self.use_masks, out=out)
         return ops.stream_assemble(self.frames, self.masks, self.head, self.taps, cur, self.use_masks)
 
     def refeed(self, in_x, img, black):
@@ -197,13 +202,17 @@ class StreamState:
                         refeed_into=in_x)
 
     def push(self, img, black):
+        img, black = img.reshape(self.frames.shape[1:]).contiguous(), black.reshape(self.frames.shape[1:]).contiguous()
+        if self.head_dev is not None:
+            ops.stream_push_dev(self.frames, self.masks, self.head_dev, img, black)
+            return
         self.head = (self.head + 1) % self.depth
-        ops.stream_push(self.frames, self.masks, self.head, img.reshape(self.frames.shape[1:]).contiguous(),
-                        black.reshape(self.frames.shape[1:]).contiguous())
+        ops.stream_push(self.frames, self.masks, self.head, img, black)
 
     def history(self):
         """(frames, masks) oldest first, as the reference's lists hold them"""
-        order = [(self.head + 1 + k) % self.depth for k in range(self.depth)]
+        head = int(self.head_dev.item()) if self.head_dev is not None else self.head
+        order = [(head + 1 + k) % self.depth for k in range(self.depth)]
         return self.frames[order], self.masks[order]
 
 

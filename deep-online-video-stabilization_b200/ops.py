@@ -456,3 +456,30 @@ def resize_linear_u8(img, xtab, ytab, out_h, out_w):
     with torch.cuda.device(img.device):
         check(lib.mgw_resize_linear_u8(_p(img), h, w, c, _p(xtab), _p(ytab), out_h, out_w, _p(dst), _st()), 'mgw_resize_linear_u8')
     return dst
+
+
+def stream_assemble_dev(frames, masks, head_dev, taps, cur, use_masks=True, out=None):
+    """stream_assemble with the ring head read on the device (head_dev: int32 [1]); `out`: optional preallocated in_x
+    (static buffers for CUDA-graph capture of the frame loop)."""
+    import ctypes
+    frames, cur, head_dev = _chk(frames, 'frames'), _chk(cur, 'cur'), _chk(head_dev, 'head_dev', torch.int32)
+    masks = _chk(masks, 'masks') if use_masks else None
+    depth, h, w = frames.shape
+    nch = (2 if use_masks else 1) * len(taps) + 1
+    in_x = out if out is not None else torch.empty((1, h, w, nch), device=frames.device, dtype=torch.float32)
+    if tuple(in_x.shape) != (1, h, w, nch) or not in_x.is_contiguous():
+        raise ValueError('out must be a contiguous [1,%d,%d,%d] tensor' % (h, w, nch))
+    arr = (ctypes.c_int * len(taps))(*[int(t) for t in taps])
+    with torch.cuda.device(frames.device):
+        check(lib.mgw_stream_assemble_dev(_p(frames), _p(masks), depth, _p(head_dev), arr, len(taps), 1 if use_masks else 0, _p(cur),
+                                          h, w, _p(in_x), _st()), 'mgw_stream_assemble_dev')
+    return in_x
+
+
+def stream_push_dev(frames, masks, head_dev, img, black):
+    """stream_push into the slot after the device-resident head, then head = (head + 1) % depth on the device."""
+    frames, img, black, head_dev = _chk(frames, 'frames'), _chk(img, 'img'), _chk(black, 'black'), _chk(head_dev, 'head_dev', torch.int32)
+    masks = None if masks is None else _chk(masks, 'masks')
+    depth, h, w = frames.shape
+    with torch.cuda.device(frames.device):
+        check(lib.mgw_stream_push_dev(_p(frames), _p(masks), depth, _p(head_dev), _p(img), _p(black), h, w, _st()), 'mgw_stream_push_dev')

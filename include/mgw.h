@@ -185,6 +185,14 @@ MGW_API int mgw_black_accumulate(const float* black, int32_t* all_black, int n, 
 MGW_API size_t mgw_crop_rect_workspace_bytes(int H, int W);
 MGW_API int mgw_crop_rect(const int32_t* all_black, int H, int W, int step, void* workspace, int32_t* rect, void* stream);
 
+/* The same with the ring head on the DEVICE (head_dev: one int32, the slot of the newest entry): no launch parameter changes
+ * from frame to frame, so the whole per-frame loop can be captured once in a CUDA graph and replayed.  mgw_stream_push_dev
+ * writes the slot after the head and then advances the head (two launches). */
+MGW_API int mgw_stream_assemble_dev(const float* frames, const float* masks, int depth, const int32_t* head_dev, const int* taps,
+                            int ntaps, int use_masks, const float* cur, int H, int W, float* in_x, void* stream);
+MGW_API int mgw_stream_push_dev(float* frames, float* masks, int depth, int32_t* head_dev, const float* img, const float* black,
+                        int H, int W, void* stream);
+
 /* ---- a6: interpolate(im, x, y, out_size), spatial_transformer.py:200-281 ------------------------------
  * im [N,IH,IW,C]; x,y [N,OH,OW] normalised coords -> out [N,OH,OW,C]. */
 MGW_API int mgw_interp_fwd(const float* im, const float* x, const float* y, int N, int IH, int IW, int C, int OH, int OW,

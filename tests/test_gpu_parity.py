@@ -804,6 +804,44 @@ def test_empty_batch_is_a_no_op(mgw):
         mgw.transformer(torch.zeros(0, 8, 8, 3), torch.zeros(0, 5, 5, 2))          # still no CPU path
 
 
+def test_deploy_stream_state_device_head_and_graph_replay(mgw):
+    """StreamState(device_head=True): same histories and inputs as the host-head rings, and a frame (assemble + push) captured
+    ONCE in a CUDA graph replays correctly for every later frame"""
+    import deploy_ref
+    g = load_golden('deploy_stream')
+    h, w = g['first'].shape
+    st = mgw.StreamState(g['first'], device_head=True)
+    cur = torch.empty((h, w), device='cuda'); img_b = torch.empty((h, w), device='cuda'); blk_b = torch.empty((h, w), device='cuda')
+    in_x_buf = torch.empty((1, h, w, 13), device='cuda')
+    graph = None
+    side = torch.cuda.Stream()
+    for k in range(g['cur_frames'].shape[0]):
+        cur.copy_(dev(g['cur_frames'][k]))
+        # the stand-in network of the fixture needs in_x on the host; its last refine pass decides what is pushed
+        in_x = st.assemble(cur)
+        assert np.array_equal(in_x.cpu().numpy(), g['in_x'][k])
+        x_np = in_x.cpu().numpy()
+        for _ in range(int(g['refine'])):
+            img, black = deploy_ref.stream_fake_net(x_np, k)
+            x_np[..., -1] = (img.reshape(h, w) + black.reshape(h, w) * np.float32(-1))
+        img_b.copy_(dev(img).reshape(h, w)); blk_b.copy_(dev(black).reshape(h, w))
+        if k < 3:
+            st.push(img_b, blk_b)
+            if k == 2:                                   # capture "assemble into a static buffer + push" once
+                torch.cuda.synchronize()
+                graph = torch.cuda.CUDAGraph()
+                snap = (st.frames.clone(), st.masks.clone(), st.head_dev.clone())
+                with torch.cuda.graph(graph):
+                    st.assemble(cur, out=in_x_buf)
+                    st.push(img_b, blk_b)
+                st.frames.copy_(snap[0]); st.masks.copy_(snap[1]); st.head_dev.copy_(snap[2])      # capture does not run anything
+        else:
+            graph.replay()
+            assert np.array_equal(in_x_buf.cpu().numpy(), g['in_x'][k])
+    fr, mk = st.history()
+    assert np.array_equal(fr.cpu().numpy()[..., None], g['final_frames']) and np.array_equal(mk.cpu().numpy()[..., None], g['final_masks'])
+
+
 def test_errors_are_loud(mgw):
     with pytest.raises(RuntimeError):
         mgw.transformer(torch.zeros(1, 8, 8, 3), torch.zeros(1, 5, 5, 2))          # CPU tensors: no fallback

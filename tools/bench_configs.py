@@ -159,7 +159,7 @@ except Exception as e:      # noqa: BLE001
 # the whole per-frame deploy loop on the device (deploy_bundle.py:259-328 minus the network, whose output is a fixed mesh here):
 # H2D of the raw 1080p BGR frame -> cvt_img2train -> input assembly from the rings -> K1 + K2 on the gray frame -> ring push +
 # black accumulation -> cv2.resize of the colour frame -> warpRevBundle2 -> D2H of the stabilised 512x288 colour frame
-loop_p50 = loop_p99 = None
+loop_p50 = loop_p99 = loop_graph_p50 = loop_graph_p99 = None
 try:
     raw_h = torch.as_tensor(np.random.RandomState(9).randint(0, 256, (1080, 1920, 3)).astype(np.uint8)).pin_memory()
     raw_d = torch.empty((1080, 1920, 3), device=dev, dtype=torch.uint8)
@@ -184,6 +184,32 @@ try:
         for _ in range(500):
             t0 = time.perf_counter(); loop_frame(); lat.append((time.perf_counter() - t0) * 1e6)
     loop_p50, loop_p99 = float(np.percentile(lat, 50)), float(np.percentile(lat, 99))
+    # the same loop captured ONCE in a CUDA graph (ring head on the device, static buffers, the two PCIe copies inside it)
+    st_g = mgw.StreamState(gray_h[0, ..., 0], device_head=True)
+    in_x_g = torch.empty((1, hn, wn, 13), device=dev)
+    with torch.cuda.stream(s):
+        def graph_frame():
+            raw_d.copy_(raw_h, non_blocking=True)
+            cur = mgw.deploy.cvt_img2train(raw_d)
+            st_g.assemble(cur.reshape(hn, wn), out=in_x_g)
+            out, black, img = mgw.transformer(cur, th)
+            st_g.push(out.reshape(hn, wn), black.reshape(hn, wn))
+            crop.add(black)
+            small = mgw.deploy.cv2_resize(raw_d, (wn, hn))
+            dst = ops.remap_bundle_u8(small.reshape(1, hn, wn, 3), img)
+            out_hh.copy_(dst[0], non_blocking=True)
+        for _ in range(3):
+            graph_frame()
+        s.synchronize()
+        want_frame = out_hh.clone()
+        gl = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(gl, stream=s):
+            graph_frame()
+        latg = []
+        for _ in range(500):
+            t0 = time.perf_counter(); gl.replay(); s.synchronize(); latg.append((time.perf_counter() - t0) * 1e6)
+        assert torch.equal(out_hh, want_frame)
+    loop_graph_p50, loop_graph_p99 = float(np.percentile(latg, 50)), float(np.percentile(latg, 99))
 except Exception as e:      # noqa: BLE001
     loop_p50 = str(e)
 # the streaming state around it (deploy_bundle.py:259-274,319-328): input assembly from the history rings + push of the new frame
@@ -231,6 +257,7 @@ res['deploy_frame_288x512'] = {
     'us_p50_host_to_host_u8_frames': float(np.percentile(lat3, 50)), 'us_p99_host_to_host': float(np.percentile(lat3, 99)),
     'us_cpu_opencv_remap_only': cpu_us, 'cpu_threads': os.cpu_count(),
     'us_p50_whole_deploy_loop_1080p_bgr_in_288x512_bgr_out_host_to_host': loop_p50, 'us_p99_whole_deploy_loop': loop_p99,
+    'us_p50_whole_deploy_loop_one_cuda_graph': loop_graph_p50, 'us_p99_whole_deploy_loop_one_cuda_graph': loop_graph_p99,
     'us_device_cvt_img2train_1080p': dev_cvt, 'us_cpu_cv2_pil_cvt_img2train_1080p': cpu_cvt,
     'us_device_warp_rev_bundle': dev_wrb, 'us_cpu_opencv_warp_rev_bundle': cpu_wrb,
     'us_device_stream_state_assemble_plus_push': dev_state, 'us_cpu_numpy_stream_state': cpu_state_us,
