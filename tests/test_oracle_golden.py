@@ -234,6 +234,16 @@ def test_crop_golden_is_reference_output():
     ns = dict(np=np, math=math, height=ab.shape[0], width=ab.shape[1], all_black=ab)
     ref_loader.quiet(exec, ref_loader.deploy_crop_block(), ns)
     assert ns['ans'] == g['tie_ans'].tolist() and ns['max_s'] == int(g['tie_max_s'])
+    # and the restatement against the reference's loops on random masks (sparse and dense black, ragged sizes)
+    import deploy_ref
+    code = ref_loader.deploy_crop_block()
+    r = np.random.RandomState(17)
+    for k in range(40):
+        h, w = int(r.randint(12, 48)), int(r.randint(12, 64))
+        ab = (r.random_sample((h, w)) < r.choice([0.0, 0.01, 0.05, 0.3])).astype(np.int64) * r.randint(1, 5, (h, w))
+        ns = dict(np=np, math=math, height=h, width=w, all_black=ab)
+        ref_loader.quiet(exec, code, ns)
+        assert deploy_ref.crop_rect(ab) == ns['ans'], (k, h, w)
 
 
 def test_vertex_loss_oracle_matches_the_reference_functions():
@@ -341,3 +351,34 @@ def test_cv2_resize_oracle_matches_opencv():
         want = g[n + '_dst']
         assert np.array_equal(deploy_ref.resize_linear_u8(g[n + '_img'], want.shape[1], want.shape[0]), want), n
         assert int(g[n + '_optimized_differs']) == 0
+
+
+@pytest.mark.reference
+def test_deploy_oracles_against_the_reference_on_random_inputs():
+    """beyond the committed fixtures: the OpenCV / Pillow restatements against the reference's own functions (and the libraries
+    they call) on random frames, sizes and homographies -- only where /root/reference, cv2 and Pillow exist"""
+    cv2 = pytest.importorskip('cv2'); pytest.importorskip('PIL')
+    import deploy_ref
+    import ref_loader
+    r = np.random.RandomState(23)
+    cv2.setUseOptimized(False)
+    try:
+        for k in range(6):
+            H, W = int(r.randint(40, 200)), int(r.randint(40, 260))
+            h, w = int(r.randint(16, 120)), int(r.randint(16, 160))
+            img = r.randint(0, 256, (H, W, 3)).astype(np.uint8)
+            cr = float(r.choice([1.0, 0.9, 0.75]))
+            f = ref_loader.config_cvt_img2train(h, w)
+            want = f(img, cr) if cr != 1 else f(img)
+            assert np.array_equal(deploy_ref.cvt_img2train(img, h, w, 1 if cr == 1 else cr), want), ('cvt', H, W, h, w, cr)
+            assert np.array_equal(deploy_ref.resize_linear_u8(img, w, h), cv2.resize(img, (w, h))), ('resize', H, W, h, w)
+            gh, gw = int(r.randint(1, 5)), int(r.randint(1, 5))
+            Hs = (np.tile(np.eye(3, dtype=np.float32).reshape(1, 1, 9), (gh, gw, 1)) +
+                  0.1 * r.standard_normal((gh, gw, 9)).astype(np.float32) * np.array([1, 1, 1, 1, 1, 1, 0.5, 0.5, 0], np.float32)).astype(np.float32)
+            warp, _ = ref_loader.deploy_warp_rev_bundle(H, W, gh, gw)
+            assert np.array_equal(deploy_ref.warp_rev_bundle(img, Hs, gh, gw), warp(img, Hs)), ('warpRevBundle', H, W, gh, gw)
+            x_map = (np.linspace(-1, 1, W, dtype=np.float32)[None, :] + 0.05 * r.standard_normal((H, W)).astype(np.float32)).astype(np.float32)
+            y_map = (np.linspace(-1, 1, H, dtype=np.float32)[:, None] + 0.05 * r.standard_normal((H, W)).astype(np.float32)).astype(np.float32)
+            assert np.array_equal(deploy_ref.warp_rev_bundle2(img, x_map, y_map), ref_loader.deploy_warp_rev_bundle2(H, W)(img, x_map, y_map)), ('wrb2', H, W)
+    finally:
+        cv2.setUseOptimized(True)
