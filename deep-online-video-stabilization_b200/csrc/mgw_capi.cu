@@ -3,6 +3,7 @@
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #include "mgw_internal.h"
@@ -33,6 +34,12 @@ int check_launch(const char* what)
 }
 
 int impl_mode() { return g_impl.load(std::memory_order_relaxed); }
+
+bool pdl_enabled()
+{
+    static const bool on = [] { const char* e = getenv("MGW_PDL"); return !(e && e[0] == '0'); }();
+    return on;
+}
 
 static bool aligned(const void* p, size_t a) { return (reinterpret_cast<uintptr_t>(p) % a) == 0; }
 
@@ -156,7 +163,8 @@ int mgw_warp_fwd(const float* U, const float* Hs, int N, int H, int W, int C, in
 size_t mgw_warp_bwd_workspace_bytes(int N, int H, int W, int C, int gh, int gw)
 {
     const WarpShape s{N, H, W, C, H, W, gh, gw};
-    return tma_bwd_supported(s) ? tma_bwd_workspace_bytes(s) : 0;
+    const size_t a = tma_bwd_supported(s) ? tma_bwd_workspace_bytes(s) : 0, b = pipe_bwd_supported(s) ? pipe_bwd_workspace_bytes(s) : 0;
+    return a > b ? a : b;
 }
 
 // shared by mgw_warp_bwd and mgw_mesh_warp_bwd: produces dH partials; returns their layout
@@ -170,7 +178,16 @@ static int warp_bwd_core(const float* U, const float* Hs, const float* d_out, co
     const int mode = impl_mode();
     const bool tma_ok = mode != 1 && workspace && tma_bwd_supported(s) && aligned(U, 16) && (!dU || aligned(dU, 16)) &&
                         (!d_img || aligned(d_img, 8));
-    if (!tma_ok && mode >= 2)      // the backward has one TMA family (tiles); mode 3 only differs in the forward
+    // the persistent pipeline serves the calls that want dU (modes auto / pipe); dH-only calls and mode 2 take the tile kernels
+    const bool pipe_ok = mode != 1 && mode != 2 && dU && workspace && pipe_bwd_supported(s) && aligned(U, 16) && aligned(dU, 16) &&
+                         (!d_img || aligned(d_img, 8));
+    if (pipe_ok) {
+        int np = 0;
+        TRY(launch_warp_bwd_pipe(U, Hs, d_out, d_img, s, dU, (float*)workspace, &np, fl, st));
+        *parts = (const float*)workspace; *nparts = np; *part_stride = 8;
+        return MGW_OK;
+    }
+    if (!tma_ok && mode >= 2)
         return set_error(MGW_ERR_UNSUPPORTED, "TMA path required (mgw_set_impl(2|3)) but shape/alignment/workspace does not allow it");
     if (tma_ok) {
         int np = 0;
@@ -247,7 +264,7 @@ static int mesh_warp_bwd_impl(const float* U, const float* theta, const float* H
     void* tma_ws = mgw_warp_bwd_workspace_bytes(N, H, W, C, gh, gw) ? (void*)((char*)workspace + off) : nullptr;
     const float* parts; int np, ps;
     TRY(warp_bwd_core(U, Hs, d_out, d_img, s, dU, dHs_acc, tma_ws, &parts, &np, &ps, st, nullptr, nullptr, zero_dU));
-    return launch_solve_h_bwd(theta, Hs, parts, np, ps, N, gh, gw, dtheta, st);
+    return launch_solve_h_bwd(theta, Hs, parts, np, ps, N, gh, gw, dtheta, st, ps == 8);
 }
 
 int mgw_mesh_warp_bwd(const float* U, const float* theta, const float* Hs, const float* d_out, const float* d_img,
@@ -283,9 +300,10 @@ int mgw_mesh_warp_img_loss_fwd(const float* U, const float* theta, const float* 
 
 size_t mgw_mesh_warp_img_loss_bwd_workspace_bytes(int N, int H, int W, int C, int gh, int gw)
 {
-    const WarpShape s{N, H, W, C, H, W, gh, gw};
+    // worst case, whatever kernel family ends up serving the call: the generic family materialises d_out in the scratch part.
+    // (The size must not depend on anything that can change between this query and the call.)
     const size_t base = mgw_mesh_warp_bwd_workspace_bytes(N, H, W, C, gh, gw);
-    return align_up(base, 256) + (tma_bwd_supported(s) && impl_mode() != 1 ? 0 : sizeof(float) * (size_t)N * H * W * C);
+    return align_up(base, 256) + sizeof(float) * (size_t)N * H * W * C;
 }
 
 int mgw_mesh_warp_img_loss_bwd(const float* U, const float* theta, const float* Hs, const float* out, const float* y,
@@ -302,11 +320,11 @@ int mgw_mesh_warp_img_loss_bwd(const float* U, const float* theta, const float* 
     const size_t tma_bytes = mgw_warp_bwd_workspace_bytes(N, H, W, C, gh, gw);
     void* tma_ws = tma_bytes ? (void*)((char*)workspace + off) : nullptr;
     const size_t base = align_up(mgw_mesh_warp_bwd_workspace_bytes(N, H, W, C, gh, gw), 256);
-    float* scratch = (mgw_mesh_warp_img_loss_bwd_workspace_bytes(N, H, W, C, gh, gw) > base) ? (float*)((char*)workspace + base) : nullptr;
+    float* scratch = (float*)((char*)workspace + base);
     const FusedImgLoss fl{out, y, black, sums, upstream * 2.0f / batch, upstream_dev};
     const float* parts; int np, ps;
     TRY(warp_bwd_core(U, Hs, nullptr, d_img, s, dU, dHs_acc, tma_ws, &parts, &np, &ps, st, &fl, scratch));
-    return launch_solve_h_bwd(theta, Hs, parts, np, ps, N, gh, gw, dtheta, st);
+    return launch_solve_h_bwd(theta, Hs, parts, np, ps, N, gh, gw, dtheta, st, ps == 8);
 }
 
 int mgw_interp_fwd(const float* im, const float* x, const float* y, int N, int IH, int IW, int C, int OH, int OW,

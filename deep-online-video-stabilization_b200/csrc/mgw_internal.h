@@ -14,6 +14,21 @@ int check_launch(const char* what);          // counts the launch, maps cudaGetL
 void count_launches(int n);
 int impl_mode();                             // mgw_set_impl value
 
+// Launch with (pdl = true) the programmatic-stream-serialization attribute: the kernel may be scheduled while the previous
+// kernel of the stream is still running and synchronises with it through griddep_wait() (mgw_device.cuh).
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_ex(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, bool pdl, Args&&... args)
+{
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+bool pdl_enabled();                          // MGW_PDL=0 switches programmatic dependent launch off (tuning / debugging aid)
+
 struct WarpShape {
     int N, H, W, C;          // source image (and output, for the mesh op)
     int OH, OW;              // output size
@@ -26,7 +41,7 @@ int launch_vertices_bwd(const float* head, const float* d_pts2, const float* d_p
                         float do_crop_rate, float* d_head, cudaStream_t st);
 int launch_solve_h_fwd(const float* theta, int N, int gh, int gw, float* Hs, cudaStream_t st);
 int launch_solve_h_bwd(const float* theta, const float* Hs, const float* dHs_part, int nparts, int part_stride,
-                       int N, int gh, int gw, float* dtheta, cudaStream_t st);
+                       int N, int gh, int gw, float* dtheta, cudaStream_t st, bool after_own_warp_kernel = false);
 
 // mgw_warp_generic.cu : any shape, global gather / global atomics
 // normalize: Hs holds raw [N,9] homographies to be divided by H[8] (spatial_transformer.py:151-153)
@@ -80,6 +95,12 @@ int launch_warp_bwd_tma(const float* U, const float* Hs, const float* d_out, con
 // out + black + img)
 bool pipe_fwd_supported(const WarpShape& s);
 int launch_warp_fwd_pipe(const float* U, const float* Hs, const WarpShape& s, float* out, float* black, float* img, cudaStream_t st);
+
+// mgw_warp_bwd_pipe.cu : backward (dU + dH partials) as a persistent warp-specialised pipeline; needs dU != nullptr
+bool pipe_bwd_supported(const WarpShape& s);
+size_t pipe_bwd_workspace_bytes(const WarpShape& s);
+int launch_warp_bwd_pipe(const float* U, const float* Hs, const float* d_out, const float* d_img, const WarpShape& s,
+                         float* dU, float* dHs_part, int* nparts, const FusedImgLoss* fl, cudaStream_t st);
 
 // mgw_deploy.cu : deploy-side colour-frame warp (deploy_bundle.py:136-146)
 size_t remap_bundle_workspace_bytes(int N, int H, int W);

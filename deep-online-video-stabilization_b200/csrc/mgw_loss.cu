@@ -201,13 +201,22 @@ static void launch_temp_loss(int C, dim3 grid, cudaStream_t st, const float* out
 }
 
 // ---------------------------------------------------------------- launchers
-// blocks per sample of the grid-stride reductions: about 8 resident blocks per SM over the whole batch (148 SMs), so that a
+// blocks per sample of the grid-stride reductions: about 8 resident blocks per SM over the whole batch (cudaDevAttrMultiProcessorCount SMs), so that a
 // block amortises its two block-wide reductions and its two atomics over many pixels (one pixel per thread made these
 // kernels latency-bound: 58 us for 132 MB)
+static int sm_count()
+{
+    static int n[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (!n[dev & 63]) cudaDeviceGetAttribute(&n[dev & 63], cudaDevAttrMultiProcessorCount, dev);
+    return n[dev & 63] > 0 ? n[dev & 63] : 148;
+}
+
 static unsigned blocks_for(int HW, int N, int resident_per_sm = 8)
 {
     const unsigned full = (unsigned)((HW + 255) / 256);
-    unsigned per = (unsigned)((148 * resident_per_sm + N - 1) / N);
+    unsigned per = (unsigned)((sm_count() * resident_per_sm + N - 1) / N);
     if (per < 1) per = 1;
     return per < full ? per : full;
 }

@@ -226,6 +226,7 @@ solve_h_fwd_kernel(const float* __restrict__ theta, int N, int gh, int gw, float
 {
     __shared__ float sLU[kCellsPerBlock][64];
     __shared__ float sINV[kCellsPerBlock][64];
+    griddep_launch_dependents();                       // the warp kernel that follows may set itself up while this one runs
     const int slot = threadIdx.x >> 3, g = threadIdx.x & 7;
     const int ncell = N * gh * gw;
     int cell = blockIdx.x * kCellsPerBlock + slot;
@@ -282,14 +283,17 @@ __global__ void solve_h_bwd_kernel(const float* __restrict__ theta, const float*
 #pragma unroll
             for (int c = 0; c < 8; ++c) Mt[c][r] = row[c];
         }
+        lu8<double>(Mt, piv);
+        // the factorisation needs theta only: under a programmatic dependent launch it runs while the backward warp kernel is
+        // still busy; the tile partials are read after that kernel has completed
+        griddep_wait();
 #pragma unroll
         for (int r = 0; r < 8; ++r) rhs[r] = 0;
         for (int p = 0; p < nparts; ++p) {
             const float* src = dHs_part + (cell * nparts + p) * part_stride;
 #pragma unroll
-            for (int r = 0; r < 8; ++r) rhs[r] += (double)__ldg(src + r);
+            for (int r = 0; r < 8; ++r) rhs[r] += (double)__ldcg(src + r);
         }
-        lu8<double>(Mt, piv);
         getrs8<double>(Mt, piv, rhs);                  // rhs -> lambda
         const double h6 = Hs[cell * 9 + 6], h7 = Hs[cell * 9 + 7];
 #pragma unroll
@@ -340,14 +344,18 @@ int launch_solve_h_fwd(const float* theta, int N, int gh, int gw, float* Hs, cud
 }
 
 int launch_solve_h_bwd(const float* theta, const float* Hs, const float* dHs_part, int nparts, int part_stride,
-                       int N, int gh, int gw, float* dtheta, cudaStream_t st)
+                       int N, int gh, int gw, float* dtheta, cudaStream_t st, bool after_own_warp_kernel)
 {
     const int ncell_s = gh * gw;
     int threads = ((ncell_s > (gh + 1) * (gw + 1) * 2 ? ncell_s : (gh + 1) * (gw + 1) * 2) + 31) / 32 * 32;
     if (threads > 128) threads = 128;
     const size_t smem = (size_t)ncell_s * 8 * sizeof(double);
     if (smem > 48 * 1024) return set_error(MGW_ERR_UNSUPPORTED, "solve_h_bwd: grid too large (gh*gw > 768)");
-    solve_h_bwd_kernel<<<N, threads, smem, st>>>(theta, Hs, dHs_part, nparts, part_stride, N, gh, gw, dtheta);
+    // after_own_warp_kernel: the previous kernel of the stream is this library's backward warp kernel, which read Hs itself and
+    // releases its dependents at once: launch programmatically, the factorisation overlaps it
+    const cudaError_t e = launch_ex(solve_h_bwd_kernel, dim3(N), dim3(threads), smem, st, after_own_warp_kernel && pdl_enabled(),
+                                    theta, Hs, dHs_part, nparts, part_stride, N, gh, gw, dtheta);
+    if (e != cudaSuccess) { count_launches(1); return set_error(MGW_ERR_CUDA, "solve_h_bwd: %s", cudaGetErrorString(e)); }
     return check_launch("solve_h_bwd");
 }
 

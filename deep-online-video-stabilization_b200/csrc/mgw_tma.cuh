@@ -54,6 +54,21 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
         "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
 }
 
+// the same with a suspend-time hint (ns): a waiter that expects to wait long (the producer on `empty`) sleeps in hardware
+// instead of spinning through issue slots its SM sub-partition's other warps could use
+__device__ __forceinline__ void mbar_wait_hint(uint64_t* bar, uint32_t parity, uint32_t ns)
+{
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "MGW_WAITH_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
+        "@p bra MGW_DONEH_%=;\n\t"
+        "bra MGW_WAITH_%=;\n\t"
+        "MGW_DONEH_%=:\n\t"
+        "}" ::"r"(smem_u32(bar)), "r"(parity), "r"(ns) : "memory");
+}
+
 __device__ __forceinline__ void load_3d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2)
 {
     asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"

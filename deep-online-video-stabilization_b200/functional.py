@@ -21,11 +21,14 @@ class MeshWarp(torch.autograd.Function):
         out, black, img, Hs = ops.mesh_warp_fwd(U, theta)
         ctx.save_for_backward(U, theta, Hs)
         ctx.mark_non_differentiable(black, Hs)
+        ctx.set_materialize_grads(False)          # an unused output arrives as None, not as a tensor of zeros to stream through the kernel
         return out, black, img, Hs
 
     @staticmethod
     def backward(ctx, d_out, _d_black, d_img, _d_Hs):
         U, theta, Hs = ctx.saved_tensors
+        if d_out is None and d_img is None:
+            return (torch.zeros_like(U) if ctx.needs_input_grad[0] else None), torch.zeros_like(theta)
         if d_out is None:
             d_out = torch.zeros_like(U)
         dU, dtheta = ops.mesh_warp_bwd(U, theta, Hs, d_out.contiguous(), None if d_img is None else d_img.contiguous(),
@@ -44,6 +47,7 @@ class MeshWarpImgLoss(torch.autograd.Function):
         ctx.save_for_backward(U, theta, Hs, out, y, black, sums)
         ctx.batch = batch
         ctx.mark_non_differentiable(black)
+        ctx.set_materialize_grads(False)          # g_out is None unless something else consumes `output`: the fused backward's condition
         loss = (sums[:, 0] / (sums[:, 1] + 1e-8)).sum() / batch
         return loss, out, black, img
 
@@ -52,6 +56,8 @@ class MeshWarpImgLoss(torch.autograd.Function):
         U, theta, Hs, out, y, black, sums = ctx.saved_tensors
         g_img = None if g_img is None else g_img.contiguous()
         up = 0.0 if g_loss is None else g_loss                   # device scalar: read by the kernel, no host sync
+        if g_loss is None and g_out is None and g_img is None:
+            return (torch.zeros_like(U) if ctx.needs_input_grad[0] else None), torch.zeros_like(theta), None, None
         if g_out is None:
             dU, dtheta = ops.mesh_warp_img_loss_bwd(U, theta, Hs, out, y, black, sums, up, ctx.batch, g_img,
                                                     want_dU=ctx.needs_input_grad[0])

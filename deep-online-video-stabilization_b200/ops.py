@@ -18,6 +18,20 @@ def _chk(t, name, dtype=torch.float32):
     return t if t.is_contiguous() else t.contiguous()
 
 
+def _chk_out(t, name, dtype=torch.float32):
+    """a tensor the kernel WRITES in place: a silent .contiguous() copy would swallow the update, so anything but a
+    contiguous CUDA tensor of the right dtype is an error"""
+    if not isinstance(t, torch.Tensor):
+        raise TypeError('%s must be a torch.Tensor' % name)
+    if not t.is_cuda:
+        raise RuntimeError('%s must live on a CUDA device: this library has no CPU path' % name)
+    if t.dtype != dtype:
+        raise TypeError('%s must be %s (got %s)' % (name, dtype, t.dtype))
+    if not t.is_contiguous():
+        raise ValueError('%s is written in place and must be contiguous' % name)
+    return t
+
+
 def _p(t):
     return None if t is None else t.data_ptr()
 
@@ -103,7 +117,7 @@ def _workspace(nbytes, dev):
 
 def _acc_target(U, accumulate_into):
     """dU buffer of the accumulate variants: the caller's tensor, added to in place (never zero-filled by the library)."""
-    dU = _chk(accumulate_into, 'accumulate_into')
+    dU = _chk_out(accumulate_into, 'accumulate_into')
     if dU.shape != U.shape or dU.device != U.device:
         raise ValueError('accumulate_into must have the shape and device of U')
     return dU
@@ -354,11 +368,13 @@ def stream_push(frames, masks, slot, img, black, refeed_into=None):
     """deploy_bundle.py:292-295,319-328: frame = img + black*(-1) -> frames[slot], black -> masks[slot]; refeed_into: an
     assembled in_x [1,H,W,nch] whose LAST channel receives the frame (the refine loop).  frames/masks None: re-feed only."""
     img, black = _chk(img, 'img'), _chk(black, 'black')
+    frames = None if frames is None else _chk_out(frames, 'frames')
+    masks = None if masks is None else _chk_out(masks, 'masks')
     ref = frames if frames is not None else refeed_into
     depth, h, w = (frames.shape if frames is not None else (1, refeed_into.shape[1], refeed_into.shape[2]))
     fo, stride = None, 1
     if refeed_into is not None:
-        refeed_into = _chk(refeed_into, 'refeed_into')
+        refeed_into = _chk_out(refeed_into, 'refeed_into')
         stride = refeed_into.shape[-1]
         fo = refeed_into.data_ptr() + 4 * (stride - 1)
     with torch.cuda.device(ref.device):
@@ -367,7 +383,7 @@ def stream_push(frames, masks, slot, img, black, refeed_into=None):
 
 def black_accumulate(all_black, black):
     """deploy_bundle.py:291: all_black = all_black + np.round(black).astype(np.int64), in place on the device (int32 counts)."""
-    black, all_black = _chk(black, 'black'), _chk(all_black, 'all_black', torch.int32)
+    black, all_black = _chk(black, 'black'), _chk_out(all_black, 'all_black', torch.int32)
     if black.numel() != all_black.numel():
         raise ValueError('black has %d pixels, all_black %d' % (black.numel(), all_black.numel()))
     with torch.cuda.device(black.device):
@@ -478,8 +494,8 @@ def stream_assemble_dev(frames, masks, head_dev, taps, cur, use_masks=True, out=
 
 def stream_push_dev(frames, masks, head_dev, img, black):
     """stream_push into the slot after the device-resident head, then head = (head + 1) % depth on the device."""
-    frames, img, black, head_dev = _chk(frames, 'frames'), _chk(img, 'img'), _chk(black, 'black'), _chk(head_dev, 'head_dev', torch.int32)
-    masks = None if masks is None else _chk(masks, 'masks')
+    frames, img, black, head_dev = _chk_out(frames, 'frames'), _chk(img, 'img'), _chk(black, 'black'), _chk_out(head_dev, 'head_dev', torch.int32)
+    masks = None if masks is None else _chk_out(masks, 'masks')
     depth, h, w = frames.shape
     with torch.cuda.device(frames.device):
         check(lib.mgw_stream_push_dev(_p(frames), _p(masks), depth, _p(head_dev), _p(img), _p(black), h, w, _st()), 'mgw_stream_push_dev')

@@ -47,6 +47,7 @@ class MeshHeadGradReducer:
     current one and starts the all-reduce of that slot's buffer there; wait() joins it back (call it right before the
     optimizer step that consumes the buffer).  With nbuf > 1 a step can compute its gradient into one slot while the previous
     step's slot is still being reduced -- the form that can be captured in a CUDA graph (fork and join inside one capture).
+    wait() must come before anything rewrites bufs[slot] (the reduction owns the slot until then).
     """
 
     def __init__(self, n_features, n_out, device, nbuf=1):
@@ -84,6 +85,10 @@ class MeshHeadGradReducer:
         self.side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(self.side):
             if features is not None:
+                # the side stream reads tensors allocated on the caller's stream: tell the caching allocator, or a backward
+                # temporary dropped right after launch() could be handed out again while the GEMM still reads it
+                features.record_stream(self.side)
+                dtheta.record_stream(self.side)
                 self.head_grad(features, dtheta, slot)
             if multi:
                 dist.all_reduce(self.bufs[slot], op=dist.ReduceOp.SUM)

@@ -182,10 +182,19 @@ def test_pipe_path_is_taken_and_matches_generic(mgw, name):
     Ud, Hd = dev(U), dev(g['ref_Hs'])
     mgw.set_impl('generic')
     o_g, b_g, i_g, _ = mgw.ops.warp_fwd(Ud, Hd)
+    dU_g, dH_g = mgw.ops.warp_bwd(Ud, Hd, dev(d_out), dev(d_img))
     mgw.set_impl('pipe')
     o_t, b_t, i_t, _ = mgw.ops.warp_fwd(Ud, Hd)
     assert torch.equal(o_g.view(torch.int32), o_t.view(torch.int32)) and torch.equal(b_g, b_t)
     assert torch.equal(i_g.view(torch.int32), i_t.view(torch.int32))
+    # the backward pipeline (fixed-point shared accumulation, 16-byte reductions) vs fp32 atomics (generic)
+    dU_t, dH_t = mgw.ops.warp_bwd(Ud, Hd, dev(d_out), dev(d_img))
+    s0 = 1 if 'fold' in name else 0      # a folded cell scatters 1e5-weighted terms: order-dependent garbage in any implementation
+    assert relmax(dU_t[s0:].cpu().numpy(), dU_g[s0:].cpu().numpy()) < 2e-5
+    if 'fold' not in name:
+        assert relmax(dH_t.cpu().numpy(), dH_g.cpu().numpy()) < 5e-5
+    dU_r, dH_r = mgw.ops.warp_bwd(Ud, Hd, dev(d_out), dev(d_img))               # run to run: dH partials are deterministic
+    assert torch.equal(dH_r, dH_t)
     with pytest.raises(mgw.MgwError):                                          # the pipeline serves the full call only
         mgw.ops.warp_fwd(Ud, Hd, want_black=False, want_img=False)
     o_r = mgw.ops.warp_fwd(Ud, Hd)[0]                                          # run to run

@@ -45,6 +45,10 @@ timeit('solve_h_fwd', lambda: ops.solve_h_fwd(th))
 timeit('solve_h_bwd', lambda: ops.solve_h_bwd(th, Hs, dHs))
 timeit('mesh fwd (K1+K2)', lambda: check(lib.mgw_mesh_warp_fwd(P(U), P(th), n, H, W, C, 4, 4, P(Hs), P(out), P(black), P(img), st), 'mf'))
 timeit('mesh bwd (memsets+K3+K4)', lambda: check(lib.mgw_mesh_warp_bwd(P(U), P(th), P(Hs), P(g), P(gi), n, H, W, C, 4, 4, P(dU), P(dth), P(ws), st), 'mb'))
-mgw.set_impl('generic')
-timeit('generic fwd', lambda: fw(out, black, img))
-timeit('generic bwd', lambda: bw(dU, gi))
+mgw.set_impl('tma')
+timeit('tile (one TMA tile per CTA) fwd', lambda: fw(out, black, img))
+timeit('tile bwd: dU + dHs, with d_img', lambda: bw(dU, gi))
+if os.environ.get('ABLATE_GENERIC'):
+    mgw.set_impl('generic')
+    timeit('generic fwd', lambda: fw(out, black, img))
+    timeit('generic bwd', lambda: bw(dU, gi))
