@@ -6,7 +6,11 @@
 
 A step = one forward + backward of spatial_transformer3.transformer over one batch of synthetic frames at
 BASELINE.json configs[1]: 32 x 288 x 512 x 3 fp32 per GPU, 4x4 mesh (weak scaling: every rank gets its own 32).
-Rank 0 prints ONE JSON line.  See DESIGN.md "Measurement" for how every field is obtained.
+Rank 0 prints ONE JSON line.  Besides the contract's fields the line carries `sustained` (>= 1 s of graph replay of the same
+step with its own clock record), `configs` (the other BASELINE.json configurations: #1 single frame, #3 the warp stage inside
+a StabNet-shaped forward, #4 1080p stream latency with uint8 frames over PCIe, #5 the 256-clip data-parallel step with the
+all-reduce overlapped and synchronous) and `e2e_u8_fused` (a second end-to-end leg: uint8 frames over PCIe, loss fused onto the
+warp).  See DESIGN.md "Measurement" for how every field is obtained.
 """
 import argparse
 import json
@@ -59,6 +63,7 @@ class ClockSampler:
             threading.Thread(target=self._pump, daemon=True).start()
         except Exception:      # noqa: BLE001
             self.proc = None
+        return self
 
     def _pump(self):
         for ln in self.proc.stdout:
@@ -69,20 +74,20 @@ class ClockSampler:
             return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
         time.sleep(0.15)
         self.proc.terminate()
-        sm, mx, reasons = [], [], set()
+        sm, mx, pw, reasons = [], [], [], set()
         for ln in self.lines:
             f = [x.strip() for x in ln.split(',')]
             if len(f) < 9:
                 continue
             try:
-                sm.append(float(f[1])); mx.append(float(f[2]))
+                sm.append(float(f[1])); mx.append(float(f[2])); pw.append(float(f[3]))
             except ValueError:
                 continue
             for name, v in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), f[5:9]):
                 if v.lower().startswith('active'):
                     reasons.add(name)
         return {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': max(mx) if mx else None,
-                'samples': len(sm), 'reasons': sorted(reasons)}
+                'power_w_max': max(pw) if pw else None, 'samples': len(sm), 'reasons': sorted(reasons)}
 
 
 def cpu_port_step(inp, n):
@@ -116,11 +121,29 @@ def run_reference(args):
         'impl': 'reference', 'metric': METRIC, 'value': val, 'unit': 'Mpix/s', 'n_gpus': args.gpus, 'steps': steps,
         'warmup': args.warmup, 'ms_per_step': 1e3 * t / steps, 'higher_is_better': True, 'scaling': 'weak',
         'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-        'config': {'workload': 'configs[1]: %dx%dx%dx%d frames, %dx%d mesh warp fwd+bwd (bounded sample: %d frames/step)' % (32, H, W, C, GH, GW, ns)},
+        'config': {'workload': 'configs[1]: %d x %dx%dx%d fp32 frames per GPU, %dx%d mesh warp forward+backward (dU + dtheta)' % (32, H, W, C, GH, GW),
+                   'sample': '%d of the 32 frames per step' % ns},
         'cpu_baseline': {'value': val, 'unit': 'Mpix/s', 'cores': torch.get_num_threads(), 'kind': 'port', 'sample': sample},
         'e2e': {'value': val, 'unit': 'Mpix/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'note': 'oracle/mesh_warp_ref.py (torch-CPU restatement of the reference graph); TensorFlow is not installable here',
     }))
+
+
+def pin_to_gpu_cores(local):
+    """run this rank on the host cores next to its GPU (NUMA-local staging buffers); returns the cpu count or None."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(local)
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+        cpus = [64 * i + b for i, wd in enumerate(words) for b in range(64) if (wd >> b) & 1]
+        cpus = [c for c in cpus if c in os.sched_getaffinity(0)]
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return len(cpus)
+    except Exception:      # noqa: BLE001
+        pass
+    return None
 
 
 def main():
@@ -132,8 +155,10 @@ def main():
     ap.add_argument('--batch', type=int, default=32, help='frames per GPU')
     ap.add_argument('--cpu-sample', type=int, default=32, help='frames per CPU-baseline step (of the 32-frame batch)')
     ap.add_argument('--no-cpu-baseline', action='store_true', help='skip the CPU leg (profiling runs)')
+    ap.add_argument('--no-configs', action='store_true', help='skip the sub-records of the other BASELINE configs and the sustained leg')
     ap.add_argument('--kernel-impl', default='auto', choices=['auto', 'generic', 'tma', 'pipe'])
     ap.add_argument('--no-graph', action='store_true', help='launch the step eagerly instead of replaying CUDA graphs')
+    ap.add_argument('--no-l2-keep', action='store_true', help='zero-fill dU without the L2 evict_last policy')
     args = ap.parse_args()
     if args.impl == 'reference':
         return run_reference(args)
@@ -144,11 +169,13 @@ def main():
     assert torch.cuda.is_available(), 'bench.py needs a CUDA device: the product has no CPU path'
     rank, world, local = mgw.parallel.init_from_env()
     assert world == args.gpus or world == 1, 'launch with torchrun --nproc-per-node %d' % args.gpus
+    ncores = pin_to_gpu_cores(local)
     dev = torch.device('cuda', local)
     torch.cuda.set_device(dev)
     mgw.set_impl(args.kernel_impl)
     n, K, Wm = args.batch, args.steps, max(args.warmup, 3)
     P = n * H * W
+    keep = not args.no_l2_keep
 
     # --- inputs: 3 rotating sets so that no step finds its inputs in L2 (each set is 151 MB, L2 is 126 MB)
     base = synth_inputs(n, seed=rank)
@@ -159,61 +186,73 @@ def main():
     feats = torch.randn(n, 512, device=dev)
     reducer = mgw.parallel.MeshHeadGradReducer(512, 2 * (GH + 1) * (GW + 1), dev, nbuf=R)
 
-    # dU of the step: zero-filled on a side stream while the forward runs, then accumulated into (mgw_mesh_warp_bwd_acc).
-    # The zero-fill is inside the timed step; it just does not sit on the critical path between forward and backward.
-    dU_buf = torch.empty_like(sets[0]['U'])
-    dth_slots = [torch.zeros_like(sets[0]['theta']) for _ in range(R)]
-    side = torch.cuda.Stream(device=dev)
+    def make_step(sets, feats, reducer, sync_reduce=False):
+        """the step over rotating input sets: K1, K2 (PDL), zero-fill of dU on a side branch, K3, K4 (PDL); with more than one
+        rank the head gradient + all-reduce of the PREVIOUS step (overlapped form) or of THIS step (synchronous form)."""
+        nset = len(sets)
+        dU_buf = torch.empty_like(sets[0]['U'])
+        dth_slots = [torch.zeros_like(sets[0]['theta']) for _ in range(nset)]
+        side = torch.cuda.Stream(device=dev)
 
-    def step_eager(i):
-        s = sets[i % R]
-        cur = torch.cuda.current_stream()
-        side.wait_stream(cur)
-        with torch.cuda.stream(side):
-            dU_buf.zero_()
-        out, black, img, Hs = ops.mesh_warp_fwd(s['U'], s['theta'])
-        if world > 1:
-            # head gradient (features^T . dtheta) and all-reduce of the PREVIOUS step on a high-priority side stream, forked
-            # AFTER the forward: the persistent forward kernel owns every SM with a static tile schedule (a CTA displaced by
-            # the NCCL kernel would finish late), the backward's 3072 one-tile CTAs are placed by the hardware scheduler and
-            # absorb it
-            reducer.launch(slot=(i - 1) % R, features=feats, dtheta=dth_slots[(i - 1) % R])
-        cur.wait_stream(side)
-        dU, dtheta = ops.mesh_warp_bwd(s['U'], s['theta'], Hs, s['d_out'], s['d_img'], accumulate_into=dU_buf,
-                                       dtheta_out=dth_slots[i % R])
-        if world > 1:
-            reducer.wait()                          # join: fork and join both lie inside the step (CUDA-graph capturable)
-        return dtheta
-
-    # The step is launch-bound on the host once NCCL is in it (a dozen launches for ~160 us of GPU work): capture one
-    # CUDA graph per rotating input set and replay.  Same kernels, same work; falls back to eager launches if capture
-    # is not possible.
-    graphs = None
-    if not args.no_graph:
-        try:
-            for i in range(R):
-                step_eager(i)
+        def step_eager(i):
+            s = sets[i % nset]
+            cur = torch.cuda.current_stream()
+            fill_mode = os.environ.get('BENCH_FILL', 'side')       # tuning aid: side | none (wrong dU) | serial | after_fwd
+            if fill_mode == 'serial':
+                ops.fill_zero(dU_buf, keep_in_l2=keep)
+            side.wait_stream(cur)
+            with torch.cuda.stream(side):
+                if fill_mode == 'side':
+                  # dU of the step: zero-filled by the library's own kernel on a side branch while the forward runs (evict_last: the
+                # lines are still in L2 when the backward's reductions arrive), then accumulated into (mgw_mesh_warp_bwd_acc).
+                # The fill is inside the timed step; it just does not sit on the critical path between forward and backward.
+                  ops.fill_zero(dU_buf, keep_in_l2=keep)
+            out, black, img, Hs = ops.mesh_warp_fwd(s['U'], s['theta'])
+            if fill_mode == 'after_fwd':
+                ops.fill_zero(dU_buf, keep_in_l2=keep)
+            if world > 1 and not sync_reduce:
+                # head gradient (features^T . dtheta) and all-reduce of the PREVIOUS step on a high-priority side stream, forked
+                # AFTER the forward: the persistent forward kernel owns every SM with a static tile schedule (a CTA displaced by
+                # the NCCL kernel would finish late)
+                reducer.launch(slot=(i - 1) % nset, features=feats, dtheta=dth_slots[(i - 1) % nset])
+            cur.wait_stream(side)
+            dU, dtheta = ops.mesh_warp_bwd(s['U'], s['theta'], Hs, s['d_out'], s['d_img'], accumulate_into=dU_buf,
+                                           dtheta_out=dth_slots[i % nset])
+            if world > 1 and sync_reduce:
+                reducer.launch(slot=i % nset, features=feats, dtheta=dth_slots[i % nset])
             if world > 1:
-                reducer.wait()
-            torch.cuda.synchronize()
-            graphs = []
-            for i in range(R):
-                gph = torch.cuda.CUDAGraph()
-                # thread_local: the NCCL watchdog thread polls CUDA events while we capture
-                with torch.cuda.graph(gph, capture_error_mode='thread_local'):
-                    step_eager(i)
-                graphs.append(gph)
-            torch.cuda.synchronize()
-        except Exception as e:      # noqa: BLE001
-            sys.stderr.write('CUDA graph capture failed (%s); running eager\n' % e)
-            graphs = None
-            torch.cuda.synchronize()
+                reducer.wait()                          # join: fork and join both lie inside the step (CUDA-graph capturable)
+            return dtheta
 
-    def step(i):
-        if graphs is not None:
-            graphs[i % R].replay()
-        else:
-            step_eager(i)
+        graphs = None
+        if not args.no_graph:
+            # The step is launch-bound on the host once NCCL is in it (a dozen launches for ~100 us of GPU work): capture one
+            # CUDA graph per rotating input set and replay.  Same kernels, same work; eager launches if capture is not possible.
+            try:
+                for i in range(nset):
+                    step_eager(i)
+                if world > 1:
+                    reducer.wait()
+                torch.cuda.synchronize()
+                graphs = []
+                for i in range(nset):
+                    gph = torch.cuda.CUDAGraph()
+                    # thread_local: the NCCL watchdog thread polls CUDA events while we capture
+                    with torch.cuda.graph(gph, capture_error_mode='thread_local'):
+                        step_eager(i)
+                    graphs.append(gph)
+                torch.cuda.synchronize()
+            except Exception as e:      # noqa: BLE001
+                sys.stderr.write('CUDA graph capture failed (%s); running eager\n' % e)
+                graphs = None
+                torch.cuda.synchronize()
+
+        def step(i):
+            if graphs is not None:
+                graphs[i % nset].replay()
+            else:
+                step_eager(i)
+        return step, step_eager, graphs, dU_buf
 
     def timed(fn, steps, warm, before_stop=None):
         for i in range(warm):
@@ -238,6 +277,7 @@ def main():
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms.item())
 
+    step, step_eager, graphs, dU_buf = make_step(sets, feats, reducer)
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
@@ -251,61 +291,112 @@ def main():
     launches_timed = launches_per_step * K
     clocks = sampler.stop() if rank == 0 else None
 
+    # --- the same step sustained: >= 1 s of replay (the K-step figure above lasts a few milliseconds)
+    sustained = None
+    if not args.no_configs:
+        ks = max(K, int(1.2e3 / max(ms_total / K, 1e-3)))
+        sm2 = ClockSampler(local).start() if rank == 0 else None
+        if rank == 0:
+            time.sleep(0.2)
+        ms_s = timed(step, ks, 3)
+        sustained = {'ms_per_step': ms_s / ks, 'steps': ks, 'seconds': ms_s * 1e-3, 'value': P * world * ks / (ms_s * 1e-3) / 1e6,
+                     'unit': 'Mpix/s', 'clocks': sm2.stop() if rank == 0 else None}
+
     # --- per-kernel timings (same rotation, CUDA events around the single C-ABI call)
     Hs_sets = [ops.solve_h_fwd(s['theta']) for s in sets]
     ms_fwd = timed(lambda i: ops.warp_fwd(sets[i % R]['U'], Hs_sets[i % R]), K, Wm)
-    ms_bwd = timed(lambda i: ops.warp_bwd(sets[i % R]['U'], Hs_sets[i % R], sets[i % R]['d_out'], sets[i % R]['d_img'], accumulate_into=dU_buf), K, Wm)
+
+    def bwd_call(i):
+        ops.fill_zero(dU_buf, keep_in_l2=keep)
+        ops.warp_bwd(sets[i % R]['U'], Hs_sets[i % R], sets[i % R]['d_out'], sets[i % R]['d_img'], accumulate_into=dU_buf)
+    ms_bwd_fill = timed(bwd_call, K, Wm)
+    ms_fill = timed(lambda i: ops.fill_zero(dU_buf, keep_in_l2=keep), K, Wm)
+    ms_bwd = ms_bwd_fill - ms_fill
     ms_fwd_full = timed(lambda i: ops.mesh_warp_fwd(sets[i % R]['U'], sets[i % R]['theta']), K, Wm)
 
     # --- end to end through the public API with HOST (pinned) buffers: H2D of the step's inputs and D2H of its result
     # Two staging sets and a copy stream: the H2D of step i+1 runs under the kernels of step i (the step is PCIe-bound:
     # 151 MB per step); every step still copies ITS inputs from pinned host memory and returns ITS dtheta to the host, and
     # the host waits for the result of step i-1 before it enqueues step i+1's copy (bounded run-ahead, as a training loop has).
-    host = {k: torch.tensor(v).pin_memory() for k, v in base.items()}
-    stages = [{k: torch.empty_like(v, device=dev) for k, v in host.items()} for _ in range(2)]
-    res_host = [torch.empty((n, GH + 1, GW + 1, 2)).pin_memory() for _ in range(2)]
-    h2d = sum(v.numel() * 4 for v in host.values())
-    d2h = res_host[0].numel() * 4
-    copy_stream = torch.cuda.Stream(device=dev)
-    ev_copied = [torch.cuda.Event() for _ in range(2)]
-    ev_free = [torch.cuda.Event() for _ in range(2)]
-    ev_res = [torch.cuda.Event() for _ in range(2)]
-    e2e_state = {'n': 0}
+    def e2e_leg(host, compute, res_shape):
+        stages = [{k: torch.empty_like(v, device=dev) for k, v in host.items()} for _ in range(2)]
+        res_host = [torch.empty(res_shape).pin_memory() for _ in range(2)]
+        copy_stream = torch.cuda.Stream(device=dev)
+        ev_copied = [torch.cuda.Event() for _ in range(2)]
+        ev_free = [torch.cuda.Event() for _ in range(2)]
+        ev_res = [torch.cuda.Event() for _ in range(2)]
+        state = {'n': 0}
 
-    def issue_h2d(j):
-        b = j % 2
-        with torch.cuda.stream(copy_stream):
-            copy_stream.wait_event(ev_free[b])              # the step that last used this staging set has finished
-            for k in host:
-                stages[b][k].copy_(host[k], non_blocking=True)
-            ev_copied[b].record(copy_stream)
+        def issue_h2d(j):
+            b = j % 2
+            with torch.cuda.stream(copy_stream):
+                copy_stream.wait_event(ev_free[b])              # the step that last used this staging set has finished
+                for k in host:
+                    stages[b][k].copy_(host[k], non_blocking=True)
+                ev_copied[b].record(copy_stream)
 
-    def e2e_step(i):
-        j = e2e_state['n']
-        b = j % 2
-        cur = torch.cuda.current_stream()
-        if j == 0:
-            for e in ev_free:
-                e.record(cur)
-            issue_h2d(0)
-        issue_h2d(j + 1)                                    # next step's inputs travel while this step computes
-        cur.wait_event(ev_copied[b])
-        st = stages[b]
+        def e2e_step(i):
+            j = state['n']
+            b = j % 2
+            cur = torch.cuda.current_stream()
+            if j == 0:
+                for e in ev_free:
+                    e.record(cur)
+                issue_h2d(0)
+            issue_h2d(j + 1)                                    # next step's inputs travel while this step computes
+            cur.wait_event(ev_copied[b])
+            res = compute(stages[b])
+            res_host[b].copy_(res, non_blocking=True)
+            ev_res[b].record(cur)
+            ev_free[b].record(cur)
+            if j > 0:
+                ev_res[1 - b].synchronize()                     # the caller reads the previous step's result on the host
+            state['n'] = j + 1
+
+        Ke = max(3, min(K, 20))
+        # the copy issued ahead by the last step is waited for inside the timed region: K steps pay for K copies
+        ms = timed(e2e_step, Ke, 3, before_stop=lambda: torch.cuda.current_stream().wait_stream(copy_stream))
+        return ms / Ke, Ke, sum(v.numel() * v.element_size() for v in host.values()), res_host[0].numel() * 4
+
+    def compute_main(st):
         Ut, th = st['U'].requires_grad_(True), st['theta'].requires_grad_(True)
         out, black, img = mgw.transformer(Ut, th)
         torch.autograd.backward([out, img], [st['d_out'], st['d_img']])
-        res_host[b].copy_(th.grad, non_blocking=True)
-        ev_res[b].record(cur)
-        ev_free[b].record(cur)
+        g = th.grad
         Ut.grad = None; th.grad = None
         Ut.requires_grad_(False); th.requires_grad_(False)
-        if j > 0:
-            ev_res[1 - b].synchronize()                     # the caller reads the previous step's result on the host
-        e2e_state['n'] = j + 1
+        return g
+    host_main = {k: torch.tensor(v).pin_memory() for k, v in base.items()}
+    ms_e2e, Ke, h2d, d2h = e2e_leg(host_main, compute_main, (n, GH + 1, GW + 1, 2))
 
-    Ke = max(3, min(K, 20))
-    # the copy issued ahead by the last step is waited for inside the timed region: K steps pay for K copies
-    ms_e2e = timed(e2e_step, Ke, 3, before_stop=lambda: torch.cuda.current_stream().wait_stream(copy_stream))
+    # second leg: what a training step really moves -- uint8 frames (the reference's frames are uint8: config.py:6-21), widened on
+    # the device exactly as config.py:19 does, img_loss fused onto the warp (s_net_bundle_nobm.py:332,347-352): no upstream
+    # gradient tensor crosses PCIe
+    e2e_u8 = None
+    if not args.no_configs:
+        rs = np.random.RandomState(7 + rank)
+        host_u8 = {'U': torch.tensor(rs.randint(0, 256, (n, H, W, C)).astype(np.uint8)).pin_memory(),
+                   'y': torch.tensor(rs.randint(0, 256, (n, H, W, C)).astype(np.uint8)).pin_memory(),
+                   'theta': torch.tensor(base['theta']).pin_memory()}
+        Uf, yf = torch.empty((n, H, W, C), device=dev), torch.empty((n, H, W, C), device=dev)
+
+        def compute_u8(st):
+            ops.u8_to_train(st['U'], out=Uf); ops.u8_to_train(st['y'], out=yf)
+            th = st['theta'].requires_grad_(True)
+            loss, out, black, img = mgw.transformer_img_loss(Uf, th, yf)
+            loss.backward()
+            g = th.grad
+            th.grad = None
+            th.requires_grad_(False)
+            return g
+        ms2, Ke2, h2d2, d2h2 = e2e_leg(host_u8, compute_u8, (n, GH + 1, GW + 1, 2))
+        e2e_u8 = {'value': P * world / (ms2 * 1e-3) / 1e6, 'unit': 'Mpix/s', 'ms_per_step': ms2, 'steps': Ke2, 'h2d_bytes_per_step': h2d2,
+                  'd2h_bytes_per_step': d2h2, 'h2d_gbs_per_rank': h2d2 / (ms2 * 1e-3) / 1e9,
+                  'workload': 'uint8 U and target frames over PCIe, exact on-device v/255-0.5, fused transformer+img_loss forward+backward (dtheta)'}
+
+    configs = None
+    if not args.no_configs:
+        configs = other_configs(mgw, ops, dev, rank, world, timed, make_step, keep)
 
     if rank != 0:
         finish(world)
@@ -330,7 +421,9 @@ def main():
         'warp_bwd': {'bound': 'hbm', 'achieved': gbs_bwd, 'peak': peak, 'unit': 'GB/s', 'frac': gbs_bwd / peak,
                      'traffic': (traffic or {}).get('warp_bwd'), 'us_per_launch': 1e3 * ms_bwd / K,
                      'algorithmic_bytes_per_launch': BWD_BYTES_PER_PX * P,
-                     'note': 'timed around mgw_warp_bwd_acc: the kernel plus the dH partial reduction (the dU zero-fill overlaps the forward)'},
+                     'note': 'mgw_warp_bwd_acc (backward kernel + dH partial reduction) timed back to back with the zero-fill of dU, '
+                             'minus the zero-fill timed alone (%.1f us): in the step the fill runs on a side branch under the forward'
+                             % (1e3 * ms_fill / K)},
     }
     line = {
         'metric': METRIC, 'value': value, 'unit': 'Mpix/s', 'n_gpus': world, 'steps': K, 'warmup': Wm,
@@ -339,14 +432,22 @@ def main():
         'config': {'workload': 'configs[1]: %d x %dx%dx%d fp32 frames per GPU, %dx%d mesh warp forward+backward (dU + dtheta)' % (n, H, W, C, GH, GW),
                    'l2': 'inputs rotate over %d sets of 151 MB (> 126 MB L2)' % R, 'kernel_impl': args.kernel_impl,
                    'launch': 'cuda graph replay' if graphs is not None else 'eager',
-                   'parallelism': 'dp%d (batch-sharded, 100 KB mesh-head grad all-reduce)' % world if world > 1 else 'single GPU'},
+                   'parallelism': ('dp%d (batch-sharded, 100 KB mesh-head grad all-reduce of step i-1 overlapped with step i; the '
+                                   'synchronous form is in configs.config5)' % world) if world > 1 else 'single GPU',
+                   'host_cores_pinned_per_rank': ncores},
         'fwd_mpix_per_s': pix_per_step * K / (ms_fwd_full * 1e-3) / 1e6,
         'step_hbm_gbs': gbs_step, 'step_hbm_frac_of_measured': gbs_step / peak, 'step_hbm_frac_of_8tbs': gbs_step / 8000.0,
         'roofline': dict(roof[dominant], kernel=dominant, peak_source=peak_src), 'roofline_kernels': roof,
-        'e2e': {'value': pix_per_step * Ke / (ms_e2e * 1e-3) / 1e6, 'unit': 'Mpix/s', 'h2d_bytes_per_step': h2d,
-                'd2h_bytes_per_step': d2h, 'ms_per_step': ms_e2e / Ke, 'steps': Ke},
+        'e2e': {'value': pix_per_step / (ms_e2e * 1e-3) / 1e6, 'unit': 'Mpix/s', 'h2d_bytes_per_step': h2d,
+                'd2h_bytes_per_step': d2h, 'ms_per_step': ms_e2e, 'steps': Ke, 'h2d_gbs_per_rank': h2d / (ms_e2e * 1e-3) / 1e9},
         'gpu_launches': launches_timed, 'clocks': clocks,
     }
+    if sustained is not None:
+        line['sustained'] = sustained
+    if e2e_u8 is not None:
+        line['e2e_u8_fused'] = e2e_u8
+    if configs is not None:
+        line['configs'] = configs
     if world == 1 and not args.no_cpu_baseline:
         torch.set_num_threads(os.cpu_count() or 1)
         ns = args.cpu_sample
@@ -359,6 +460,120 @@ def main():
                                 % (ns, n, len(ts), sum(ts))}
     print(json.dumps(line))
     finish(world)
+
+
+def other_configs(mgw, ops, dev, rank, world, timed, make_step, keep):
+    """sub-records for the BASELINE.json configurations that are not the headline (bounded: a few seconds in total)."""
+    import synth
+    from dovs_b200._lib import lib, check
+    res = {}
+    flush = torch.empty(48 * 1024 * 1024, device=dev)
+
+    def dev_us(fn, reps=30, flush_l2=True):
+        for _ in range(3):
+            fn()
+        ts = []
+        for _ in range(reps):
+            if flush_l2:
+                flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); fn(); e1.record(); torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1) * 1e3)
+        return float(np.median(ts))
+
+    if rank == 0:
+        # ---- config #1: single 288x512x3 frame, forward (K1 + K2)
+        U1 = torch.tensor(synth.noise_image(1, H, W, C, 1), device=dev)
+        th1 = torch.tensor(synth.random_mesh(1, GH, GW, 0.05, 2), device=dev)
+        t1 = dev_us(lambda: ops.mesh_warp_fwd(U1, th1))
+        res['config1_single_frame_fwd'] = {'us_device': t1, 'mpix_per_s': H * W / t1}
+
+        # ---- config #3: the warp stage inside a StabNet-shaped forward (torch ResNet-50-v2 carrier, random init, batch 16, 13 channels)
+        try:
+            net = mgw.StabNet(in_ch=13).to(dev).eval()
+            x13 = torch.randn(16, H, W, 13, device=dev) * 0.2
+            with torch.no_grad():
+                def fwd3():
+                    theta = net(x13)
+                    _, pts2 = mgw.get_4_pts(theta, 16)
+                    return mgw.transformer(x13[..., 12:13].contiguous(), pts2)
+                t_all = dev_us(fwd3, 10, flush_l2=False)
+                theta = net(x13)
+                _, pts2 = mgw.get_4_pts(theta, 16)
+                x1 = x13[..., 12:13].contiguous()
+                t_warp = dev_us(lambda: mgw.transformer(x1, pts2), 30)
+            res['config3_stabnet_fwd_b16'] = {'ms_forward': t_all * 1e-3, 'us_warp_stage': t_warp, 'warp_share': t_warp / t_all,
+                                              'note': 'backbone = torch/cuDNN carrier (parity unpinned); the warp stage is this library (C = 1)'}
+            del net, x13
+        except Exception as e:      # noqa: BLE001
+            res['config3_stabnet_fwd_b16'] = {'error': str(e)[:200]}
+
+        # ---- config #4: 1080p stream, batch 1, per-frame latency host-to-host.  Frames are uint8 (config.py:6-21,
+        # deploy_bundle.py:301): H2D uint8 -> v/255-0.5 on the device -> K1 + K2 -> (x+0.5)*255 -> uint8 -> D2H, one CUDA graph
+        Hh, Ww = 1080, 1920
+        fr_h = torch.randint(0, 256, (1, Hh, Ww, 3), dtype=torch.uint8).pin_memory()
+        out_h = torch.empty((1, Hh, Ww, 3), dtype=torch.uint8).pin_memory()
+        th4 = torch.tensor(synth.random_mesh(1, GH, GW, 0.03, 4), device=dev)
+        fr_d = torch.empty((1, Hh, Ww, 3), device=dev, dtype=torch.uint8)
+        f32_d, o32_d = torch.empty((1, Hh, Ww, 3), device=dev), torch.empty((1, Hh, Ww, 3), device=dev)
+        bl_d, xy_d, Hs_d = torch.empty((1, Hh, Ww), device=dev), torch.empty((1, Hh, Ww, 2), device=dev), torch.empty((1, GH, GW, 9), device=dev)
+        ou_d = torch.empty((1, Hh, Ww, 3), device=dev, dtype=torch.uint8)
+        PP = lambda x: x.data_ptr()      # noqa: E731
+        s4 = torch.cuda.Stream(device=dev)
+        with torch.cuda.stream(s4):
+            def kernels():
+                ops.u8_to_train(fr_d, out=f32_d)
+                check(lib.mgw_mesh_warp_fwd(PP(f32_d), PP(th4), 1, Hh, Ww, 3, GH, GW, PP(Hs_d), PP(o32_d), PP(bl_d), PP(xy_d),
+                                            torch.cuda.current_stream().cuda_stream), 'fwd')
+                ops.train_to_u8(o32_d, out=ou_d)
+
+            def frame():
+                fr_d.copy_(fr_h, non_blocking=True)
+                kernels()
+                out_h.copy_(ou_d, non_blocking=True)
+            for _ in range(3):
+                frame()
+            s4.synchronize()
+            g4 = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g4, stream=s4):
+                frame()
+            gk = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(gk, stream=s4):
+                kernels()
+            us_dev = dev_us(gk.replay, 100, flush_l2=False)
+            lat = []
+            for _ in range(1000):
+                t0 = time.perf_counter()
+                g4.replay()
+                s4.synchronize()
+                lat.append((time.perf_counter() - t0) * 1e6)
+        res['config4_1080p_stream'] = {'us_device_kernels': us_dev, 'us_p50_host_to_host': float(np.percentile(lat, 50)),
+                                       'us_p99_host_to_host': float(np.percentile(lat, 99)), 'frames': 1000,
+                                       'bytes_h2d_per_frame': fr_h.numel(), 'bytes_d2h_per_frame': out_h.numel(),
+                                       'note': 'uint8 frames over PCIe, u8->fp32->warp->u8 on the device, H2D + 4 kernels + D2H as ONE CUDA graph'}
+        del f32_d, o32_d, xy_d
+
+    # ---- config #5: data-parallel train step, batch 256 clips sharded over the ranks (256/N per rank), mesh-head all-reduce
+    nb = 256 // world
+    base5 = synth_inputs(32, seed=50 + rank)
+    rep = (nb + 31) // 32
+    set5 = [{k: torch.tensor(np.concatenate([np.roll(v, j, axis=0) for j in range(rep)])[:nb], device=dev) for k, v in base5.items()}]
+    feats5 = torch.randn(nb, 512, device=dev)
+    red5 = mgw.parallel.MeshHeadGradReducer(512, 2 * (GH + 1) * (GW + 1), dev, nbuf=2)
+    rec5 = {'frames_per_rank': nb, 'global_batch': nb * world,
+            'l2': 'one input set of %.0f MB per rank (> 126 MB L2)' % (nb * 151.0 / 32)}
+    for name, sync in (('overlapped', False), ('synchronous', True)):
+        if world == 1 and sync:
+            continue
+        step5, _, _, _ = make_step(set5 * 2, feats5, red5, sync_reduce=sync)
+        k5 = 20
+        ms5 = timed(step5, k5, 3)
+        rec5['ms_per_step_' + name] = ms5 / k5
+        rec5['mpix_per_s_' + name] = nb * world * H * W * k5 / (ms5 * 1e-3) / 1e6
+    if world == 1:
+        rec5['note'] = 'one rank: no collective; ms_per_step_overlapped is the 256-frame step on one GPU'
+    res['config5_dp_train_step_256'] = rec5
+    return res
 
 
 def finish(world):

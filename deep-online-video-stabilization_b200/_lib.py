@@ -19,7 +19,6 @@ SIGNATURES = {
     'mgw_version': (c_i, []),
     'mgw_last_error': (ctypes.c_char_p, []),
     'mgw_launch_count': (ctypes.c_uint64, []),
-    'mgw_set_impl': (c_i, [c_i]),
     'mgw_vertices_fwd': (c_i, [c_f, c_i, c_i, c_i, c_fl, c_f, c_f, c_st]),
     'mgw_vertices_bwd': (c_i, [c_f, c_f, c_f, c_i, c_i, c_i, c_fl, c_f, c_st]),
     'mgw_solve_h_fwd': (c_i, [c_f, c_i, c_i, c_i, c_f, c_st]),
@@ -44,6 +43,9 @@ SIGNATURES = {
     'mgw_stream_push': (c_i, [c_f, c_f, c_i, c_i, c_f, c_f, c_i, c_i, c_f, c_i, c_st]),
     'mgw_vertex_losses_fwd': (c_i, [c_f, c_f, c_f, c_i, c_i, c_i, c_fl, c_f, c_f, c_st]),
     'mgw_vertex_losses_bwd': (c_i, [c_f, c_f, c_f, c_i, c_i, c_i, c_fl, c_f, c_f, c_f, c_f, c_st]),
+    'mgw_u8_to_train_f32': (c_i, [c_f, c_f, ctypes.c_size_t, c_st]),
+    'mgw_train_f32_to_u8': (c_i, [c_f, c_f, ctypes.c_size_t, c_st]),
+    'mgw_fill_zero': (c_i, [c_f, ctypes.c_size_t, c_i, c_st]),
     'mgw_black_accumulate': (c_i, [c_f, c_f, c_i, c_st]),
     'mgw_crop_rect_workspace_bytes': (ctypes.c_size_t, [c_i, c_i]),
     'mgw_crop_rect': (c_i, [c_f, c_i, c_i, c_i, c_f, c_f, c_st]),
@@ -96,5 +98,7 @@ def launch_count():
 
 def set_impl(mode):
     """'auto' (pipeline / TMA tiles when the shape allows, else generic) | 'generic' | 'tma' (one TMA tile per CTA, error if the
-    shape does not fit) | 'pipe' (the persistent forward pipeline; the backward then takes the TMA tiles)"""
-    check(lib.mgw_set_impl({'auto': 0, 'generic': 1, 'tma': 2, 'pipe': 3}[mode]), 'mgw_set_impl')
+    shape does not fit) | 'pipe' (the persistent pipelines, error if the shape does not fit)"""
+    if mode not in ('auto', 'generic', 'tma', 'pipe'):
+        raise ValueError('unknown kernel family %r' % (mode,))
+    os.environ['MGW_IMPL'] = mode          # the library reads the variable at every call: a test / tuning hook, not an ABI entry

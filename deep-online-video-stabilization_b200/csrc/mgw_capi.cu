@@ -12,7 +12,6 @@ namespace mgw {
 
 static thread_local char g_err[512] = "";
 static std::atomic<uint64_t> g_launches{0};
-static std::atomic<int> g_impl{0};
 
 int set_error(int code, const char* fmt, ...)
 {
@@ -33,7 +32,14 @@ int check_launch(const char* what)
     return MGW_OK;
 }
 
-int impl_mode() { return g_impl.load(std::memory_order_relaxed); }
+// Kernel-family override for tests and tuning: environment variable MGW_IMPL = auto | generic | tma | pipe, read at every
+// call (there is no setter in the ABI and no state in the library).
+int impl_mode()
+{
+    const char* e = getenv("MGW_IMPL");
+    if (!e) return 0;
+    switch (e[0]) { case 'g': return 1; case 't': return 2; case 'p': return 3; default: return 0; }
+}
 
 bool pdl_enabled()
 {
@@ -85,13 +91,6 @@ const char* mgw_last_error(void) { return g_err; }
 
 uint64_t mgw_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 
-int mgw_set_impl(int impl)
-{
-    REQUIRE(impl >= 0 && impl <= 3, "mgw_set_impl: impl must be 0 (auto), 1 (generic), 2 (tma tiles) or 3 (tma pipeline)");
-    g_impl.store(impl);
-    return MGW_OK;
-}
-
 int mgw_vertices_fwd(const float* head, int N, int gh, int gw, float do_crop_rate, float* pts2, float* pts1, void* stream)
 {
     REQUIRE(head && pts2, "mgw_vertices_fwd: null pointer");
@@ -128,7 +127,7 @@ static bool use_tma_fwd(const WarpShape& s, const float* U, const float* out, co
     if (mode == 1 || mode == 3) return false;
     const bool ok = tma_fwd_supported(s) && aligned(U, 16) && (!out || aligned(out, 16)) && (!black || aligned(black, 16)) &&
                     (!img || aligned(img, 16));
-    if (!ok && mode == 2) *rc = set_error(MGW_ERR_UNSUPPORTED, "TMA path required (mgw_set_impl(2)) but shape/alignment does not allow it");
+    if (!ok && mode == 2) *rc = set_error(MGW_ERR_UNSUPPORTED, "TMA path required (MGW_IMPL=tma) but shape/alignment does not allow it");
     return ok;
 }
 
@@ -140,7 +139,7 @@ static bool use_pipe_fwd(const WarpShape& s, const float* U, const float* out, c
     if (mode == 1 || mode == 2) return false;
     const bool ok = out && black && img && pipe_fwd_supported(s) && aligned(U, 16) && aligned(out, 16) && aligned(black, 16) &&
                     aligned(img, 16);
-    if (!ok && mode == 3) *rc = set_error(MGW_ERR_UNSUPPORTED, "pipeline path required (mgw_set_impl(3)) but shape/alignment does not allow it");
+    if (!ok && mode == 3) *rc = set_error(MGW_ERR_UNSUPPORTED, "pipeline path required (MGW_IMPL=pipe) but shape/alignment does not allow it");
     return ok;
 }
 
@@ -187,8 +186,9 @@ static int warp_bwd_core(const float* U, const float* Hs, const float* d_out, co
         *parts = (const float*)workspace; *nparts = np; *part_stride = 8;
         return MGW_OK;
     }
+    // (MGW_IMPL=pipe: the backward pipeline has one tile shape (cells of at least 24 x 32 px); smaller cells take the tile kernels)
     if (!tma_ok && mode >= 2)
-        return set_error(MGW_ERR_UNSUPPORTED, "TMA path required (mgw_set_impl(2|3)) but shape/alignment/workspace does not allow it");
+        return set_error(MGW_ERR_UNSUPPORTED, "TMA path required (MGW_IMPL=tma|pipe) but shape/alignment/workspace does not allow it");
     if (tma_ok) {
         int np = 0;
         TRY(launch_warp_bwd_tma(U, Hs, d_out, d_img, s, dU, (float*)workspace, &np, fl, st));
@@ -325,6 +325,27 @@ int mgw_mesh_warp_img_loss_bwd(const float* U, const float* theta, const float* 
     const float* parts; int np, ps;
     TRY(warp_bwd_core(U, Hs, nullptr, d_img, s, dU, dHs_acc, tma_ws, &parts, &np, &ps, st, &fl, scratch));
     return launch_solve_h_bwd(theta, Hs, parts, np, ps, N, gh, gw, dtheta, st, ps == 8);
+}
+
+int mgw_fill_zero(void* p, size_t bytes, int keep_in_l2, void* stream)
+{
+    REQUIRE(p && aligned(p, 16) && bytes % 16 == 0, "mgw_fill_zero: pointer and size must be multiples of 16 bytes");
+    if (bytes == 0) return MGW_OK;
+    return launch_fill_zero(p, bytes, keep_in_l2 != 0, (cudaStream_t)stream);
+}
+
+int mgw_u8_to_train_f32(const uint8_t* src, float* dst, size_t n, void* stream)
+{
+    REQUIRE(src && dst, "mgw_u8_to_train_f32: null pointer");
+    if (n == 0) return MGW_OK;
+    return launch_u8_to_train(src, dst, n, (cudaStream_t)stream);
+}
+
+int mgw_train_f32_to_u8(const float* src, uint8_t* dst, size_t n, void* stream)
+{
+    REQUIRE(src && dst, "mgw_train_f32_to_u8: null pointer");
+    if (n == 0) return MGW_OK;
+    return launch_train_to_u8(src, dst, n, (cudaStream_t)stream);
 }
 
 int mgw_interp_fwd(const float* im, const float* x, const float* y, int N, int IH, int IW, int C, int OH, int OW,

@@ -302,4 +302,88 @@ int launch_warp_rev_bundle_u8(const uint8_t* img, const double* Hs_cvt, int N, i
     return check_launch("warp_rev_bundle");
 }
 
+// ---------------------------------------------------------------- frame transport
+// config.py:19: img * (1. / 255) - 0.5 in double (numpy: uint8 array times a Python float), then the float32 cast of the network's
+// placeholder.  Frames cross PCIe as uint8 (a quarter of the fp32 bytes) and are widened here.
+__global__ void u8_to_train_kernel(const uint8_t* __restrict__ src, float* __restrict__ dst, size_t n)
+{
+    const size_t i4 = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    if (i4 >= n) return;
+    if (i4 + 4 <= n && ((reinterpret_cast<uintptr_t>(src) | (reinterpret_cast<uintptr_t>(dst) >> 2)) & 3) == 0) {
+        const uchar4 v = *reinterpret_cast<const uchar4*>(src + i4);
+        float4 o;
+        o.x = (float)__dadd_rn(__dmul_rn((double)v.x, 1.0 / 255), -0.5); o.y = (float)__dadd_rn(__dmul_rn((double)v.y, 1.0 / 255), -0.5);
+        o.z = (float)__dadd_rn(__dmul_rn((double)v.z, 1.0 / 255), -0.5); o.w = (float)__dadd_rn(__dmul_rn((double)v.w, 1.0 / 255), -0.5);
+        *reinterpret_cast<float4*>(dst + i4) = o;
+    } else {
+        for (size_t i = i4; i < n && i < i4 + 4; ++i) dst[i] = (float)__dadd_rn(__dmul_rn((double)src[i], 1.0 / 255), -0.5);
+    }
+}
+
+// cvt_train2img, deploy_bundle.py:75: ((x + 0.5) * 255).astype(np.uint8) on a float32 array: two fp32 operations, truncation
+// towards zero; values outside [0, 256) wrap like the x86 conversion numpy compiles to (int32 truncation, low byte; NaN -> 0).
+__device__ __forceinline__ uint8_t train_to_u8(float x)
+{
+    const float v = __fmul_rn(__fadd_rn(x, 0.5f), 255.0f);
+    const int t = (fabsf(v) < 2147483648.0f) ? __float2int_rz(v) : (int)0x80000000;
+    return (uint8_t)(t & 0xff);
+}
+
+__global__ void train_to_u8_kernel(const float* __restrict__ src, uint8_t* __restrict__ dst, size_t n)
+{
+    const size_t i4 = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    if (i4 >= n) return;
+    if (i4 + 4 <= n && (((reinterpret_cast<uintptr_t>(src) >> 2) | reinterpret_cast<uintptr_t>(dst)) & 3) == 0) {
+        const float4 v = *reinterpret_cast<const float4*>(src + i4);
+        *reinterpret_cast<uchar4*>(dst + i4) = make_uchar4(train_to_u8(v.x), train_to_u8(v.y), train_to_u8(v.z), train_to_u8(v.w));
+    } else {
+        for (size_t i = i4; i < n && i < i4 + 4; ++i) dst[i] = train_to_u8(src[i]);
+    }
+}
+
+// 16 bytes per thread and iteration; keep = the lines are written with an L2 evict_last policy, so that a buffer which is
+// accumulated into next (dU of the backward: reductions at L2) is still resident when its kernel starts
+// Small blocks with a handful of registers on purpose: the fill is meant to run NEXT TO the persistent warp kernels, which
+// leave only ~3 K registers and a few hundred thread slots per SM free (a 256-thread block does not fit and would wait for
+// them to finish).
+template <bool KEEP>
+__global__ void __launch_bounds__(64) fill_zero_kernel(uint4* __restrict__ p, size_t n16)
+{
+    uint64_t pol = 0;
+    if (KEEP) asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += (size_t)gridDim.x * blockDim.x) {
+        if (KEEP) asm volatile("st.global.L2::cache_hint.v4.b32 [%0], {%1, %1, %1, %1}, %2;" ::"l"(p + i), "r"(0), "l"(pol) : "memory");
+        else p[i] = make_uint4(0, 0, 0, 0);
+    }
+}
+
+int launch_u8_to_train(const uint8_t* src, float* dst, size_t n, cudaStream_t st)
+{
+    const size_t blocks = ((n + 3) / 4 + 255) / 256;
+    if (blocks > 0x7fffffffULL) return set_error(MGW_ERR_INVALID, "u8_to_train: too many elements");
+    u8_to_train_kernel<<<(unsigned)blocks, 256, 0, st>>>(src, dst, n);
+    return check_launch("u8_to_train");
+}
+
+int launch_train_to_u8(const float* src, uint8_t* dst, size_t n, cudaStream_t st)
+{
+    const size_t blocks = ((n + 3) / 4 + 255) / 256;
+    if (blocks > 0x7fffffffULL) return set_error(MGW_ERR_INVALID, "train_to_u8: too many elements");
+    train_to_u8_kernel<<<(unsigned)blocks, 256, 0, st>>>(src, dst, n);
+    return check_launch("train_to_u8");
+}
+
+int launch_fill_zero(void* p, size_t bytes, bool keep_in_l2, cudaStream_t st)
+{
+    const size_t n16 = bytes / 16;
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const size_t want = (n16 + 63) / 64, cap = (size_t)sms * 16;
+    const unsigned grid = (unsigned)(want < cap ? want : cap);
+    if (keep_in_l2) fill_zero_kernel<true><<<grid, 64, 0, st>>>(reinterpret_cast<uint4*>(p), n16);
+    else fill_zero_kernel<false><<<grid, 64, 0, st>>>(reinterpret_cast<uint4*>(p), n16);
+    return check_launch("fill_zero");
+}
+
 }  // namespace mgw

@@ -12,7 +12,7 @@ namespace mgw {
 int set_error(int code, const char* fmt, ...);
 int check_launch(const char* what);          // counts the launch, maps cudaGetLastError() to MGW_ERR_CUDA
 void count_launches(int n);
-int impl_mode();                             // mgw_set_impl value
+int impl_mode();                             // MGW_IMPL environment override: 0 auto, 1 generic, 2 tma tiles, 3 pipelines
 
 // Launch with (pdl = true) the programmatic-stream-serialization attribute: the kernel may be scheduled while the previous
 // kernel of the stream is still running and synchronises with it through griddep_wait() (mgw_device.cuh).
@@ -114,6 +114,12 @@ int launch_cvt_img2train_u8(const uint8_t* bgr, int H, int W, const int32_t* kx,
                             float* out, cudaStream_t st);
 int launch_warp_rev_bundle_u8(const uint8_t* img, const double* Hs_cvt, int N, int H, int W, int C, int gh, int gw, uint8_t* dst,
                               cudaStream_t st);
+
+// frame transport: uint8 <-> the network's fp32 range (config.py:19, deploy_bundle.py:75), and a zero-fill that can leave its
+// lines resident in L2 (the dU buffer the backward accumulates into)
+int launch_u8_to_train(const uint8_t* src, float* dst, size_t n, cudaStream_t st);
+int launch_train_to_u8(const float* src, uint8_t* dst, size_t n, cudaStream_t st);
+int launch_fill_zero(void* p, size_t bytes, bool keep_in_l2, cudaStream_t st);
 
 // mgw_vertex_loss.cu : vertex regularisers (s_net_bundle_nobm.py:139-210,246-247)
 int launch_vertex_losses_fwd(const float* theta, const float* pts1, const float* pts2, int N, int gh, int gw, float do_crop_rate,

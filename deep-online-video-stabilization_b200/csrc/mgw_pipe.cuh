@@ -11,6 +11,8 @@ struct PipeCfg {
     TileCfg t;
     int nty, ntx;                   // tiles per image along y / x
     int total;                      // N * nty * ntx
+    // backward: a CTA walks CHUNKS of chunk_L vertically adjacent tiles of one cell (one dH partial per chunk); 1 = tile by tile
+    int chunk_L, chunk_rows, nchunks;      // tiles per chunk, chunks per image column (nty / chunk_L), N * chunk_rows * ntx
 };
 
 // BW x BH = staged source box in pixels.  The benchmark meshes (sigma = 0.05) stretch and shear a 32 x 24 tile into a
@@ -55,7 +57,7 @@ constexpr int kInfoRing = 16;
 // taps are.
 template <class G, int TW, int TH, int C>
 __device__ __forceinline__ void make_record(const PipeCfg& cfg, const float* __restrict__ Hs, int t, bool valid, float stepx,
-                                            float stepy, PInfo* rec, int lane)
+                                            float stepy, PInfo* rec, int lane, bool writer)
 {
     const int H = cfg.t.H, W = cfg.t.W;
     const int tx = t % cfg.ntx, qq = t / cfg.ntx, ty = qq % cfg.nty;
@@ -86,7 +88,7 @@ __device__ __forceinline__ void make_record(const PipeCfg& cfg, const float* __r
         sgn += __shfl_xor_sync(0xffffffffu, sgn, o);
         ok = ok && (__shfl_xor_sync(0xffffffffu, (int)ok, o) != 0);
     }
-    if (k4 != 0 || !valid) return;
+    if (!writer || !valid) return;
     ok = ok && (sgn == 4 || sgn == -4);
     int bx0 = 0, by0 = 0, complete = 0, ncol = G::SBW, nrow = G::SBH;
     if (ok) {
@@ -106,7 +108,8 @@ __device__ __forceinline__ void make_record(const PipeCfg& cfg, const float* __r
     for (int k = 0; k < 9; ++k) rec->Hc[k] = Hc[k];
     rec->n = n; rec->r0 = r0; rec->c0 = c0; rec->vr0 = cfg.t.rows.vstart[ty]; rec->vc0 = cfg.t.cols.vstart[tx];
     rec->bx0 = bx0; rec->by0 = by0; rec->complete = complete;
-    rec->cell = cell; rec->part = cfg.t.rows.part[ty] * cfg.t.parts_x + cfg.t.cols.part[tx];
+    rec->cell = cell;
+    rec->part = cfg.chunk_L > 1 ? cfg.t.cols.part[tx] : cfg.t.rows.part[ty] * cfg.t.parts_x + cfg.t.cols.part[tx];
     // the part of the box inside the image ((W - bx0) * C is a multiple of 4 floats: W % 4 == 0 and bx0 % kXalign == 0)
     rec->nrow = min(nrow, H - by0);
     rec->nq = min((min(ncol * C, G::kRowF) + 3) / 4, (W - bx0) * C / 4);
@@ -120,7 +123,7 @@ __device__ __forceinline__ void prepare_round(const PipeCfg& cfg, const float* _
     const int j = lane >> 2;
     const long long tj = (long long)t + (long long)j * gridDim.x;
     const bool valid = tj < cfg.total;
-    make_record<G, TW, TH, C>(cfg, Hs, valid ? (int)tj : cfg.total - 1, valid, stepx, stepy, info + ((it + j) % kInfoRing), lane);
+    make_record<G, TW, TH, C>(cfg, Hs, valid ? (int)tj : cfg.total - 1, valid, stepx, stepy, info + ((it + j) % kInfoRing), lane, (lane & 3) == 0);
     __syncwarp();
 }
 
@@ -221,6 +224,7 @@ static bool plan(const WarpShape& s, int TW, int TH, PipePlan* out)
     const long long total = (long long)s.N * p.cfg.nty * p.cfg.ntx;
     if (total >= (1LL << 31)) return false;
     p.cfg.total = (int)total;
+    p.cfg.chunk_L = 1; p.cfg.chunk_rows = p.cfg.nty; p.cfg.nchunks = p.cfg.total;
     *out = p;
     return true;
 }

@@ -381,6 +381,40 @@ def stream_push(frames, masks, slot, img, black, refeed_into=None):
         check(lib.mgw_stream_push(_p(frames), _p(masks), depth, int(slot), _p(img), _p(black), h, w, fo, stride, _st()), 'mgw_stream_push')
 
 
+def u8_to_train(frame, out=None):
+    """config.py:19 on the device: uint8 tensor (any shape) -> float32 v * (1/255) - 0.5, exact."""
+    frame = _chk(frame, 'frame', torch.uint8)
+    out = torch.empty(frame.shape, device=frame.device, dtype=torch.float32) if out is None else _chk_out(out, 'out')
+    if out.numel() != frame.numel():
+        raise ValueError('out has %d elements, frame %d' % (out.numel(), frame.numel()))
+    with torch.cuda.device(frame.device):
+        check(lib.mgw_u8_to_train_f32(_p(frame), _p(out), frame.numel(), _st()), 'mgw_u8_to_train_f32')
+    return out
+
+
+def train_to_u8(x, out=None):
+    """cvt_train2img (deploy_bundle.py:75) on the device: float32 -> uint8 ((x + 0.5) * 255, truncated)."""
+    x = _chk(x, 'x')
+    out = torch.empty(x.shape, device=x.device, dtype=torch.uint8) if out is None else _chk_out(out, 'out', torch.uint8)
+    if out.numel() != x.numel():
+        raise ValueError('out has %d elements, x %d' % (out.numel(), x.numel()))
+    with torch.cuda.device(x.device):
+        check(lib.mgw_train_f32_to_u8(_p(x), _p(out), x.numel(), _st()), 'mgw_train_f32_to_u8')
+    return out
+
+
+def fill_zero(t, keep_in_l2=False):
+    """zero-fill of a contiguous CUDA tensor by the library's own kernel; keep_in_l2: evict_last policy (dU before *_bwd_acc)."""
+    if not (isinstance(t, torch.Tensor) and t.is_cuda and t.is_contiguous()):
+        raise ValueError('fill_zero needs a contiguous CUDA tensor')
+    nbytes = t.numel() * t.element_size()
+    if nbytes % 16 or t.data_ptr() % 16:
+        raise ValueError('fill_zero needs a 16-byte aligned tensor whose size is a multiple of 16 bytes')
+    with torch.cuda.device(t.device):
+        check(lib.mgw_fill_zero(_p(t), nbytes, 1 if keep_in_l2 else 0, _st()), 'mgw_fill_zero')
+    return t
+
+
 def black_accumulate(all_black, black):
     """deploy_bundle.py:291: all_black = all_black + np.round(black).astype(np.int64), in place on the device (int32 counts)."""
     black, all_black = _chk(black, 'black'), _chk_out(all_black, 'all_black', torch.int32)

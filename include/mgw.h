@@ -44,9 +44,9 @@ MGW_API const char* mgw_last_error(void);
 /* Number of kernels this library has launched on the calling process so far (bench.py's gpu_launches). */
 MGW_API uint64_t mgw_launch_count(void);
 
-/* Select the warp implementation: 0 = auto (TMA-staged tiles when shape/alignment allow, else generic),
- * 1 = force the generic global-gather kernels, 2 = require the TMA path (error if impossible). */
-MGW_API int mgw_set_impl(int impl);
+/* Kernel family: chosen per call from shape and alignment (persistent TMA pipelines, else one TMA tile per CTA, else the
+ * generic global-gather kernels).  Tests and tuning runs can force one through the environment variable
+ * MGW_IMPL = auto | generic | tma | pipe ("tma" / "pipe" fail instead of falling back); the library keeps no such state. */
 
 /* ---- a0: get_4_pts, s_net_bundle_nobm.py:29-71 --------------------------------------------------------
  * head [N, 2*(gh+1)*(gw+1)] -> pts2 [N,gh+1,gw+1,2] (absolute clamped vertices, (x,y) last),
@@ -173,6 +173,18 @@ MGW_API int mgw_vertex_losses_fwd(const float* theta, const float* pts1, const f
 MGW_API int mgw_vertex_losses_bwd(const float* theta, const float* pts1, const float* pts2, int N, int gh, int gw,
                           float do_crop_rate, const float* f, float* d_theta, float* d_pts1,
                           float* d_pts2, void* stream);
+
+/* ---- frame transport -------------------------------------------------------------------------------------------------
+ * Frames cross PCIe as uint8 (the reference's frames ARE uint8: config.py:6-21, deploy_bundle.py:301) and are widened on the device.
+ * mgw_u8_to_train_f32: dst[i] = float32(src[i] * (1./255) - 0.5), the double-precision expression of config.py:19 and the
+ *   float32 cast of the network's placeholder; exact.
+ * mgw_train_f32_to_u8: cvt_train2img, deploy_bundle.py:75 = ((x + 0.5) * 255).astype(np.uint8) on float32 (truncation; values
+ *   outside [0,256) wrap like numpy on x86).
+ * mgw_fill_zero: zero-fill of `bytes` (multiple of 16, 16-byte aligned) device bytes; keep_in_l2 != 0 writes the lines with an
+ *   L2 evict_last policy -- for the dU buffer that mgw_*_bwd_acc accumulates into next (its reductions then hit L2). */
+MGW_API int mgw_u8_to_train_f32(const uint8_t* src, float* dst, size_t n, void* stream);
+MGW_API int mgw_train_f32_to_u8(const float* src, uint8_t* dst, size_t n, void* stream);
+MGW_API int mgw_fill_zero(void* p, size_t bytes, int keep_in_l2, void* stream);
 
 /* ---- f4 (deploy side): the crop of deploy_bundle.py:240,291,344-365 -------------------------------------------------
  * mgw_black_accumulate: all_black[p] += round(black[p])  (all_black = all_black + np.round(black).astype(np.int64), :291;

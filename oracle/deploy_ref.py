@@ -374,3 +374,15 @@ def resize_linear_u8(img, out_w, out_h):
     b0, b1 = ay[:, 0][:, None, None], ay[:, 1][:, None, None]
     out = (((b0 * (r0 >> 4)) >> 16) + ((b1 * (r1 >> 4)) >> 16) + 2) >> 2
     return np.clip(out, 0, 255).astype(np.uint8).reshape((out_h, out_w) + img.shape[2:])
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# frame transport: the two literal expressions of the reference (numpy evaluates them exactly as the reference does)
+def u8_to_train(frame_u8):
+    """config.py:19: img * (1. / 255) - 0.5 (float64), then the float32 cast of the network's placeholder."""
+    return (np.asarray(frame_u8, np.uint8) * (1. / 255) - 0.5).astype(np.float32)
+
+
+def train_to_u8(x):
+    """deploy_bundle.py:75 cvt_train2img without the reshape: ((x + 0.5) * 255).astype(np.uint8) on a float32 array."""
+    return ((np.asarray(x, np.float32) + 0.5) * 255).astype(np.uint8)

@@ -125,7 +125,9 @@ def test_config3_c1_forward_and_backward(mgw, impl):
     up = dHs[sl].cpu().double()
     up[..., 8] = 0
     (ref.solve_h(th64) * up).sum().backward()
-    assert relmax(dth[sl].cpu().numpy(), th64.grad.numpy()) < 1e-4
+    # (the adjoint solve amplifies the fp32 summation noise of dHs by the conditioning of the cell's 8x8 system; the generic
+    # family sums dHs with fp32 atomics in arbitrary order)
+    assert relmax(dth[sl].cpu().numpy(), th64.grad.numpy()) < 2e-4
 
 
 # ------------------------------------------------------------------ loss epilogues on their PRODUCTION code paths
@@ -214,6 +216,37 @@ def test_fused_img_loss_production_path(mgw, c):
     up[..., 8] = 0
     (ref.solve_h(th64) * up).sum().backward()
     assert relmax(ta.grad.cpu().numpy(), th64.grad.numpy()) < 2e-4
+
+
+@pytest.mark.parametrize('n', [1, 7, 4096, 1080 * 1920 * 3 + 3])
+def test_frame_transport_u8(mgw, n):
+    """uint8 <-> the network's fp32 range on the device (config.py:19, deploy_bundle.py:75): exact / byte-exact vs the literal
+    numpy expressions, odd lengths and unaligned views included."""
+    import deploy_ref
+    r = np.random.RandomState(n % 1000)
+    frame = r.randint(0, 256, n + 1).astype(np.uint8)
+    for off in (0, 1):                                         # off = 1: a view whose base is not 4-byte aligned
+        src = frame[off:off + n]
+        got = mgw.ops.u8_to_train(dev(frame, torch.uint8)[off:off + n])
+        assert bits_equal(got.cpu().numpy(), deploy_ref.u8_to_train(src)).all()
+    x = (r.rand(n).astype(np.float32) - 0.5) * 0.999           # in range: the cast is defined
+    x[: min(n, 256)] = deploy_ref.u8_to_train(np.arange(256, dtype=np.uint8))[: min(n, 256)]      # every representable level
+    got = mgw.ops.train_to_u8(dev(x))
+    assert np.array_equal(got.cpu().numpy(), deploy_ref.train_to_u8(x))
+    # round trip of every level
+    lv = dev(np.arange(256, dtype=np.uint8), torch.uint8)
+    back = mgw.ops.train_to_u8(mgw.ops.u8_to_train(lv)).cpu().numpy()
+    assert np.array_equal(back, deploy_ref.train_to_u8(deploy_ref.u8_to_train(np.arange(256, dtype=np.uint8))))
+
+
+def test_fill_zero(mgw):
+    for keep in (False, True):
+        t = torch.full((3, 97, 64), 7.0, device='cuda')
+        mgw.ops.fill_zero(t, keep_in_l2=keep)
+        assert float(t.abs().max()) == 0.0
+    guard = torch.full((1024 + 8,), 5.0, device='cuda')
+    mgw.ops.fill_zero(guard[4:1028], keep_in_l2=True)
+    assert float(guard[:4].min()) == 5.0 and float(guard[1028:].min()) == 5.0 and float(guard[4:1028].abs().max()) == 0.0
 
 
 def test_autograd_reaches_the_fused_backward(mgw, monkeypatch):
