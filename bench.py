@@ -197,7 +197,7 @@ def main():
         def step_eager(i):
             s = sets[i % nset]
             cur = torch.cuda.current_stream()
-            fill_mode = os.environ.get('BENCH_FILL', 'side')       # tuning aid: side | none (wrong dU) | serial | after_fwd
+            fill_mode = os.environ.get('BENCH_FILL', 'after_fwd')       # tuning aid: side | none (wrong dU) | serial | after_fwd
             if fill_mode == 'serial':
                 ops.fill_zero(dU_buf, keep_in_l2=keep)
             side.wait_stream(cur)

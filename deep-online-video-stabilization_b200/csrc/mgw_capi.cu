@@ -173,13 +173,14 @@ static int warp_bwd_core(const float* U, const float* Hs, const float* d_out, co
                          bool zero_dU = true)
 {
     const size_t ncell = (size_t)s.N * s.gh * s.gw;
-    if (dU && zero_dU) TRY(check_memset(cudaMemsetAsync(dU, 0, sizeof(float) * (size_t)s.N * s.H * s.W * s.C, st), "memset dU"));
     const int mode = impl_mode();
     const bool tma_ok = mode != 1 && workspace && tma_bwd_supported(s) && aligned(U, 16) && (!dU || aligned(dU, 16)) &&
                         (!d_img || aligned(d_img, 8));
     // the persistent pipeline serves the calls that want dU (modes auto / pipe); dH-only calls and mode 2 take the tile kernels
-    const bool pipe_ok = mode != 1 && mode != 2 && dU && workspace && pipe_bwd_supported(s) && aligned(U, 16) && aligned(dU, 16) &&
+    static const bool prefer_tiles = [] { const char* v = getenv("MGW_BWD"); return v && v[0] == 't'; }();      // tuning aid: MGW_BWD=tile
+    const bool pipe_ok = mode != 1 && mode != 2 && !(prefer_tiles && mode == 0) && dU && workspace && pipe_bwd_supported(s) && aligned(U, 16) && aligned(dU, 16) &&
                          (!d_img || aligned(d_img, 8));
+    if (dU && zero_dU) TRY(launch_fill_zero(dU, sizeof(float) * (size_t)s.N * s.H * s.W * s.C, true, st));
     if (pipe_ok) {
         int np = 0;
         TRY(launch_warp_bwd_pipe(U, Hs, d_out, d_img, s, dU, (float*)workspace, &np, fl, st));

@@ -349,6 +349,10 @@ __global__ void train_to_u8_kernel(const float* __restrict__ src, uint8_t* __res
 template <bool KEEP>
 __global__ void __launch_bounds__(64) fill_zero_kernel(uint4* __restrict__ p, size_t n16)
 {
+    // programmatic dependent launch on both sides: the blocks may be scheduled under the tail of the previous kernel (the forward
+    // warp) and the next one (the backward warp) may set itself up while the fill runs
+    griddep_wait();
+    griddep_launch_dependents();
     uint64_t pol = 0;
     if (KEEP) asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += (size_t)gridDim.x * blockDim.x) {
@@ -381,8 +385,9 @@ int launch_fill_zero(void* p, size_t bytes, bool keep_in_l2, cudaStream_t st)
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const size_t want = (n16 + 63) / 64, cap = (size_t)sms * 16;
     const unsigned grid = (unsigned)(want < cap ? want : cap);
-    if (keep_in_l2) fill_zero_kernel<true><<<grid, 64, 0, st>>>(reinterpret_cast<uint4*>(p), n16);
-    else fill_zero_kernel<false><<<grid, 64, 0, st>>>(reinterpret_cast<uint4*>(p), n16);
+    const cudaError_t e = keep_in_l2 ? launch_ex(fill_zero_kernel<true>, dim3(grid), dim3(64), 0, st, pdl_enabled(), reinterpret_cast<uint4*>(p), n16)
+                                     : launch_ex(fill_zero_kernel<false>, dim3(grid), dim3(64), 0, st, pdl_enabled(), reinterpret_cast<uint4*>(p), n16);
+    if (e != cudaSuccess) { count_launches(1); return set_error(MGW_ERR_CUDA, "fill_zero: %s", cudaGetErrorString(e)); }
     return check_launch("fill_zero");
 }
 

@@ -130,6 +130,18 @@ __device__ __forceinline__ int tile_of(const PipeCfg& cfg, int j)
 #define MGW_PIPE_BWD_MINB 2
 #endif
 
+// records of round r (the CTA's tiles 8r .. 8r+7): warp w prepares tile 8r + w (4 lanes project the corners)
+template <class G, int TW, int TH, int C>
+__device__ __forceinline__ void prepare_round_by_warps(const PipeCfg& cfg, const float* __restrict__ Hs, int r, int nj, PInfo* info, uint64_t* recbar)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int j = r * kRoundTiles + warp;
+    const bool valid = j < nj;
+    make_record<G, TW, TH, C>(cfg, Hs, valid ? tile_of(cfg, j) : 0, valid, lin_step(cfg.t.W), lin_step(cfg.t.H), info + (j % kInfoRing), lane, lane == 0);
+    __syncwarp();
+    if (lane == 0) tma::mbar_arrive(recbar + (r & 1));
+}
+
 template <int C, int TW, int K, int NT, int S, int BW, int BH, bool LOSS>
 __global__ void __launch_bounds__(NT, MGW_PIPE_BWD_MINB)
 warp_bwd_pipe_kernel(const __grid_constant__ CUtensorMap mapU, const float* __restrict__ U, const float* __restrict__ Hs,
@@ -162,21 +174,16 @@ warp_bwd_pipe_kernel(const __grid_constant__ CUtensorMap mapU, const float* __re
         for (int i = tid; i < 2 * G::kBoxF / 4; i += NT) a4[i] = make_int4(0, 0, 0, 0);
     }
     __syncthreads();
-    griddep_launch_dependents();                                  // K4 may be scheduled now: its factorisation overlaps this kernel
+    // programmatic dependent launch: the set-up above overlapped the tail of the previous kernel of the stream; nothing below
+    // touches global memory before that kernel has completed.  K4 may be scheduled from now on: its factorisation overlaps us.
+    griddep_wait();
+    griddep_launch_dependents();
     const float stepx = lin_step(W), stepy = lin_step(H);
     const int tx = tid % TW, g = tid / TW;
     // tiles of this CTA: its chunks (dealt round-robin) times the tiles per chunk
     const int nj = (int)blockIdx.x < cfg.nchunks ? ((cfg.nchunks - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x) * cfg.chunk_L : 0;
 
     // ---- bookkeeping spread over the warps
-    // records of round r (the CTA's tiles 8r .. 8r+7): warp w prepares tile 8r + w (4 lanes project the corners)
-    auto prepare_round_by_warps = [&](int r) {
-        const int j = r * kRoundTiles + warp;
-        const bool valid = j < nj;
-        make_record<G, TW, TH, C>(cfg, Hs, valid ? tile_of(cfg, j) : 0, valid, stepx, stepy, info + (j % kInfoRing), lane, lane == 0);
-        __syncwarp();
-        if (lane == 0) tma::mbar_arrive(recbar + (r & 1));
-    };
     auto wait_round = [&](int r) { tma::mbar_wait(recbar + (r & 1), (r >> 1) & 1); };
     // source box of the CTA's j-th tile -> stage j % S (one thread)
     auto request_box = [&](int j) {
@@ -192,25 +199,29 @@ warp_bwd_pipe_kernel(const __grid_constant__ CUtensorMap mapU, const float* __re
     float gcur[K][C], gicur[K][2];
     float na[K][C], nb[LOSS ? K : 1][LOSS ? C : 1], nbk[LOSS ? K : 1];
     // issue the loads of a tile's upstream gradients (pixels the tile does not own are never read: they count as zero)
+    // (pixel indices fit 32 bits -- N*H*W < 2^31 is validated by the C ABI -- so every address is one IMAD.WIDE off a base)
     auto load_next = [&](const PInfo* in) {
         const int row0 = in->r0 + g * K, col = in->c0 + tx;
         const int kfirst = (col >= in->vc0) ? in->vr0 - row0 : K;      // first owned pixel of the thread (<= 0: all of them)
-        const size_t p0 = ((size_t)in->n * H + row0) * W + col;
-        const float* po = (LOSS ? loss.out : d_out) + p0 * C;
-        const float2* pi = reinterpret_cast<const float2*>(d_img) + p0;
+        const int p0 = (in->n * H + row0) * W + col;
+        const float* gsrc = LOSS ? loss.out : d_out;
 #pragma unroll
         for (int k = 0; k < K; ++k) {
             const bool own = k >= kfirst;
+            const int p = p0 + k * W;
+            const float* po = gsrc + (size_t)(unsigned)p * C;
 #pragma unroll
-            for (int ch = 0; ch < C; ++ch) na[k][ch] = own ? __ldg(po + (size_t)k * W * C + ch) : 0.0f;
+            for (int ch = 0; ch < C; ++ch) na[k][ch] = own ? __ldg(po + ch) : 0.0f;
             if constexpr (LOSS) {
-                nbk[k] = own ? 1.0f - __ldg(loss.black + p0 + (size_t)k * W) : 0.0f;
+                nbk[k] = own ? 1.0f - __ldg(loss.black + (unsigned)p) : 0.0f;
+                const float* py = loss.y + (size_t)(unsigned)p * C;
 #pragma unroll
-                for (int ch = 0; ch < C; ++ch) nb[k][ch] = own ? __ldg(loss.y + (p0 + (size_t)k * W) * C + ch) : 0.0f;
+                for (int ch = 0; ch < C; ++ch) nb[k][ch] = own ? __ldg(py + ch) : 0.0f;
             }
             // d_img of the next tile only travels to L2 now (a warp's row is 256 contiguous bytes: two lines) and is loaded at
             // the top of its own tile: 6 registers less across the gather / scatter phase, where ptxas would spill them
-            if (d_img != nullptr && (lane & 15) == 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(pi + (size_t)k * W));
+            if (d_img != nullptr && (lane & 15) == 0)
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const float2*>(d_img) + (unsigned)p));
         }
         if constexpr (LOSS) {      // the per-sample factor rides in nbk: kn * (1-black)^2
             const float kn = (loss.kscale_dev ? loss.kscale * __ldg(loss.kscale_dev) : loss.kscale) / (__ldg(loss.sums + 2 * in->n + 1) + 1e-8f);
@@ -234,8 +245,8 @@ warp_bwd_pipe_kernel(const __grid_constant__ CUtensorMap mapU, const float* __re
     };
 
     if (nj > 0) {
-        prepare_round_by_warps(0);
-        if (nj > kRoundTiles) prepare_round_by_warps(1);
+        prepare_round_by_warps<G, TW, TH, C>(cfg, Hs, 0, nj, info, recbar);
+        if (nj > kRoundTiles) prepare_round_by_warps<G, TW, TH, C>(cfg, Hs, 1, nj, info, recbar);
         if (tid == 0) { request_box(0); request_box(1); }
         wait_round(0);
         load_next(info);
@@ -251,7 +262,7 @@ warp_bwd_pipe_kernel(const __grid_constant__ CUtensorMap mapU, const float* __re
         const int s = j % S, b = j & 1;
         const PInfo* in = info + (j % kInfoRing);
         // records of the round after the next one are due in 5 tiles: every warp prepares its one now
-        if (j % kRoundTiles == 3 && j >= kRoundTiles && (j / kRoundTiles + 1) * kRoundTiles < nj) prepare_round_by_warps(j / kRoundTiles + 1);
+        if (j % kRoundTiles == 3 && j >= kRoundTiles && (j / kRoundTiles + 1) * kRoundTiles < nj) prepare_round_by_warps<G, TW, TH, C>(cfg, Hs, j / kRoundTiles + 1, nj, info, recbar);
         const bool has_next = j + 1 < nj;
         if (has_next) {
             if ((j + 1) % kRoundTiles == 0) wait_round((j + 1) / kRoundTiles);
@@ -261,11 +272,11 @@ warp_bwd_pipe_kernel(const __grid_constant__ CUtensorMap mapU, const float* __re
         {       // d_img of this tile (L2-resident since the previous tile; consumed at the end of each pixel)
             const int row0 = r0 + g * K, col = c0 + tx;
             const int kfirst = (col >= in->vc0) ? in->vr0 - row0 : K;
-            const float2* pi = reinterpret_cast<const float2*>(d_img) + ((size_t)in->n * H + row0) * W + col;
+            const int p0 = (in->n * H + row0) * W + col;
 #pragma unroll
             for (int k = 0; k < K; ++k) {
                 float2 di = make_float2(0.0f, 0.0f);
-                if (d_img != nullptr && k >= kfirst) di = __ldg(pi + (size_t)k * W);
+                if (d_img != nullptr && k >= kfirst) di = __ldg(reinterpret_cast<const float2*>(d_img) + (unsigned)(p0 + k * W));
                 gicur[k][0] = di.x; gicur[k][1] = di.y;
             }
         }
@@ -409,15 +420,17 @@ warp_bwd_pipe_kernel(const __grid_constant__ CUtensorMap mapU, const float* __re
         if (fixed && !allzero) {
             const float inv_scale = __int_as_float((e - (kFixedBits - 1) + 127) << 23);
             int4* a4 = reinterpret_cast<int4*>(abase);
-            float* dbox = dU + (((size_t)in->n * H + in->by0) * W + in->bx0) * C;
+            float* dbox = dU + (size_t)(unsigned)((in->n * H + in->by0) * W + in->bx0) * C;      // one 64-bit base per tile ...
             const int nq = in->nq, items = in->nrow * nq;
+            const unsigned pitch = (unsigned)(W * C);                                             // ... 32-bit offsets inside the box
             const float rnq = __frcp_rn((float)nq);
             for (int idx = tid; idx < items; idx += NT) {
                 const int r = __float2int_rz(__fmul_rn((float)idx + 0.5f, rnq)), q = idx - r * nq;      // exact: idx < 2^11
-                const int4 v = a4[r * (G::kRowF / 4) + q];
+                int4* cell = a4 + r * (G::kRowF / 4) + q;
+                const int4 v = *cell;
                 if ((v.x | v.y | v.z | v.w) != 0) {
-                    a4[r * (G::kRowF / 4) + q] = make_int4(0, 0, 0, 0);
-                    tma::red_add_v4(dbox + (size_t)r * W * C + 4 * q, (float)v.x * inv_scale, (float)v.y * inv_scale,
+                    *cell = make_int4(0, 0, 0, 0);
+                    tma::red_add_v4(dbox + ((unsigned)r * pitch + 4u * (unsigned)q), (float)v.x * inv_scale, (float)v.y * inv_scale,
                                     (float)v.z * inv_scale, (float)v.w * inv_scale);
                 }
             }
@@ -434,16 +447,21 @@ static int launch_v(const float* U, const float* Hs, const float* d_out, const f
     const TileCfg& c = p.cfg.t;
     CUtensorMap mU;
     TRY_RC(make_map(&mU, U, c.W * C, c.H, c.N, G::kRowF, G::SBH));
+    cudaError_t e;
+    const float* no_d_out = nullptr;
     const int grid = grid_for(p.cfg.nchunks, MGW_PIPE_BWD_MINB);
     if (loss) {
         static bool attr[64] = {};
         TRY_RC(allow_smem(warp_bwd_pipe_kernel<C, TW, K, NT, S, BW, BH, true>, attr, "warp_bwd_pipe(loss)"));
-        warp_bwd_pipe_kernel<C, TW, K, NT, S, BW, BH, true><<<grid, NT, L::kTotal, st>>>(mU, U, Hs, nullptr, d_img, p.cfg, dU, parts, *loss);
+        e = launch_ex(warp_bwd_pipe_kernel<C, TW, K, NT, S, BW, BH, true>, dim3(grid), dim3(NT), L::kTotal, st, pdl_enabled(), mU, U, Hs,
+                      no_d_out, d_img, p.cfg, dU, parts, *loss);
     } else {
         static bool attr[64] = {};
         TRY_RC(allow_smem(warp_bwd_pipe_kernel<C, TW, K, NT, S, BW, BH, false>, attr, "warp_bwd_pipe"));
-        warp_bwd_pipe_kernel<C, TW, K, NT, S, BW, BH, false><<<grid, NT, L::kTotal, st>>>(mU, U, Hs, d_out, d_img, p.cfg, dU, parts, LossSrc{});
+        e = launch_ex(warp_bwd_pipe_kernel<C, TW, K, NT, S, BW, BH, false>, dim3(grid), dim3(NT), L::kTotal, st, pdl_enabled(), mU, U, Hs,
+                      d_out, d_img, p.cfg, dU, parts, LossSrc{});
     }
+    if (e != cudaSuccess) { count_launches(1); return set_error(MGW_ERR_CUDA, "warp_bwd_pipe: %s", cudaGetErrorString(e)); }
     return check_launch("warp_bwd_pipe");
 }
 
@@ -478,12 +496,17 @@ static int nparts_of(const PipeCfg& c) { return c.chunk_L > 1 ? c.t.parts_x : c.
 
 bool pipe_bwd_supported(const WarpShape& s) { PipePlan p; return plan_bwd(s, &p); }
 
+// dH partials, sized for the tile-by-tile layout (the chunked one needs less): independent of the schedule switch
+static size_t parts_bytes(const WarpShape& s, const PipeCfg& c)
+{
+    return ((size_t)s.N * s.gh * s.gw * c.t.parts_y * c.t.parts_x * 8 * sizeof(float) + 255) / 256 * 256;
+}
+
 size_t pipe_bwd_workspace_bytes(const WarpShape& s)
 {
     PipePlan p;
     if (!plan_bwd(s, &p)) return 0;
-    // sized for the tile-by-tile layout (the chunked one needs less): independent of the schedule switch
-    return (size_t)s.N * s.gh * s.gw * p.cfg.t.parts_y * p.cfg.t.parts_x * 8 * sizeof(float);
+    return parts_bytes(s, p.cfg);
 }
 
 int launch_warp_bwd_pipe(const float* U, const float* Hs, const float* d_out, const float* d_img, const WarpShape& s, float* dU,
@@ -500,7 +523,7 @@ int launch_warp_bwd_pipe(const float* U, const float* Hs, const float* d_out, co
     const int cell_h = s.H / s.gh, cell_w = s.W / s.gw;
     const bool all_slots_written = (s.H % s.gh == 0) && (s.W % s.gw == 0) && (p.cfg.nty == s.gh * ((cell_h + kTH - 1) / kTH)) &&
                                    (p.cfg.ntx == s.gw * ((cell_w + kTW - 1) / kTW));
-    if (!all_slots_written && cudaMemsetAsync(parts, 0, pipe_bwd_workspace_bytes(s), st) != cudaSuccess)
+    if (!all_slots_written && cudaMemsetAsync(parts, 0, parts_bytes(s, p.cfg), st) != cudaSuccess)
         return set_error(MGW_ERR_CUDA, "memset parts: %s", cudaGetErrorString(cudaGetLastError()));
     if (s.C == 1) return launch_v<1, MGW_PIPE_BWD>(U, Hs, d_out, d_img, p, dU, parts, loss, st);
     if (s.C == 3) return launch_v<3, MGW_PIPE_BWD>(U, Hs, d_out, d_img, p, dU, parts, loss, st);

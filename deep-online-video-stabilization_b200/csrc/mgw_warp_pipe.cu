@@ -96,6 +96,7 @@ warp_fwd_pipe_kernel(const __grid_constant__ CUtensorMap mapU, const __grid_cons
     // programmatic dependent launch: everything above overlapped the previous kernel of the stream (K1 when called through
     // mgw_mesh_warp_fwd); nothing below may touch global memory before that kernel has completed
     griddep_wait();
+    griddep_launch_dependents();          // a programmatically launched successor (the backward pipeline) may set itself up under our tail
     const float stepx = lin_step(W), stepy = lin_step(H);
 
     if (warp == NCW) {

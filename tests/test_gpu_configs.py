@@ -125,9 +125,12 @@ def test_config3_c1_forward_and_backward(mgw, impl):
     up = dHs[sl].cpu().double()
     up[..., 8] = 0
     (ref.solve_h(th64) * up).sum().backward()
-    # (the adjoint solve amplifies the fp32 summation noise of dHs by the conditioning of the cell's 8x8 system; the generic
-    # family sums dHs with fp32 atomics in arbitrary order)
-    assert relmax(dth[sl].cpu().numpy(), th64.grad.numpy()) < 2e-4
+    # the adjoint solve on the SAME dHs (K4 alone), then the fused call's dtheta against it: the two calls are separate runs, and
+    # the generic family sums dHs with fp32 atomics in arbitrary order -- noise the adjoint solve amplifies by the conditioning
+    # of the cell's 8x8 system
+    dth2 = mgw.ops.solve_h_bwd(dev(theta), Hs, dHs)
+    assert relmax(dth2[sl].cpu().numpy(), th64.grad.numpy()) < 1e-4
+    assert relmax(dth.cpu().numpy(), dth2.cpu().numpy()) < (2e-3 if impl == 'generic' else 1e-4)
 
 
 # ------------------------------------------------------------------ loss epilogues on their PRODUCTION code paths
