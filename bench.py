@@ -197,25 +197,33 @@ def main():
         def step_eager(i):
             s = sets[i % nset]
             cur = torch.cuda.current_stream()
-            fill_mode = os.environ.get('BENCH_FILL', 'after_fwd')       # tuning aid: side | none (wrong dU) | serial | after_fwd
+            # dU of the step is zero-filled by the library's own kernel (evict_last: its lines are still in L2 when the backward's
+            # reductions arrive), INSIDE the timed step.  Placement is a tuning aid (BENCH_FILL): after_fwd = between forward
+            # and backward on the main stream (default: the measured best); with_k1 = on a side branch next to K1, joined before
+            # K2; side = on a side branch next to the whole forward; serial = before K1; none = no fill (wrong dU, timing only)
+            fill_mode = os.environ.get('BENCH_FILL', 'after_fwd')
             if fill_mode == 'serial':
                 ops.fill_zero(dU_buf, keep_in_l2=keep)
-            side.wait_stream(cur)
-            with torch.cuda.stream(side):
-                if fill_mode == 'side':
-                  # dU of the step: zero-filled by the library's own kernel on a side branch while the forward runs (evict_last: the
-                # lines are still in L2 when the backward's reductions arrive), then accumulated into (mgw_mesh_warp_bwd_acc).
-                # The fill is inside the timed step; it just does not sit on the critical path between forward and backward.
-                  ops.fill_zero(dU_buf, keep_in_l2=keep)
-            out, black, img, Hs = ops.mesh_warp_fwd(s['U'], s['theta'])
-            if fill_mode == 'after_fwd':
-                ops.fill_zero(dU_buf, keep_in_l2=keep)
+            if fill_mode in ('side', 'with_k1'):
+                side.wait_stream(cur)
+                with torch.cuda.stream(side):
+                    ops.fill_zero(dU_buf, keep_in_l2=keep)
+            if fill_mode == 'with_k1':
+                Hs = ops.solve_h_fwd(s['theta'])
+                cur.wait_stream(side)
+                out, black, img, _ = ops.warp_fwd(s['U'], Hs)
+            else:
+                out, black, img, Hs = ops.mesh_warp_fwd(s['U'], s['theta'])
             if world > 1 and not sync_reduce:
                 # head gradient (features^T . dtheta) and all-reduce of the PREVIOUS step on a high-priority side stream, forked
-                # AFTER the forward: the persistent forward kernel owns every SM with a static tile schedule (a CTA displaced by
-                # the NCCL kernel would finish late)
+                # right AFTER the forward and BEFORE the zero-fill: the persistent forward kernel owns every SM with a static tile
+                # schedule (a CTA displaced by the NCCL kernel would finish late), the fill's 64-thread blocks leave the SMs
+                # nearly empty, so the GEMM and the NCCL kernel become resident at once
                 reducer.launch(slot=(i - 1) % nset, features=feats, dtheta=dth_slots[(i - 1) % nset])
-            cur.wait_stream(side)
+            if fill_mode == 'after_fwd':
+                ops.fill_zero(dU_buf, keep_in_l2=keep)
+            if fill_mode == 'side':
+                cur.wait_stream(side)
             dU, dtheta = ops.mesh_warp_bwd(s['U'], s['theta'], Hs, s['d_out'], s['d_img'], accumulate_into=dU_buf,
                                            dtheta_out=dth_slots[i % nset])
             if world > 1 and sync_reduce:

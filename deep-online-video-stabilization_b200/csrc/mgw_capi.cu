@@ -177,10 +177,19 @@ static int warp_bwd_core(const float* U, const float* Hs, const float* d_out, co
     const bool tma_ok = mode != 1 && workspace && tma_bwd_supported(s) && aligned(U, 16) && (!dU || aligned(dU, 16)) &&
                         (!d_img || aligned(d_img, 8));
     // the persistent pipeline serves the calls that want dU (modes auto / pipe); dH-only calls and mode 2 take the tile kernels
-    static const bool prefer_tiles = [] { const char* v = getenv("MGW_BWD"); return v && v[0] == 't'; }();      // tuning aid: MGW_BWD=tile
-    const bool pipe_ok = mode != 1 && mode != 2 && !(prefer_tiles && mode == 0) && dU && workspace && pipe_bwd_supported(s) && aligned(U, 16) && aligned(dU, 16) &&
+    // auto takes the one-tile-per-CTA backward: on one GPU the two families are equally fast (73 us at config #2), but the tile
+    // kernel's 3072 short CTAs share the SMs gracefully with a concurrent NCCL kernel, while a CTA of the persistent pipeline
+    // that starts late finishes late (2 GPUs: 141 vs 146 us per step).  MGW_IMPL=pipe or MGW_BWD=pipe selects the pipeline.
+    static const bool prefer_pipe = [] { const char* v = getenv("MGW_BWD"); return v && v[0] == 'p'; }();
+    const bool pipe_ok = mode != 1 && mode != 2 && (prefer_pipe || mode == 3) && dU && workspace && pipe_bwd_supported(s) && aligned(U, 16) && aligned(dU, 16) &&
                          (!d_img || aligned(d_img, 8));
-    if (dU && zero_dU) TRY(launch_fill_zero(dU, sizeof(float) * (size_t)s.N * s.H * s.W * s.C, true, st));
+    if (dU && zero_dU) {
+        // the library's own fill (evict_last: the lines are still in L2 when the reductions arrive) where its 16-byte granularity
+        // fits, the driver's memset otherwise (odd sizes only occur on the generic path)
+        const size_t bytes = sizeof(float) * (size_t)s.N * s.H * s.W * s.C;
+        if (bytes % 16 == 0 && aligned(dU, 16)) TRY(launch_fill_zero(dU, bytes, true, st));
+        else TRY(check_memset(cudaMemsetAsync(dU, 0, bytes, st), "memset dU"));
+    }
     if (pipe_ok) {
         int np = 0;
         TRY(launch_warp_bwd_pipe(U, Hs, d_out, d_img, s, dU, (float*)workspace, &np, fl, st));

@@ -345,6 +345,7 @@ warp_bwd_tma_kernel(const __grid_constant__ CUtensorMap mapU, const __grid_const
         tma::mbar_init(bar, 1);
         tma::fence_barrier_init();
     }
+    griddep_launch_dependents();                      // K4 (launched programmatically) may run its factorisation under this kernel
     const Tile tl = this_tile(cfg);
     float Hc[9];
 #pragma unroll
@@ -415,12 +416,17 @@ warp_bwd_tma_kernel(const __grid_constant__ CUtensorMap mapU, const __grid_const
         for (int w = 0; w < NT / 32; ++w) mb = max(mb, (unsigned)__float_as_int(ti->wmax[w]));
         const float mm = __int_as_float((int)mb);
         const int e = (int)(mb >> 23) - 127;                                // floor(log2 mm) for normal mm; 128 for Inf/NaN
-        // quantum = 2^-22 of the tile's max|d_out| (tap weights are in [0,1] on this path, so |w*g*scale| < 2^22), 9 bits
-        // of headroom = up to 512 coincident full-size taps per word; tiles magnified beyond ~4x4 (area test) take the
-        // fp32 path instead
-        fixed = (mm > 0.0f) && (e > -100) && (e < 100) && ti->area_ok;
-        scale = __int_as_float((21 - e + 127) << 23);
-        inv_scale = __int_as_float((e - 21 + 127) << 23);
+        // |w*g*scale| < 2^kBits per term (tap weights are in [0,1] on this path).  A pixel adds at most ONE term to a word (its
+        // four taps are four different pixels), so a word receives at most TH*TW terms: with kBits = 31 - ceil(log2(TH*TW)) the
+        // int32 sum cannot overflow whatever the map does (no magnification heuristic); the quantum is 2^-kBits of the tile's
+        // max|d_out| (2^-20 for the 64 x 24 tile: a millionth, against a 1e-4 tolerance)
+        constexpr int kTerms = G::TH * TW;
+        // (never more than 22: fixed_of()'s magic-number rounding holds |v| <= 2^22)
+        constexpr int kBits = 31 - (kTerms <= 512 ? 9 : kTerms <= 1024 ? 10 : kTerms <= 2048 ? 11 : 12);
+        static_assert(kTerms <= 4096 && kBits <= 22, "fixed-point headroom");
+        fixed = (mm > 0.0f) && (e > -100) && (e < 100);
+        scale = __int_as_float((kBits - 1 - e + 127) << 23);
+        inv_scale = __int_as_float((e - (kBits - 1) + 127) << 23);
     }
 
     const float xt = lin_at(col, stepx);
