@@ -351,11 +351,6 @@ warp_bwd_pipe_kernel(const __grid_constant__ CUtensorMap mapU, const float* __re
                 }
                 accumulate_dh_r(dh, fmaf(gx, halfW, gicur[k][0]), fmaf(gy, halfH, gicur[k][1]), xn[k], yn[k], rz[k], xt,
                                 lin_at(row0 + k, stepy));
-#ifndef MGW_PB_NOFENCE
-                // keep the pixels' gather / scatter groups apart: a pixel already offers 12 independent loads and 12 independent
-                // chains; interleaving three of them only drives ptxas into spilling (no L1 to speak of next to 227 KB of smem)
-                asm volatile("" ::: "memory");
-#endif
             }
         } else {
             const float* Un = U + (size_t)in->n * H * W * C;

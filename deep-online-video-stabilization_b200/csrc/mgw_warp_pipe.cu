@@ -63,6 +63,9 @@ struct FwdLayout {
     static_assert(kInfoRing == 2 * kRoundTiles && S <= kRoundTiles / 2, "a record must outlive its tile");
 };
 
+#ifndef MGW_PRODUCER_HINT
+#define MGW_PRODUCER_HINT 2000      // ns the producer may sleep between two looks at `empty` (0 = plain try_wait loop)
+#endif
 #ifndef MGW_PIPE_FWD_MINB
 #define MGW_PIPE_FWD_MINB 3
 #endif
@@ -119,7 +122,11 @@ warp_fwd_pipe_kernel(const __grid_constant__ CUtensorMap mapU, const __grid_cons
             if (lane == 0) {
                 const int s = it % S;
                 const PInfo* in = info + (it % kInfoRing);
-                tma::mbar_wait_hint(empty + s, ((it / S) & 1) ^ 1, 2000);
+                #if MGW_PRODUCER_HINT > 0
+                tma::mbar_wait_hint(empty + s, ((it / S) & 1) ^ 1, MGW_PRODUCER_HINT);
+#else
+                tma::mbar_wait(empty + s, ((it / S) & 1) ^ 1);
+#endif
                 tma::mbar_expect_tx(full + s, (uint32_t)(G::kBoxF * 4));
                 tma::load_3d(s_src + (size_t)s * G::kBoxF, &mapU, full + s, in->bx0 * C, in->by0, in->n);
             }
