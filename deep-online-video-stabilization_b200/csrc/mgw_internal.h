@@ -72,6 +72,14 @@ int launch_temp_loss_bwd(const float* out1, const float* black1, const float* ou
                          const float* flow, const float* sums, float upstream, const float* up_dev, int N, int H, int W, int C,
                          float* d_out1, float* d_out2, cudaStream_t st);
 
+// mgw_loss_tile.cu : temp_loss on TMA-staged tiles (locally compact flow fields; per-pixel fallback inside)
+bool temp_loss_tile_supported(const float* out2, const float* black2, const float* d_out2, int N, int H, int W, int C);
+int launch_temp_loss_tile_fwd(const float* out1, const float* black1, const float* out2, const float* black2, const float* flow, int N,
+                              int H, int W, int C, float* sums, cudaStream_t st);
+int launch_temp_loss_tile_bwd(const float* out1, const float* black1, const float* out2, const float* black2, const float* flow,
+                              const float* sums, float upstream, const float* up_dev, int N, int H, int W, int C, float* d_out1,
+                              float* d_out2, cudaStream_t st);
+
 // mgw_warp_tma.cu : TMA-staged tiles (fast path)
 struct FusedImgLoss {            // img_loss fused onto the warp (s_net_bundle_nobm.py:347-352)
     const float* out;            // backward: the forward's output_img

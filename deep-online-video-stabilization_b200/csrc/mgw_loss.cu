@@ -4,6 +4,8 @@
 //   temp_loss     train_bundle_nobm.py:115-125 (two interpolate() passes + masked MSE in ONE kernel)
 // Forward kernels produce the per-sample partial sums the losses are built from; the final O(N) scalar
 // arithmetic (s0/(s1+1e-8), /batch) is left to the caller so the multi-GPU path can divide by the GLOBAL batch.
+#include <cstdlib>
+
 #include "mgw_internal.h"
 
 namespace mgw {
@@ -264,6 +266,10 @@ int launch_temp_loss_fwd(const float* out1, const float* black1, const float* ou
                          const float* flow, int N, int H, int W, int C, float* sums, cudaStream_t st)
 {
     cudaMemsetAsync(sums, 0, sizeof(float) * 2 * N, st);
+    // (the tiled kernel of mgw_loss_tile.cu also has a forward, MGW_LOSS_TILE=fwd; measured at config #2 size it is no faster
+    // than this per-pixel kernel -- 68 vs 66 us at C = 3: the forward has no scatter to win on)
+    if (impl_mode() != 1 && getenv("MGW_LOSS_TILE") && getenv("MGW_LOSS_TILE")[0] == 'f' && temp_loss_tile_supported(out2, black2, out2, N, H, W, C))
+        return launch_temp_loss_tile_fwd(out1, black1, out2, black2, flow, N, H, W, C, sums, st);
     launch_temp_loss<false>(C, dim3(blocks_iters(H * W, N, 5, MGW_LOSS_ITERS), N), st, out1, black1, out2, black2, flow, nullptr, 0.0f, nullptr, N, H, W,
                             sums, nullptr, nullptr);
     return check_launch("temp_loss_fwd");
@@ -273,6 +279,13 @@ int launch_temp_loss_bwd(const float* out1, const float* black1, const float* ou
                          const float* flow, const float* sums, float upstream, const float* up_dev, int N, int H, int W, int C,
                          float* d_out1, float* d_out2, cudaStream_t st)
 {
+    // tiles pay where the scatter dominates: 12 atomics per pixel at C = 3 (220 -> 105 us at config #2 size incl. the zero-fill);
+    // at C = 1 the per-pixel kernel's 4 global atomics are cheaper than staging the boxes (60 vs 70 us)
+    if (impl_mode() != 1 && C >= 3 && temp_loss_tile_supported(out2, black2, d_out2, N, H, W, C)) {
+        const int rc = launch_fill_zero(d_out2, sizeof(float) * (size_t)N * H * W * C, true, st);      // W % 4 == 0: a multiple of 16 bytes
+        if (rc != MGW_OK) return rc;
+        return launch_temp_loss_tile_bwd(out1, black1, out2, black2, flow, sums, upstream, up_dev, N, H, W, C, d_out1, d_out2, st);
+    }
     cudaMemsetAsync(d_out2, 0, sizeof(float) * (size_t)N * H * W * C, st);
     launch_temp_loss<true>(C, dim3(blocks_iters(H * W, N, 4, MGW_LOSS_ITERS), N), st, out1, black1, out2, black2, flow, sums, upstream, up_dev, N, H, W,
                            nullptr, d_out1, d_out2);

@@ -178,6 +178,27 @@ def test_temp_loss_production_path(mgw, c):
     assert relmax(b2.grad.cpu().numpy(), b64.grad.numpy()) < 1e-4
 
 
+@pytest.mark.parametrize('c', [1, 3])
+@pytest.mark.parametrize('wild', [False, True])
+def test_temp_loss_partial_tiles_and_fallback(mgw, c, wild):
+    """the tiled temp_loss on an image that is no multiple of its 32 x 24 tiles, with a compact flow (boxes fit: shared-memory
+    path) and with a flow that jumps all over the frame (boxes do not fit: per-pixel fallback inside the same kernel), forward
+    and backward against the fp64 port"""
+    n, h, w = 2, 100, 132
+    out1, out2, _, black1, black2, flow = _loss_inputs(n, h, w, c, 620 + c)
+    if wild:
+        flow = np.random.RandomState(7).uniform(-1.2, 1.2, flow.shape).astype(np.float32)
+    a, b2 = dev(out1).requires_grad_(True), dev(out2).requires_grad_(True)
+    loss = mgw.temp_loss(a, dev(black1), b2, dev(black2), dev(flow))
+    loss.backward()
+    a64, b64 = t64(out1, True), t64(out2, True)
+    l64 = ref.temp_loss(a64, t64(black1), b64, t64(black2), t64(flow))
+    l64.backward()
+    assert abs(float(loss) - float(l64)) <= 2e-5 * abs(float(l64))
+    assert relmax(a.grad.cpu().numpy(), a64.grad.numpy()) < 1e-4
+    assert relmax(b2.grad.cpu().numpy(), b64.grad.numpy()) < 1e-4
+
+
 def test_feature_loss_production_path(mgw):
     n, h, w, m = 4, 288, 512, 3000
     r = np.random.RandomState(540)
