@@ -199,9 +199,10 @@ def main():
             cur = torch.cuda.current_stream()
             # dU of the step is zero-filled by the library's own kernel (evict_last: its lines are still in L2 when the backward's
             # reductions arrive), INSIDE the timed step.  Placement is a tuning aid (BENCH_FILL): after_fwd = between forward
-            # and backward on the main stream (default: the measured best); with_k1 = on a side branch next to K1, joined before
-            # K2; side = on a side branch next to the whole forward; serial = before K1; none = no fill (wrong dU, timing only)
-            fill_mode = os.environ.get('BENCH_FILL', 'after_fwd')
+            # and backward on the main stream; with_k1 = on a side branch next to K1, joined before K2; side = on a side branch next
+            # to the whole forward; serial = before K1; none = no fill (wrong dU, timing only); fused (default) = no fill here at
+            # all: the plain backward entry point zero-fills dU itself (under the backward pipeline's own shadow when that runs)
+            fill_mode = os.environ.get('BENCH_FILL', 'fused')
             if fill_mode == 'serial':
                 ops.fill_zero(dU_buf, keep_in_l2=keep)
             if fill_mode in ('side', 'with_k1'):
@@ -224,8 +225,11 @@ def main():
                 ops.fill_zero(dU_buf, keep_in_l2=keep)
             if fill_mode == 'side':
                 cur.wait_stream(side)
-            dU, dtheta = ops.mesh_warp_bwd(s['U'], s['theta'], Hs, s['d_out'], s['d_img'], accumulate_into=dU_buf,
-                                           dtheta_out=dth_slots[i % nset])
+            if fill_mode == 'fused':
+                dU, dtheta = ops.mesh_warp_bwd(s['U'], s['theta'], Hs, s['d_out'], s['d_img'], dU_out=dU_buf, dtheta_out=dth_slots[i % nset])
+            else:
+                dU, dtheta = ops.mesh_warp_bwd(s['U'], s['theta'], Hs, s['d_out'], s['d_img'], accumulate_into=dU_buf,
+                                               dtheta_out=dth_slots[i % nset])
             if world > 1 and sync_reduce:
                 reducer.launch(slot=i % nset, features=feats, dtheta=dth_slots[i % nset])
             if world > 1:

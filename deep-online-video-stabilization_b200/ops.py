@@ -156,14 +156,20 @@ def mesh_warp_fwd(U, theta, want_out=True, want_black=True, want_img=True):
     return out, black, img, Hs
 
 
-def mesh_warp_bwd(U, theta, Hs, d_out, d_img=None, want_dU=True, accumulate_into=None, dtheta_out=None):
-    """dtheta_out: optional preallocated [N,gh+1,gw+1,2] tensor to receive dtheta (static buffers for CUDA-graph pipelines)."""
+def mesh_warp_bwd(U, theta, Hs, d_out, d_img=None, want_dU=True, accumulate_into=None, dtheta_out=None, dU_out=None):
+    """dtheta_out / dU_out: optional preallocated tensors to receive dtheta / dU (static buffers for CUDA-graph pipelines);
+    accumulate_into: dU += gradient into the caller's tensor instead (never zero-filled by the library)."""
     U, theta, Hs, d_out = _chk(U, 'U'), _chk(theta, 'theta'), _chk(Hs, 'Hs'), _chk(d_out, 'd_out')
     d_img = None if d_img is None else _chk(d_img, 'd_img')
     n, h, w, c = _mesh_dims(U, theta, 'theta')
     gh, gw = Hs.shape[1:3]
     acc = accumulate_into is not None
-    dU = _acc_target(U, accumulate_into) if acc else (torch.empty_like(U) if want_dU else None)
+    if acc:
+        dU = _acc_target(U, accumulate_into)
+    elif dU_out is not None:
+        dU = _acc_target(U, dU_out)
+    else:
+        dU = torch.empty_like(U) if want_dU else None
     if dtheta_out is not None:
         dtheta = _chk(dtheta_out, 'dtheta_out')
         if dtheta.shape != theta.shape or not dtheta_out.is_contiguous():
