@@ -221,6 +221,7 @@ __device__ __forceinline__ void group_getrs(const T* __restrict__ LU, const int 
 
 constexpr int kCellsPerBlock = 16;      // 128 threads
 
+template <bool REDUNDANT_LU>
 __global__ void __launch_bounds__(kCellsPerBlock * 8)
 solve_h_fwd_kernel(const float* __restrict__ theta, int N, int gh, int gw, float* __restrict__ Hs)
 {
@@ -235,23 +236,37 @@ solve_h_fwd_kernel(const float* __restrict__ theta, int N, int gh, int gw, float
     const int n = cell / (gh * gw), ij = cell % (gh * gw), i = ij / gw, j = ij % gw;
     const float* theta_n = theta + (size_t)n * (gh + 1) * (gw + 1) * 2;
 
-    float row[8], b; int piv[8];
-    dlt_row<float>(theta_n, i, j, gh, gw, g, row, b);
-    group_lu<float>(row, piv, g);
+    float col[8], bk[8];
+    if (REDUNDANT_LU) {
+        // every lane of the group factorises the whole system in its own registers (no shuffles on the pivot chain), then
+        // lane g solves for column g of the inverse
+        float M[8][8]; int piv[8];
 #pragma unroll
-    for (int c = 0; c < 8; ++c) sLU[slot][g * 8 + c] = row[c];
-    __syncwarp();
-    float col[8];
+        for (int r = 0; r < 8; ++r) dlt_row<float>(theta_n, i, j, gh, gw, r, M[r], bk[r]);
+        lu8<float>(M, piv);
 #pragma unroll
-    for (int r = 0; r < 8; ++r) col[r] = (r == g) ? 1.0f : 0.0f;
-    group_getrs<float>(sLU[slot], piv, col);
+        for (int r = 0; r < 8; ++r) col[r] = (r == g) ? 1.0f : 0.0f;
+        getrs8<float>(M, piv, col);
+    } else {
+        float row[8], b; int piv[8];
+        dlt_row<float>(theta_n, i, j, gh, gw, g, row, b);
+        group_lu<float>(row, piv, g);
+#pragma unroll
+        for (int c = 0; c < 8; ++c) sLU[slot][g * 8 + c] = row[c];
+        __syncwarp();
+#pragma unroll
+        for (int r = 0; r < 8; ++r) col[r] = (r == g) ? 1.0f : 0.0f;
+        group_getrs<float>(sLU[slot], piv, col);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) bk[k] = __shfl_sync(0xffffffffu, b, k, 8);
+    }
 #pragma unroll
     for (int r = 0; r < 8; ++r) sINV[slot][r * 8 + g] = col[r];
     __syncwarp();
     // matmul(pinv(A), b): FMA chain over k (spatial_transformer3.py:173)
-    float acc = __fmul_rn(sINV[slot][g * 8], __shfl_sync(0xffffffffu, b, 0, 8));
+    float acc = __fmul_rn(sINV[slot][g * 8], bk[0]);
 #pragma unroll
-    for (int k = 1; k < 8; ++k) acc = __fmaf_rn(sINV[slot][g * 8 + k], __shfl_sync(0xffffffffu, b, k, 8), acc);
+    for (int k = 1; k < 8; ++k) acc = __fmaf_rn(sINV[slot][g * 8 + k], bk[k], acc);
     if (live) {
         Hs[(size_t)cell * 9 + g] = acc;
         if (g == 0) Hs[(size_t)cell * 9 + 8] = 1.0f;
@@ -260,49 +275,67 @@ solve_h_fwd_kernel(const float* __restrict__ theta, int N, int gh, int gw, float
 
 // ---------------------------------------------------------------- K4: adjoint of the solve
 // dHs_part [N*gh*gw, nparts, part_stride] tile partials (nparts may be 1) -> dtheta [N,gh+1,gw+1,2].
-// One thread per cell, fp64: g = sum of the partials, lambda = (A+1e-4 I)^-T g by a fresh pivoted LU of the transposed
+// One thread per cell, fp64 (eight for the sum of the partials): g = sum of the partials, lambda = (A+1e-4 I)^-T g by a fresh pivoted LU of the transposed
 // system, d u_k = lambda_k * s_k, d v_k = lambda_{4+k} * s_k with s_k = 1 + h6 x_k + h7 y_k; then
 // each vertex gathers its (up to) four cells in a fixed order -> deterministic, no atomics.  One block per sample.
 __global__ void solve_h_bwd_kernel(const float* __restrict__ theta, const float* __restrict__ Hs,
                                    const float* __restrict__ dHs_part, int nparts, int part_stride,
                                    int N, int gh, int gw, float* __restrict__ dtheta)
 {
-    extern __shared__ double sDuv[];                   // [gh*gw][8]  (du0..3, dv0..3)
+    extern __shared__ double sDuv[];                   // [gh*gw][8]  (du0..3, dv0..3), then [gh*gw][8] summed partials
     const int ncell_s = gh * gw;
+    double* sRhs = sDuv + (size_t)ncell_s * 8;
     const int n = blockIdx.x;
     const float* theta_n = theta + (size_t)n * (gh + 1) * (gw + 1) * 2;
-    for (int ij = threadIdx.x; ij < ncell_s; ij += blockDim.x) {
+    for (int base = 0; base < ncell_s; base += blockDim.x) {
+        const int ij = base + threadIdx.x;
+        const bool live = ij < ncell_s;
         const int i = ij / gw, j = ij % gw;
         const size_t cell = (size_t)n * ncell_s + ij;
-        double Mt[8][8], rhs[8];
+        double Mt[8][8], rhs[8], h6 = 0, h7 = 0;
         int piv[8];
+        if (live) {
+            h6 = Hs[cell * 9 + 6]; h7 = Hs[cell * 9 + 7];      // written two kernels back (K1): complete under any launch form
 #pragma unroll
-        for (int r = 0; r < 8; ++r) {
-            double row[8], bdummy;
-            dlt_row<double>(theta_n, i, j, gh, gw, r, row, bdummy);
+            for (int r = 0; r < 8; ++r) {
+                double row[8], bdummy;
+                dlt_row<double>(theta_n, i, j, gh, gw, r, row, bdummy);
 #pragma unroll
-            for (int c = 0; c < 8; ++c) Mt[c][r] = row[c];
+                for (int c = 0; c < 8; ++c) Mt[c][r] = row[c];
+            }
+            lu8<double>(Mt, piv);
         }
-        lu8<double>(Mt, piv);
         // the factorisation needs theta only: under a programmatic dependent launch it runs while the backward warp kernel is
         // still busy; the tile partials are read after that kernel has completed
-        griddep_wait();
-#pragma unroll
-        for (int r = 0; r < 8; ++r) rhs[r] = 0;
-        for (int p = 0; p < nparts; ++p) {
-            const float* src = dHs_part + (cell * nparts + p) * part_stride;
-#pragma unroll
-            for (int r = 0; r < 8; ++r) rhs[r] += (double)__ldcg(src + r);
+        if (base == 0) griddep_wait();
+        // the partials of this round's cells, summed by all threads of the block: one (cell, component) pair per thread, every
+        // load independent of the others (a one-thread-per-cell loop pays one L2 round trip per partial)
+        const int cells_here = min((int)blockDim.x, ncell_s - base);
+        for (int e = threadIdx.x; e < cells_here * 8; e += blockDim.x) {
+            const float* src = dHs_part + (((size_t)n * ncell_s + base + (e >> 3)) * nparts) * part_stride + (e & 7);
+            double s0 = 0, s1 = 0, s2 = 0, s3 = 0;
+            int p = 0;
+            for (; p + 4 <= nparts; p += 4) {
+                const float a = __ldcg(src + (size_t)p * part_stride), b = __ldcg(src + (size_t)(p + 1) * part_stride);
+                const float c = __ldcg(src + (size_t)(p + 2) * part_stride), d = __ldcg(src + (size_t)(p + 3) * part_stride);
+                s0 += (double)a; s1 += (double)b; s2 += (double)c; s3 += (double)d;
+            }
+            for (; p < nparts; ++p) s0 += (double)__ldcg(src + (size_t)p * part_stride);
+            sRhs[(size_t)(base + (e >> 3)) * 8 + (e & 7)] = (s0 + s1) + (s2 + s3);
         }
-        getrs8<double>(Mt, piv, rhs);                  // rhs -> lambda
-        const double h6 = Hs[cell * 9 + 6], h7 = Hs[cell * 9 + 7];
+        __syncthreads();
+        if (live) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            float xf, yf; int vid;
-            cell_corner(i, j, gh, gw, k, xf, yf, vid);
-            const double s = 1.0 + h6 * (double)xf + h7 * (double)yf;
-            sDuv[(size_t)ij * 8 + k] = rhs[k] * s;
-            sDuv[(size_t)ij * 8 + 4 + k] = rhs[4 + k] * s;
+            for (int r = 0; r < 8; ++r) rhs[r] = sRhs[(size_t)ij * 8 + r];
+            getrs8<double>(Mt, piv, rhs);                  // rhs -> lambda
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                float xf, yf; int vid;
+                cell_corner(i, j, gh, gw, k, xf, yf, vid);
+                const double s = 1.0 + h6 * (double)xf + h7 * (double)yf;
+                sDuv[(size_t)ij * 8 + k] = rhs[k] * s;
+                sDuv[(size_t)ij * 8 + 4 + k] = rhs[4 + k] * s;
+            }
         }
     }
     __syncthreads();
@@ -339,7 +372,10 @@ int launch_vertices_bwd(const float* head, const float* d_pts2, const float* d_p
 int launch_solve_h_fwd(const float* theta, int N, int gh, int gw, float* Hs, cudaStream_t st)
 {
     const int ncell = N * gh * gw;
-    solve_h_fwd_kernel<<<(ncell + kCellsPerBlock - 1) / kCellsPerBlock, kCellsPerBlock * 8, 0, st>>>(theta, N, gh, gw, Hs);
+    static const bool group = [] { const char* v = getenv("MGW_K1"); return v && v[0] == 'g'; }();
+    const int blocks = (ncell + kCellsPerBlock - 1) / kCellsPerBlock;
+    if (group) solve_h_fwd_kernel<false><<<blocks, kCellsPerBlock * 8, 0, st>>>(theta, N, gh, gw, Hs);
+    else solve_h_fwd_kernel<true><<<blocks, kCellsPerBlock * 8, 0, st>>>(theta, N, gh, gw, Hs);
     return check_launch("solve_h_fwd");
 }
 
@@ -347,10 +383,11 @@ int launch_solve_h_bwd(const float* theta, const float* Hs, const float* dHs_par
                        int N, int gh, int gw, float* dtheta, cudaStream_t st, bool after_own_warp_kernel)
 {
     const int ncell_s = gh * gw;
-    int threads = ((ncell_s > (gh + 1) * (gw + 1) * 2 ? ncell_s : (gh + 1) * (gw + 1) * 2) + 31) / 32 * 32;
+    // 8 threads per cell for the sum of the partials (one thread per cell for the solve itself)
+    int threads = ((ncell_s * 8 > (gh + 1) * (gw + 1) * 2 ? ncell_s * 8 : (gh + 1) * (gw + 1) * 2) + 31) / 32 * 32;
     if (threads > 128) threads = 128;
-    const size_t smem = (size_t)ncell_s * 8 * sizeof(double);
-    if (smem > 48 * 1024) return set_error(MGW_ERR_UNSUPPORTED, "solve_h_bwd: grid too large (gh*gw > 768)");
+    const size_t smem = (size_t)ncell_s * 16 * sizeof(double);
+    if (smem > 48 * 1024) return set_error(MGW_ERR_UNSUPPORTED, "solve_h_bwd: grid too large (gh*gw > 384)");
     // after_own_warp_kernel: the previous kernel of the stream is this library's backward warp kernel, which read Hs itself and
     // releases its dependents at once: launch programmatically, the factorisation overlaps it
     const cudaError_t e = launch_ex(solve_h_bwd_kernel, dim3(N), dim3(threads), smem, st, after_own_warp_kernel && pdl_enabled(),
