@@ -181,8 +181,9 @@ static int warp_bwd_core(const float* U, const float* Hs, const float* d_out, co
     // kernel's 3072 short CTAs share the SMs gracefully with a concurrent NCCL kernel, while a CTA of the persistent pipeline
     // that starts late finishes late (2 GPUs: 141 vs 146 us per step).  MGW_IMPL=pipe or MGW_BWD=pipe selects the pipeline.
     static const bool prefer_pipe = [] { const char* v = getenv("MGW_BWD"); return v && v[0] == 'p'; }();
+    // (a fused img_loss with a second gradient on `output` is served by the tile kernels)
     const bool pipe_ok = mode != 1 && mode != 2 && (prefer_pipe || mode == 3) && dU && workspace && pipe_bwd_supported(s) && aligned(U, 16) && aligned(dU, 16) &&
-                         (!d_img || aligned(d_img, 8));
+                         (!d_img || aligned(d_img, 8)) && !(fl && d_out);
     if (dU && zero_dU) {
         // the library's own fill (evict_last: the lines are still in L2 when the reductions arrive) where its 16-byte granularity
         // fits, the driver's memset otherwise (odd sizes only occur on the generic path)
@@ -208,7 +209,8 @@ static int warp_bwd_core(const float* U, const float* Hs, const float* d_out, co
     TRY(check_memset(cudaMemsetAsync(dHs_acc, 0, sizeof(float) * ncell * 9, st), "memset dHs"));
     if (fl) {       // generic path: materialise d_out of the fused loss first
         if (!d_out_scratch) return set_error(MGW_ERR_INVALID, "fused img_loss backward: workspace too small for the generic path");
-        TRY(launch_img_loss_bwd(fl->out, fl->y, fl->black, fl->sums, fl->kscale * 0.5f * (float)s.N, fl->kscale_dev, s.N, s.H, s.W, s.C, d_out_scratch, st));
+        TRY(launch_img_loss_bwd(fl->out, fl->y, fl->black, fl->sums, fl->kscale * 0.5f * (float)s.N, fl->kscale_dev, s.N, s.H, s.W, s.C, d_out_scratch, st,
+                                d_out /* a second gradient on `output`, nullable */));
         d_out = d_out_scratch;
     }
     TRY(launch_warp_bwd_generic(U, Hs, d_out, d_img, s, false, dU, dHs_acc, st));
@@ -320,7 +322,8 @@ size_t mgw_mesh_warp_img_loss_bwd_workspace_bytes(int N, int H, int W, int C, in
 
 int mgw_mesh_warp_img_loss_bwd(const float* U, const float* theta, const float* Hs, const float* out, const float* y,
                                const float* black, const float* sums, float upstream, const float* upstream_dev, float batch, const float* d_img,
-                               int N, int H, int W, int C, int gh, int gw, float* dU, float* dtheta, void* workspace, void* stream)
+                               const float* d_out_extra, int N, int H, int W, int C, int gh, int gw, float* dU, float* dtheta,
+                               void* workspace, void* stream)
 {
     REQUIRE(U && theta && Hs && out && y && black && sums && dtheta && workspace, "mgw_mesh_warp_img_loss_bwd: null pointer");
     TRY(validate_mesh_shape("mgw_mesh_warp_img_loss_bwd", N, H, W, C, gh, gw));
@@ -335,8 +338,116 @@ int mgw_mesh_warp_img_loss_bwd(const float* U, const float* theta, const float* 
     float* scratch = (float*)((char*)workspace + base);
     const FusedImgLoss fl{out, y, black, sums, upstream * 2.0f / batch, upstream_dev};
     const float* parts; int np, ps;
-    TRY(warp_bwd_core(U, Hs, nullptr, d_img, s, dU, dHs_acc, tma_ws, &parts, &np, &ps, st, &fl, scratch));
+    TRY(warp_bwd_core(U, Hs, d_out_extra, d_img, s, dU, dHs_acc, tma_ws, &parts, &np, &ps, st, &fl, scratch));
     return launch_solve_h_bwd(theta, Hs, parts, np, ps, N, gh, gw, dtheta, st, ps == 8);
+}
+
+int mgw_feature_loss_dh(const float* matches, const float* mask, const float* img, const float* Hs, const float* facc, float upstream,
+                        const float* upstream_dev, int N, int M, int H, int W, int gh, int gw, float* dH_part, void* stream)
+{
+    REQUIRE(matches && mask && img && Hs && facc && dH_part, "mgw_feature_loss_dh: null pointer");
+    REQUIRE(N > 0 && N <= 65535 && M > 0 && H > 1 && W > 1 && gh > 0 && gw > 0 && gh <= H && gw <= W, "mgw_feature_loss_dh: bad sizes");
+    REQUIRE(aligned(matches, 16) && aligned(img, 8), "mgw_feature_loss_dh: alignment");
+    return launch_feature_dh(matches, mask, img, Hs, facc, upstream, upstream_dev, N, M, H, W, gh, gw, dH_part, (cudaStream_t)stream);
+}
+
+int mgw_loss_ratio_sum(const float* sums, int N, int clamp, float scale, float* out, void* stream)
+{
+    REQUIRE(sums && out && N > 0, "mgw_loss_ratio_sum: null pointer or N <= 0");
+    return launch_ratio_sum(sums, N, clamp != 0, scale, out, (cudaStream_t)stream);
+}
+
+// ------------------------------------------------------------------------------------------------ one training pass
+// coef (host, 11 floats) = PassCoef: v[4], img, feat, regu, theta_share, grid_theta_share, inv_batch, gate
+static mgw::PassCoef pass_coef(const float* c)
+{
+    mgw::PassCoef p;
+    for (int k = 0; k < 4; ++k) p.v[k] = c[k];
+    p.img = c[4]; p.feat = c[5]; p.regu = c[6]; p.theta_share = c[7]; p.grid_theta_share = c[8]; p.inv_batch = c[9]; p.gate = c[10];
+    return p;
+}
+
+int mgw_train_pass_fwd(const float* head, const float* U, const float* y, const float* matches, const float* mask, const float* regu_dev,
+                       const float* coef, int N, int H, int W, int C, int gh, int gw, int M, float do_crop_rate, float* pts1, float* pts2,
+                       float* Hs, float* out, float* black, float* img, float* acc, float* warpped, float* vsums, float* result,
+                       void* stream)
+{
+    REQUIRE(head && U && y && matches && mask && coef && pts1 && pts2 && Hs && out && black && img && acc && vsums && result,
+            "mgw_train_pass_fwd: null pointer");
+    TRY(validate_mesh_shape("mgw_train_pass_fwd", N, H, W, C, gh, gw));
+    REQUIRE(M > 0 && N <= 65535 && do_crop_rate > 0.0f, "mgw_train_pass_fwd: need M > 0, N <= 65535, do_crop_rate > 0");
+    REQUIRE(aligned(matches, 16) && aligned(img, 8) && (!warpped || aligned(warpped, 8)), "mgw_train_pass_fwd: alignment");
+    cudaStream_t st = (cudaStream_t)stream;
+    const WarpShape s{N, H, W, C, H, W, gh, gw};
+    const PassCoef pc = pass_coef(coef);
+    TRY(launch_vertices_fwd(head, N, gh, gw, do_crop_rate, pts2, pts1, st));                 // get_4_pts          :29-71
+    TRY(launch_solve_h_fwd(pts2, N, gh, gw, Hs, st));                                        // get_Hs             st3:144-198
+    TRY(check_memset(cudaMemsetAsync(acc, 0, sizeof(float) * 4 * N, st), "memset acc"));     // img sums [N,2] | feature sums [N,2]
+    int rc = MGW_OK;
+    if (use_tma_fwd(s, U, out, black, img, &rc)) {                                           // transformer + img_loss  :332,:347-352
+        TRY(launch_warp_fwd_tma(U, Hs, s, out, black, img, y, acc, st));
+    } else {
+        if (rc != MGW_OK) return rc;
+        TRY(launch_warp_fwd_generic(U, Hs, s, false, out, black, img, nullptr, st));
+        TRY(launch_img_loss_fwd(out, y, black, N, H, W, C, acc, st));
+    }
+    TRY(launch_feature_acc_fwd(matches, mask, img, N, M, H, W, warpped, acc + 2 * (size_t)N, st));      // feature_loss  :335-343
+    TRY(launch_vertex_losses_fwd(head, pts1, pts2, N, gh, gw, do_crop_rate, vsums, nullptr, st));       // :139-210,:246
+    return launch_objective_fwd(acc, acc + 2 * (size_t)N, vsums, regu_dev, N, pc, result, st);           // :308-317,:354-359
+}
+
+static size_t pass_bwd_offsets(int N, int H, int W, int C, int gh, int gw, size_t* extra, size_t* dp2, size_t* dp1)
+{
+    size_t off = mgw::align_up(mgw_mesh_warp_img_loss_bwd_workspace_bytes(N, H, W, C, gh, gw), 256);
+    *extra = off; off += mgw::align_up(sizeof(float) * (size_t)N * gh * gw * 8, 256);
+    *dp2 = off; off += mgw::align_up(sizeof(float) * (size_t)N * (gh + 1) * (gw + 1) * 2, 256);
+    *dp1 = off; off += mgw::align_up(sizeof(float) * (size_t)N * gh * gw * 8, 256);
+    return off;
+}
+
+size_t mgw_train_pass_bwd_workspace_bytes(int N, int H, int W, int C, int gh, int gw)
+{
+    size_t a, b, c;
+    return pass_bwd_offsets(N, H, W, C, gh, gw, &a, &b, &c);
+}
+
+int mgw_train_pass_bwd(const float* head, const float* pts1, const float* pts2, const float* U, const float* y, const float* matches,
+                       const float* mask, const float* Hs, const float* out, const float* black, const float* img, const float* acc,
+                       const float* g_total_dev, const float* d_out_extra, const float* coef, int N, int H, int W, int C, int gh, int gw,
+                       int M, float do_crop_rate, float* dU, float* d_head, void* workspace, void* stream)
+{
+    REQUIRE(head && pts1 && pts2 && U && y && matches && mask && Hs && out && black && img && acc && coef && d_head && workspace,
+            "mgw_train_pass_bwd: null pointer");
+    TRY(validate_mesh_shape("mgw_train_pass_bwd", N, H, W, C, gh, gw));
+    REQUIRE(M > 0 && N <= 65535 && do_crop_rate > 0.0f, "mgw_train_pass_bwd: need M > 0, N <= 65535, do_crop_rate > 0");
+    REQUIRE(aligned(workspace, 256) && aligned(matches, 16) && aligned(img, 8), "mgw_train_pass_bwd: alignment");
+    cudaStream_t st = (cudaStream_t)stream;
+    const WarpShape s{N, H, W, C, H, W, gh, gw};
+    const PassCoef pc = pass_coef(coef);
+    size_t o_extra, o_dp2, o_dp1;
+    pass_bwd_offsets(N, H, W, C, gh, gw, &o_extra, &o_dp2, &o_dp1);
+    float* extra = (float*)((char*)workspace + o_extra);
+    float* d_pts2 = (float*)((char*)workspace + o_dp2);
+    float* d_pts1 = (float*)((char*)workspace + o_dp1);
+    // feature_loss backward straight to one dH partial per cell (no dense d(flow map))
+    TRY(launch_feature_dh(matches, mask, img, Hs, acc + 2 * (size_t)N, pc.gate * pc.feat * (float)N * pc.inv_batch, g_total_dev, N, M, H, W, gh, gw,
+                          extra, st));
+    // warp backward with the img_loss gradient formed in registers (+ the gradient of another consumer of `output`)
+    float* dHs_acc = (float*)workspace;
+    const size_t off = align_up(sizeof(float) * (size_t)N * gh * gw * 9, 256);
+    const size_t tma_bytes = mgw_warp_bwd_workspace_bytes(N, H, W, C, gh, gw);
+    void* tma_ws = tma_bytes ? (void*)((char*)workspace + off) : nullptr;
+    const size_t base = align_up(mgw_mesh_warp_bwd_workspace_bytes(N, H, W, C, gh, gw), 256);
+    float* scratch = (float*)((char*)workspace + base);
+    const FusedImgLoss fl{out, y, black, acc, pc.gate * pc.img * 2.0f * pc.inv_batch, g_total_dev};
+    const float* parts; int np, ps;
+    TRY(warp_bwd_core(U, Hs, d_out_extra, nullptr, s, dU, dHs_acc, tma_ws, &parts, &np, &ps, st, &fl, scratch));
+    TRY(launch_solve_h_bwd(pts2, Hs, parts, np, ps, N, gh, gw, d_pts2, st, ps == 8, extra));
+    // vertex regularisers: d_pts2 += consistency term, d_pts1 = black_pos + distortion terms; then back through get_4_pts with
+    // the id term on the head itself
+    const float vc[4] = {pc.v[0], pc.gate * pc.v[1], pc.gate * pc.v[2], pc.gate * pc.v[3]};
+    TRY(launch_vertex_losses_bwd_coef(pts1, pts2, N, gh, gw, do_crop_rate, vc, g_total_dev, d_pts1, d_pts2, st));
+    return launch_vertices_bwd(head, d_pts2, d_pts1, N, gh, gw, do_crop_rate, d_head, st, pc.v[0], g_total_dev);
 }
 
 int mgw_fill_zero(void* p, size_t bytes, int keep_in_l2, void* stream)

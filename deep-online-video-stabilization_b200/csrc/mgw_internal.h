@@ -37,11 +37,13 @@ struct WarpShape {
 
 // mgw_solve.cu
 int launch_vertices_fwd(const float* head, int N, int gh, int gw, float do_crop_rate, float* pts2, float* pts1, cudaStream_t st);
+// id_coef / id_dev: optional id-loss term added to d_head: id_coef * (id_dev ? *id_dev : 1) * sign(head)  (s_net_bundle_nobm.py:246)
 int launch_vertices_bwd(const float* head, const float* d_pts2, const float* d_pts1, int N, int gh, int gw,
-                        float do_crop_rate, float* d_head, cudaStream_t st);
+                        float do_crop_rate, float* d_head, cudaStream_t st, float id_coef = 0.0f, const float* id_dev = nullptr);
 int launch_solve_h_fwd(const float* theta, int N, int gh, int gw, float* Hs, cudaStream_t st);
 int launch_solve_h_bwd(const float* theta, const float* Hs, const float* dHs_part, int nparts, int part_stride,
-                       int N, int gh, int gw, float* dtheta, cudaStream_t st, bool after_own_warp_kernel = false);
+                       int N, int gh, int gw, float* dtheta, cudaStream_t st, bool after_own_warp_kernel = false,
+                       const float* extra_part = nullptr /*[cells,8] one more partial per cell*/);
 
 // mgw_warp_generic.cu : any shape, global gather / global atomics
 // normalize: Hs holds raw [N,9] homographies to be divided by H[8] (spatial_transformer.py:151-153)
@@ -61,7 +63,7 @@ int launch_interp_bwd(const float* im, const float* x, const float* y, const flo
 // mgw_loss.cu
 int launch_img_loss_fwd(const float* out, const float* y, const float* black, int N, int H, int W, int C, float* sums, cudaStream_t st);
 int launch_img_loss_bwd(const float* out, const float* y, const float* black, const float* sums, float upstream,
-                        const float* up_dev, int N, int H, int W, int C, float* d_out, cudaStream_t st);
+                        const float* up_dev, int N, int H, int W, int C, float* d_out, cudaStream_t st, const float* add = nullptr);
 int launch_feature_loss_fwd(const float* matches, const float* mask, const float* img, int N, int M, int H, int W,
                             float* warpped, float* per_sample, cudaStream_t st);
 int launch_feature_loss_bwd(const float* matches, const float* mask, const float* img, float upstream, const float* up_dev, int N, int M,
@@ -135,6 +137,25 @@ int launch_vertex_losses_fwd(const float* theta, const float* pts1, const float*
 int launch_vertex_losses_bwd(const float* theta, const float* pts1, const float* pts2, int N, int gh, int gw, float do_crop_rate,
                              const float* f, float* d_theta, float* d_pts1, float* d_pts2,
                              cudaStream_t st);
+// the same with f[k] = coef[k] * (g_dev ? *g_dev : 1) and d_pts2 += instead of = (the warp's dtheta is already in it)
+int launch_vertex_losses_bwd_coef(const float* pts1, const float* pts2, int N, int gh, int gw, float do_crop_rate, const float coef[4],
+                                  const float* g_dev, float* d_pts1, float* d_pts2_acc, cudaStream_t st);
+
+// mgw_pass.cu : the pieces that turn one training pass (s_net_bundle_nobm.py:266-381) into a handful of launches
+struct PassCoef {            // total = v[0] vsums[0] + gate * (sum_{k>0} v[k] vsums[k] + img IMG + feat FEAT + regu REGU)   (:354-359)
+    float v[4];              // multipliers of the vertex sums (id, black_pos, distortion, consistency), element counts folded in
+    float img, feat, regu;   // IMG = sum_n e2_n / (nb_n + 1e-8) / batch, FEAT = sum_n acc_n / max(cnt_n, 1) / batch
+    float theta_share, grid_theta_share;   // split of the id term into ret['theta_loss'] / ret['grid_theta_loss']
+    float inv_batch;
+    float gate;              // 1 - use_theta_only; the parts of `ret` are reported without it, as the reference does
+};
+int launch_ratio_sum(const float* sums /*[N,2]*/, int N, bool clamp, float scale, float* out, cudaStream_t st);
+int launch_feature_acc_fwd(const float* matches, const float* mask, const float* img, int N, int M, int H, int W, float* warpped,
+                           float* facc /*[N,2] zeroed*/, cudaStream_t st);
+int launch_feature_dh(const float* matches, const float* mask, const float* img, const float* Hs, const float* facc, float upstream,
+                      const float* up_dev, int N, int M, int H, int W, int gh, int gw, float* extra_part /*[cells,8]*/, cudaStream_t st);
+int launch_objective_fwd(const float* img_sums, const float* facc, const float* vsums, const float* regu_dev, int N, const PassCoef& c,
+                         float* result /*[9]: total, then the 8 weighted parts*/, cudaStream_t st);
 
 // mgw_crop.cu : deploy-side crop (deploy_bundle.py:240,291,344-365)
 int launch_black_accumulate(const float* black, int32_t* all_black, int n, cudaStream_t st);

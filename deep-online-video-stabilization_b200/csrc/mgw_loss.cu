@@ -46,8 +46,8 @@ img_loss_fwd_kernel(const float* __restrict__ out, const float* __restrict__ y, 
 
 __global__ void __launch_bounds__(256)
 img_loss_bwd_kernel(const float* __restrict__ out, const float* __restrict__ y, const float* __restrict__ black,
-                    const float* __restrict__ sums, float upstream, const float* __restrict__ up_dev, int N, int HW, int C,
-                    float* __restrict__ d_out)
+                    const float* __restrict__ sums, float upstream, const float* __restrict__ up_dev, const float* __restrict__ add,
+                    int N, int HW, int C, float* __restrict__ d_out)
 {
     const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= (long long)N * HW) return;
@@ -56,7 +56,7 @@ img_loss_bwd_kernel(const float* __restrict__ out, const float* __restrict__ y, 
     const float k = upstream * 2.0f / ((__ldg(sums + 2 * n + 1) + 1e-8f) * (float)N);
     const float nb = 1.0f - __ldg(black + p);
     for (int ch = 0; ch < C; ++ch)
-        d_out[p * C + ch] = k * (__ldg(out + p * C + ch) - __ldg(y + p * C + ch)) * nb * nb;
+        d_out[p * C + ch] = k * (__ldg(out + p * C + ch) - __ldg(y + p * C + ch)) * nb * nb + (add ? __ldg(add + p * C + ch) : 0.0f);
 }
 
 // ---------------------------------------------------------------- feature_loss
@@ -241,10 +241,10 @@ int launch_img_loss_fwd(const float* out, const float* y, const float* black, in
 }
 
 int launch_img_loss_bwd(const float* out, const float* y, const float* black, const float* sums, float upstream,
-                        const float* up_dev, int N, int H, int W, int C, float* d_out, cudaStream_t st)
+                        const float* up_dev, int N, int H, int W, int C, float* d_out, cudaStream_t st, const float* add)
 {
     const unsigned grid = (unsigned)(((long long)N * H * W + 255) / 256);
-    img_loss_bwd_kernel<<<grid, 256, 0, st>>>(out, y, black, sums, upstream, up_dev, N, H * W, C, d_out);
+    img_loss_bwd_kernel<<<grid, 256, 0, st>>>(out, y, black, sums, upstream, up_dev, add, N, H * W, C, d_out);
     return check_launch("img_loss_bwd");
 }
 

@@ -39,7 +39,7 @@ __global__ void vertices_fwd_kernel(const float* __restrict__ head, int N, int g
 
 __global__ void vertices_bwd_kernel(const float* __restrict__ head, const float* __restrict__ d_pts2,
                                     const float* __restrict__ d_pts1, int N, int gh, int gw, float do_crop_rate,
-                                    float* __restrict__ d_head)
+                                    float* __restrict__ d_head, float id_coef, const float* __restrict__ id_dev)
 {
     const int nv = (gh + 1) * (gw + 1);
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
@@ -60,7 +60,12 @@ __global__ void vertices_bwd_kernel(const float* __restrict__ head, const float*
     }
     // tf.minimum(tf.maximum(p,-lim),lim): the gradient passes where the clamp is inactive.  At an exact tie
     // TF's Maximum/Minimum gradients route to the first argument (x >= y / x <= y), i.e. they pass.
-    d_head[t] = (p >= -lim && p <= lim) ? g : 0.0f;
+    float d = (p >= -lim && p <= lim) ? g : 0.0f;
+    if (id_coef != 0.0f) {                               // id loss on the head itself: d|t| = sign(t), 0 at 0
+        const float t0 = head[t], f = id_dev ? id_coef * __ldg(id_dev) : id_coef;
+        d += f * (t0 > 0.0f ? 1.0f : (t0 < 0.0f ? -1.0f : 0.0f));
+    }
+    d_head[t] = d;
 }
 
 // ---------------------------------------------------------------- K1: per-cell DLT solve
@@ -280,7 +285,7 @@ solve_h_fwd_kernel(const float* __restrict__ theta, int N, int gh, int gw, float
 // each vertex gathers its (up to) four cells in a fixed order -> deterministic, no atomics.  One block per sample.
 __global__ void solve_h_bwd_kernel(const float* __restrict__ theta, const float* __restrict__ Hs,
                                    const float* __restrict__ dHs_part, int nparts, int part_stride,
-                                   int N, int gh, int gw, float* __restrict__ dtheta)
+                                   int N, int gh, int gw, float* __restrict__ dtheta, const float* __restrict__ extra_part)
 {
     extern __shared__ double sDuv[];                   // [gh*gw][8]  (du0..3, dv0..3), then [gh*gw][8] summed partials
     const int ncell_s = gh * gw;
@@ -321,6 +326,7 @@ __global__ void solve_h_bwd_kernel(const float* __restrict__ theta, const float*
                 s0 += (double)a; s1 += (double)b; s2 += (double)c; s3 += (double)d;
             }
             for (; p < nparts; ++p) s0 += (double)__ldcg(src + (size_t)p * part_stride);
+            if (extra_part) s1 += (double)__ldcg(extra_part + ((size_t)n * ncell_s + base + (e >> 3)) * 8 + (e & 7));
             sRhs[(size_t)(base + (e >> 3)) * 8 + (e & 7)] = (s0 + s1) + (s2 + s3);
         }
         __syncthreads();
@@ -362,10 +368,10 @@ int launch_vertices_fwd(const float* head, int N, int gh, int gw, float do_crop_
 }
 
 int launch_vertices_bwd(const float* head, const float* d_pts2, const float* d_pts1, int N, int gh, int gw,
-                        float do_crop_rate, float* d_head, cudaStream_t st)
+                        float do_crop_rate, float* d_head, cudaStream_t st, float id_coef, const float* id_dev)
 {
     const int tot = N * (gh + 1) * (gw + 1) * 2;
-    vertices_bwd_kernel<<<(tot + 127) / 128, 128, 0, st>>>(head, d_pts2, d_pts1, N, gh, gw, do_crop_rate, d_head);
+    vertices_bwd_kernel<<<(tot + 127) / 128, 128, 0, st>>>(head, d_pts2, d_pts1, N, gh, gw, do_crop_rate, d_head, id_coef, id_dev);
     return check_launch("vertices_bwd");
 }
 
@@ -380,7 +386,7 @@ int launch_solve_h_fwd(const float* theta, int N, int gh, int gw, float* Hs, cud
 }
 
 int launch_solve_h_bwd(const float* theta, const float* Hs, const float* dHs_part, int nparts, int part_stride,
-                       int N, int gh, int gw, float* dtheta, cudaStream_t st, bool after_own_warp_kernel)
+                       int N, int gh, int gw, float* dtheta, cudaStream_t st, bool after_own_warp_kernel, const float* extra_part)
 {
     const int ncell_s = gh * gw;
     // 8 threads per cell for the sum of the partials (one thread per cell for the solve itself)
@@ -391,7 +397,7 @@ int launch_solve_h_bwd(const float* theta, const float* Hs, const float* dHs_par
     // after_own_warp_kernel: the previous kernel of the stream is this library's backward warp kernel, which read Hs itself and
     // releases its dependents at once: launch programmatically, the factorisation overlaps it
     const cudaError_t e = launch_ex(solve_h_bwd_kernel, dim3(N), dim3(threads), smem, st, after_own_warp_kernel && pdl_enabled(),
-                                    theta, Hs, dHs_part, nparts, part_stride, N, gh, gw, dtheta);
+                                    theta, Hs, dHs_part, nparts, part_stride, N, gh, gw, dtheta, extra_part);
     if (e != cudaSuccess) { count_launches(1); return set_error(MGW_ERR_CUDA, "solve_h_bwd: %s", cudaGetErrorString(e)); }
     return check_launch("solve_h_bwd");
 }

@@ -115,15 +115,19 @@ vertex_losses_fwd_kernel(const float* __restrict__ theta, const float* __restric
     if (threadIdx.x == 0) { sums[0] = s_id; sums[1] = s_black; sums[2] = s_dist; sums[3] = s_cons; }
 }
 
-// f[k] (device) = d(total) / d(sums[k])
+// f[k] (device) = d(total) / d(sums[k]); or (f == nullptr) coef[k] * (g_dev ? *g_dev : 1).  ACC: d_pts2 += instead of =
+struct Coef4 { float v[4]; };
+template <bool ACC>
 __global__ void __launch_bounds__(kThreads)
 vertex_losses_bwd_kernel(const float* __restrict__ theta, const float* __restrict__ pts1, const float* __restrict__ pts2, int N, int gh,
-                         int gw, float one, float k0, float k1, const float* f,
+                         int gw, float one, float k0, float k1, const float* f, const Coef4 coef, const float* __restrict__ g_dev,
                          float* __restrict__ d_theta, float* __restrict__ d_pts1, float* __restrict__ d_pts2)
 {
     const int V = (gh + 1) * (gw + 1);
     const int tid = blockIdx.x * kThreads + threadIdx.x, nthr = gridDim.x * kThreads;
-    const float f_id = __ldg(f), f_black = __ldg(f + 1), f_dist = __ldg(f + 2), f_cons = __ldg(f + 3);
+    const float gg = g_dev ? __ldg(g_dev) : 1.0f;
+    const float f_id = f ? __ldg(f) : coef.v[0] * gg, f_black = f ? __ldg(f + 1) : coef.v[1] * gg;
+    const float f_dist = f ? __ldg(f + 2) : coef.v[2] * gg, f_cons = f ? __ldg(f + 3) : coef.v[3] * gg;
     if (theta && d_theta)
         for (int q = tid; q < N * V * 2; q += nthr) {
             const float t = __ldg(theta + q);
@@ -160,7 +164,7 @@ vertex_losses_bwd_kernel(const float* __restrict__ theta, const float* __restric
             if (j >= 1 && j <= gw - 1) g += 2.0f * pair(at(i, j - 1), at(i, j), at(i, j + 1));
             if (j >= 2) g -= pair(at(i, j - 2), at(i, j - 1), at(i, j));
             if (j + 2 <= gw) g -= pair(at(i, j), at(i, j + 1), at(i, j + 2));
-            d_pts2[q] = f_cons * 2.0f * g;
+            if (ACC) d_pts2[q] += f_cons * 2.0f * g; else d_pts2[q] = f_cons * 2.0f * g;
         }
 }
 
@@ -183,8 +187,20 @@ int launch_vertex_losses_bwd(const float* theta, const float* pts1, const float*
     const double h = 2.0 / gh, w = 2.0 / gw;
     const int items = N * (gh + 1) * (gw + 1) * 2;
     const int blocks = std::min(148, (items + kThreads - 1) / kThreads);
-    vertex_losses_bwd_kernel<<<blocks, kThreads, 0, st>>>(theta, pts1, pts2, N, gh, gw, 1.0f / do_crop_rate, (float)(h / w), (float)(w / h),
-                                                           f, d_theta, d_pts1, d_pts2);
+    vertex_losses_bwd_kernel<false><<<blocks, kThreads, 0, st>>>(theta, pts1, pts2, N, gh, gw, 1.0f / do_crop_rate, (float)(h / w),
+                                                                  (float)(w / h), f, Coef4{}, nullptr, d_theta, d_pts1, d_pts2);
+    return check_launch("vertex_losses_bwd");
+}
+
+int launch_vertex_losses_bwd_coef(const float* pts1, const float* pts2, int N, int gh, int gw, float do_crop_rate, const float coef[4],
+                                  const float* g_dev, float* d_pts1, float* d_pts2_acc, cudaStream_t st)
+{
+    const double h = 2.0 / gh, w = 2.0 / gw;
+    const int items = N * (gh + 1) * (gw + 1) * 2;
+    const int blocks = std::min(148, (items + kThreads - 1) / kThreads);
+    const Coef4 c{{coef[0], coef[1], coef[2], coef[3]}};
+    vertex_losses_bwd_kernel<true><<<blocks, kThreads, 0, st>>>(nullptr, pts1, pts2, N, gh, gw, 1.0f / do_crop_rate, (float)(h / w),
+                                                                 (float)(w / h), nullptr, c, g_dev, nullptr, d_pts1, d_pts2_acc);
     return check_launch("vertex_losses_bwd");
 }
 

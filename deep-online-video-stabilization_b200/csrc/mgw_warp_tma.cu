@@ -307,7 +307,8 @@ __device__ __forceinline__ void accumulate_dh_r(float (&dh)[8], float gxn, float
 }
 
 // LOSS = true takes the upstream gradient from the fused img_loss instead of a d_out tensor:
-// d_out = kscale/(sums[n][1]+1e-8) * (out - y) * (1-black)^2, computed in registers from the forward's out / black.
+// d_out = kscale/(sums[n][1]+1e-8) * (out - y) * (1-black)^2, computed in registers from the forward's out / black; a d_out tensor
+// given on top of that (nullable) is added to it (the gradient of another consumer of `output`, e.g. temp_loss).
 struct LossBwd {
     const float* out;       // forward output_img
     const float* y;         // target
@@ -365,7 +366,10 @@ warp_bwd_tma_kernel(const __grid_constant__ CUtensorMap mapU, const __grid_const
                 const float nb = 1.0f - __ldg(loss.black + p);
                 const float kk = kn * nb * nb;
 #pragma unroll
-                for (int ch = 0; ch < C; ++ch) gout[k][ch] = kk * (__ldg(loss.out + p * C + ch) - __ldg(loss.y + p * C + ch));
+                for (int ch = 0; ch < C; ++ch) {
+                    gout[k][ch] = kk * (__ldg(loss.out + p * C + ch) - __ldg(loss.y + p * C + ch));
+                    if (d_out) gout[k][ch] += __ldg(d_out + p * C + ch);       // gradient reaching `output` from elsewhere (temp_loss)
+                }
             } else {
 #pragma unroll
                 for (int ch = 0; ch < C; ++ch) gout[k][ch] = __ldg(d_out + p * C + ch);
@@ -681,11 +685,11 @@ static int launch_bwd_v(const float* U, const float* Hs, const float* d_out, con
     if (loss && dU) {
         static bool attr[64] = {};
         TRY_RC(allow_smem(warp_bwd_tma_kernel<C, TW, K, NT, true, true>, attr, "warp_bwd_tma(loss)"));
-        warp_bwd_tma_kernel<C, TW, K, NT, true, true><<<grid, NT, smem, st>>>(mU, mDU, U, Hs, nullptr, d_img, c, dU, parts, *loss);
+        warp_bwd_tma_kernel<C, TW, K, NT, true, true><<<grid, NT, smem, st>>>(mU, mDU, U, Hs, d_out, d_img, c, dU, parts, *loss);
     } else if (loss) {
         static bool attr[64] = {};
         TRY_RC(allow_smem(warp_bwd_tma_kernel<C, TW, K, NT, true, false>, attr, "warp_bwd_tma(loss, no dU)"));
-        warp_bwd_tma_kernel<C, TW, K, NT, true, false><<<grid, NT, smem, st>>>(mU, mDU, U, Hs, nullptr, d_img, c, nullptr, parts, *loss);
+        warp_bwd_tma_kernel<C, TW, K, NT, true, false><<<grid, NT, smem, st>>>(mU, mDU, U, Hs, d_out, d_img, c, nullptr, parts, *loss);
     } else if (dU) {
         static bool attr[64] = {};
         TRY_RC(allow_smem(warp_bwd_tma_kernel<C, TW, K, NT, false, true>, attr, "warp_bwd_tma"));

@@ -48,7 +48,7 @@ class MeshWarpImgLoss(torch.autograd.Function):
         ctx.batch = batch
         ctx.mark_non_differentiable(black)
         ctx.set_materialize_grads(False)          # g_out is None unless something else consumes `output`: the fused backward's condition
-        loss = (sums[:, 0] / (sums[:, 1] + 1e-8)).sum() / batch
+        loss = ops.loss_ratio_sum(sums, 1.0 / batch)
         return loss, out, black, img
 
     @staticmethod
@@ -62,9 +62,42 @@ class MeshWarpImgLoss(torch.autograd.Function):
             dU, dtheta = ops.mesh_warp_img_loss_bwd(U, theta, Hs, out, y, black, sums, up, ctx.batch, g_img,
                                                     want_dU=ctx.needs_input_grad[0])
         else:
-            d_out = g_out.contiguous() + ops.img_loss_bwd(out, y, black, sums, up * out.shape[0] / ctx.batch)
-            dU, dtheta = ops.mesh_warp_bwd(U, theta, Hs, d_out, g_img, want_dU=ctx.needs_input_grad[0])
+            # a second gradient on `output` (temp_loss): added to the loss gradient inside the warp backward
+            dU, dtheta = ops.mesh_warp_img_loss_bwd(U, theta, Hs, out, y, black, sums, up, ctx.batch, g_img,
+                                                    want_dU=ctx.needs_input_grad[0], d_out_extra=g_out.contiguous())
         return dU, dtheta, None, None
+
+
+class TrainPass(torch.autograd.Function):
+    """One training pass after the network head (reference s_net_bundle_nobm.py:266-381: get_4_pts, transformer, img_loss,
+    feature_loss, the vertex regularisers, the weighted total) as 7 forward and 5 backward launches.
+    -> (result [9] = total + weighted parts, h_trans, black_pix, flow, stable_warpped, pts2).  Differentiable outputs: result[0]
+    through `total` and h_trans (another consumer of the warped frame, i.e. temp_loss, adds its gradient inside the warp
+    backward); flow / pts2 / the parts are returned for display only."""
+
+    @staticmethod
+    def forward(ctx, head, U, y, matches, mask, regu, coef, gh, gw, do_crop_rate):
+        f = ops.train_pass_fwd(head, U, y, matches, mask, coef, gh, gw, do_crop_rate, regu=regu)
+        ctx.save_for_backward(head, U, y, matches, mask)
+        ctx.fwd = {k: f[k] for k in ('pts1', 'pts2', 'Hs', 'out', 'black', 'img', 'acc')}
+        ctx.cfg = (coef, gh, gw, do_crop_rate)
+        total, parts = f['result'][0], f['result'][1:]
+        ctx.mark_non_differentiable(parts, f['black'], f['img'], f['warpped'], f['pts2'])
+        ctx.set_materialize_grads(False)
+        return total, parts, f['out'], f['black'], f['img'], f['warpped'], f['pts2']
+
+    @staticmethod
+    def backward(ctx, g_total, _g_parts, g_out, *_unused):
+        head, U, y, matches, mask = ctx.saved_tensors
+        coef, gh, gw, rate = ctx.cfg
+        if g_total is None:
+            coef = (0.0,) * 9 + (coef[9], 0.0)      # only the gradient through h_trans is alive
+        d_head, dU = ops.train_pass_bwd(head, U, y, matches, mask, ctx.fwd, coef, gh, gw, rate, g_total=g_total,
+                                        d_out_extra=None if g_out is None else g_out.contiguous(), want_dU=ctx.needs_input_grad[1])
+        regu_grad = None
+        if ctx.needs_input_grad[5]:
+            regu_grad = (g_total if g_total is not None else torch.zeros((), device=head.device)) * (coef[6] * coef[10])
+        return d_head, dU, None, None, None, regu_grad, None, None, None, None
 
 
 class HomographyWarp(torch.autograd.Function):
@@ -130,12 +163,12 @@ class ImgLoss(torch.autograd.Function):
         sums = ops.img_loss_fwd(out, y, black)
         ctx.save_for_backward(out, y, black, sums)
         ctx.batch = batch
-        return (sums[:, 0] / (sums[:, 1] + 1e-8)).sum() / batch
+        return ops.loss_ratio_sum(sums, 1.0 / batch)
 
     @staticmethod
     def backward(ctx, g):
         out, y, black, sums = ctx.saved_tensors
-        d_out = ops.img_loss_bwd(out, y, black, sums, g * (out.shape[0] / ctx.batch))
+        d_out = ops.img_loss_bwd(out, y, black, sums, (out.shape[0] / ctx.batch, g))
         return d_out, (-d_out if ctx.needs_input_grad[1] else None), None, None
 
 
@@ -153,7 +186,7 @@ class FeatureLoss(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g, _gw):
         matches, mask, flow = ctx.saved_tensors
-        d_flow = ops.feature_loss_bwd(matches, mask, flow, g * (flow.shape[0] / ctx.batch))
+        d_flow = ops.feature_loss_bwd(matches, mask, flow, (flow.shape[0] / ctx.batch, g))
         return None, None, d_flow, None
 
 
@@ -165,13 +198,13 @@ class TempLoss(torch.autograd.Function):
         sums = ops.temp_loss_fwd(out1, black1, out2, black2, flow)
         ctx.save_for_backward(out1, black1, out2, black2, flow, sums)
         ctx.cfg = (batch, use_temp_loss)
-        return (sums[:, 0] / (sums[:, 1] + 1e-8)).sum() / batch * use_temp_loss
+        return ops.loss_ratio_sum(sums, use_temp_loss / batch)
 
     @staticmethod
     def backward(ctx, g):
         out1, black1, out2, black2, flow, sums = ctx.saved_tensors
         batch, use = ctx.cfg
-        d1, d2 = ops.temp_loss_bwd(out1, black1, out2, black2, flow, sums, g * (use * out1.shape[0] / batch))
+        d1, d2 = ops.temp_loss_bwd(out1, black1, out2, black2, flow, sums, (use * out1.shape[0] / batch, g))
         return d1, None, d2, None, None, None, None
 
 

@@ -115,3 +115,41 @@ def total_loss(theta, pts1, pts2, img_loss, feature_loss, regu_loss=0.0, use_bla
                  feature_loss=feature_loss * m['feature_mul'], img_loss=img_loss * m['img_mul'],
                  regu_loss=torch.as_tensor(regu_loss) * m['regu_mul'])
     return total, parts
+
+
+# the weighted parts of one pass, in the order mgw_train_pass_fwd reports them (result[1:]), keys as in the reference's `ret`
+PASS_PARTS = ('theta_loss', 'grid_theta_loss', 'black_loss', 'distortion_loss', 'consistency_loss', 'feature_loss', 'img_loss',
+              'regu_loss')
+
+
+def pass_coef(n, gh, gw, use_black_loss=1.0, use_theta_only=0.0, mul=None):
+    """The 11 host coefficients of mgw_train_pass_fwd/bwd for a (global) batch n: reference s_net_bundle_nobm.py:308-317,354-359
+    with the element counts of the four means folded in."""
+    m = dict(V2_93_MULS)
+    m.update(mul or {})
+    n = float(n)
+    terms = 2 * (max(gh - 1, 0) * (gw + 1) + (gh + 1) * max(gw - 1, 0))
+    idw = m['theta_mul'] + m['grid_theta_mul']
+    return (m['id_mul'] * idw / (n * 2 * (gh + 1) * (gw + 1)),
+            float(use_black_loss) * m['black_mul'] / (n * gh * gw * 8),
+            m['distortion_mul'] / (n * gh * gw * 2) / 8,
+            m['consistency_mul'] / (n * 2 * terms) if terms else 0.0,
+            m['img_mul'], m['feature_mul'], m['regu_mul'],
+            m['theta_mul'] / idw if idw else 0.0, m['grid_theta_mul'] / idw if idw else 0.0,
+            1.0 / n, 1.0 - float(use_theta_only))
+
+
+def train_pass(theta, x, y, matches, mask, regu_loss=None, use_black_loss=1.0, use_theta_only=0.0, mul=None, grid=(4, 4),
+               do_crop_rate=0.8, batch_size=None):
+    """Everything of one pass after the network head in ONE autograd node (7 + 5 launches): get_4_pts, transformer + img_loss,
+    feature_loss, the vertex regularisers and the weighted total (reference s_net_bundle_nobm.py:303-359).  theta = the head's
+    output [N, 2(gh+1)(gw+1)], x = the frame to warp.  -> (total_loss, parts dict as in the reference's `ret`, h_trans, black_pix,
+    flow, stable_warpped, pts2).  h_trans may feed another differentiable consumer (temp_loss); flow and pts2 are for display
+    (take them from transformer() / get_4_pts() if they need a gradient of their own)."""
+    gh, gw = int(grid[0]), int(grid[1])
+    coef = pass_coef(batch_size or x.shape[0], gh, gw, use_black_loss, use_theta_only, mul)
+    regu = regu_loss if isinstance(regu_loss, torch.Tensor) else None
+    if regu is None and regu_loss:
+        regu = torch.full((1,), float(regu_loss), device=x.device)
+    total, parts, out, black, flow, warpped, pts2 = F.TrainPass.apply(theta, x, y, matches, mask, regu, coef, gh, gw, float(do_crop_rate))
+    return total, dict(zip(PASS_PARTS, parts.unbind(0))), out, black, flow, warpped, pts2

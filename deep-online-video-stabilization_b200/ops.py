@@ -37,7 +37,11 @@ def _p(t):
 
 
 def _up(upstream):
-    """upstream gradient as (host factor, device pointer): a CUDA tensor is read by the kernel itself (no host sync)"""
+    """upstream gradient as (host factor, device pointer): a CUDA tensor is read by the kernel itself (no host sync); a pair
+    (host factor, CUDA tensor) is their product, formed inside the kernel"""
+    if isinstance(upstream, tuple):
+        f, t = _up(upstream[1])
+        return f * float(upstream[0]), t
     if isinstance(upstream, torch.Tensor) and upstream.is_cuda:
         t = upstream.detach().reshape(-1)[:1].to(torch.float32).contiguous()
         return 1.0, t
@@ -203,10 +207,13 @@ def mesh_warp_img_loss_fwd(U, theta, y, want_img=True):
     return out, black, img, Hs, sums
 
 
-def mesh_warp_img_loss_bwd(U, theta, Hs, out, y, black, sums, upstream, batch, d_img=None, want_dU=True):
+def mesh_warp_img_loss_bwd(U, theta, Hs, out, y, black, sums, upstream, batch, d_img=None, want_dU=True, d_out_extra=None):
     U, theta, Hs, out, y, black, sums = (_chk(t, nm) for t, nm in ((U, 'U'), (theta, 'theta'), (Hs, 'Hs'), (out, 'out'), (y, 'y'),
                                                                    (black, 'black'), (sums, 'sums')))
     d_img = None if d_img is None else _chk(d_img, 'd_img')
+    d_out_extra = None if d_out_extra is None else _chk(d_out_extra, 'd_out_extra')
+    if d_out_extra is not None and d_out_extra.shape != U.shape:
+        raise ValueError('d_out_extra must have the shape of U')
     up = _up(upstream)
     n, h, w, c = _mesh_dims(U, theta, 'theta')
     gh, gw = Hs.shape[1:3]
@@ -215,9 +222,86 @@ def mesh_warp_img_loss_bwd(U, theta, Hs, out, y, black, sums, upstream, batch, d
     ws = _workspace(lib.mgw_mesh_warp_img_loss_bwd_workspace_bytes(n, h, w, c, gh, gw), U.device)
     with torch.cuda.device(U.device):
         check(lib.mgw_mesh_warp_img_loss_bwd(_p(U), _p(theta), _p(Hs), _p(out), _p(y), _p(black), _p(sums), up[0], _p(up[1]),
-                                             float(batch), _p(d_img), n, h, w, c, gh, gw, _p(dU), _p(dtheta), _p(ws), _st()),
+                                             float(batch), _p(d_img), _p(d_out_extra), n, h, w, c, gh, gw, _p(dU), _p(dtheta), _p(ws), _st()),
               'mgw_mesh_warp_img_loss_bwd')
     return dU, dtheta
+
+
+def feature_loss_dh(matches, mask, img, Hs, upstream):
+    """mgw_feature_loss_dh: d(feature_loss)/dH as one partial per cell [N,gh,gw,8] (what the warp backward would form from the dense
+    d_img of feature_loss_bwd)."""
+    matches, mask, img, Hs = _chk(matches, 'matches'), _chk(mask, 'mask'), _chk(img, 'img'), _chk(Hs, 'Hs')
+    n, h, w, _ = img.shape
+    gh, gw = Hs.shape[1:3]
+    up = _up(upstream)
+    facc = torch.stack([torch.zeros_like(mask[:, 0]), mask.sum(1)], 1).contiguous()
+    part = torch.empty((n, gh, gw, 8), device=img.device, dtype=torch.float32)
+    with torch.cuda.device(img.device):
+        check(lib.mgw_feature_loss_dh(_p(matches), _p(mask), _p(img), _p(Hs), _p(facc), up[0], _p(up[1]), n, matches.shape[1], h, w, gh, gw,
+                                      _p(part), _st()), 'mgw_feature_loss_dh')
+    return part
+
+
+def loss_ratio_sum(sums, scale, clamp=False):
+    """scale * sum_n sums[n,0] / (sums[n,1] + 1e-8)  (clamp: / max(sums[n,1], 1)) -> 0-dim tensor, one launch"""
+    sums = _chk(sums, 'sums')
+    if sums.dim() != 2 or sums.shape[1] != 2:
+        raise ValueError('sums [N,2] expected')
+    out = torch.empty(1, device=sums.device, dtype=torch.float32)
+    with torch.cuda.device(sums.device):
+        check(lib.mgw_loss_ratio_sum(_p(sums), sums.shape[0], int(bool(clamp)), float(scale), _p(out), _st()), 'mgw_loss_ratio_sum')
+    return out[0]
+
+
+def _coef_array(coef):
+    import ctypes
+    if len(coef) != 11:
+        raise ValueError('coef: 11 floats expected (see include/mgw.h, mgw_train_pass_fwd)')
+    return (ctypes.c_float * 11)(*[float(c) for c in coef])
+
+
+def train_pass_fwd(head, U, y, matches, mask, coef, gh, gw, do_crop_rate=0.8, regu=None, want_warpped=True):
+    """mgw_train_pass_fwd: head -> get_4_pts -> transformer + img_loss -> feature_loss -> vertex terms -> total, 7 launches.
+    -> dict(pts1, pts2, Hs, out, black, img, acc, warpped, vsums, result)."""
+    head, U, y, matches, mask = (_chk(t, nm) for t, nm in ((head, 'head'), (U, 'U'), (y, 'y'), (matches, 'matches'), (mask, 'mask')))
+    n, h, w, c = U.shape
+    if tuple(y.shape) != (n, h, w, c):
+        raise ValueError('y must have the shape of U')
+    if head.shape[0] != n or head.numel() != n * 2 * (gh + 1) * (gw + 1):
+        raise ValueError('head has shape %s for a %dx%d grid, batch %d' % (tuple(head.shape), gh, gw, n))
+    if matches.dim() != 3 or matches.shape[0] != n or matches.shape[2] != 4 or tuple(mask.shape) != tuple(matches.shape[:2]):
+        raise ValueError('matches [N,M,4] / mask [N,M] expected, got %s / %s' % (tuple(matches.shape), tuple(mask.shape)))
+    m = matches.shape[1]
+    regu = None if regu is None else _chk(regu.reshape(-1)[:1], 'regu')
+    dev = U.device
+    f = lambda *shape: torch.empty(shape, device=dev, dtype=torch.float32)      # noqa: E731
+    r = dict(pts1=f(n, gh, gw, 8), pts2=f(n, gh + 1, gw + 1, 2), Hs=f(n, gh, gw, 9), out=f(n, h, w, c), black=f(n, h, w), img=f(n, h, w, 2),
+             acc=f(n, 4), warpped=f(n, m, 2) if want_warpped else None, vsums=f(4), result=f(9))
+    with torch.cuda.device(dev):
+        check(lib.mgw_train_pass_fwd(_p(head), _p(U), _p(y), _p(matches), _p(mask), _p(regu), _coef_array(coef), n, h, w, c, gh, gw, m,
+                                     float(do_crop_rate), _p(r['pts1']), _p(r['pts2']), _p(r['Hs']), _p(r['out']), _p(r['black']),
+                                     _p(r['img']), _p(r['acc']), _p(r['warpped']), _p(r['vsums']), _p(r['result']), _st()),
+              'mgw_train_pass_fwd')
+    return r
+
+
+def train_pass_bwd(head, U, y, matches, mask, fwd, coef, gh, gw, do_crop_rate=0.8, g_total=None, d_out_extra=None, want_dU=False):
+    """mgw_train_pass_bwd -> (d_head, dU or None); fwd = the dict train_pass_fwd returned; g_total: device scalar or None (= 1)."""
+    n, h, w, c = U.shape
+    m = matches.shape[1]
+    g = None if g_total is None else _chk(g_total.detach().reshape(-1)[:1], 'g_total')
+    extra = None if d_out_extra is None else _chk(d_out_extra, 'd_out_extra')
+    if extra is not None and tuple(extra.shape) != (n, h, w, c):
+        raise ValueError('d_out_extra must have the shape of U')
+    d_head = torch.empty_like(head)
+    dU = torch.empty_like(U) if want_dU else None
+    ws = _workspace(lib.mgw_train_pass_bwd_workspace_bytes(n, h, w, c, gh, gw), U.device)
+    with torch.cuda.device(U.device):
+        check(lib.mgw_train_pass_bwd(_p(head), _p(fwd['pts1']), _p(fwd['pts2']), _p(U), _p(y), _p(matches), _p(mask), _p(fwd['Hs']),
+                                     _p(fwd['out']), _p(fwd['black']), _p(fwd['img']), _p(fwd['acc']), _p(g), _p(extra),
+                                     _coef_array(coef), n, h, w, c, gh, gw, m, float(do_crop_rate), _p(dU), _p(d_head), _p(ws), _st()),
+              'mgw_train_pass_bwd')
+    return d_head, dU
 
 
 def interp_fwd(im, x, y, out_size):

@@ -94,31 +94,51 @@ class StabNet(nn.Module):
         return self.head(self.features(x_tensor))
 
 
+class _Ret(dict):
+    """the reference's `ret`; 'error' = |h_trans - y| (a display tensor, :361) is formed when somebody asks for it"""
+
+    def __missing__(self, key):
+        if key != 'error':
+            raise KeyError(key)
+        self[key] = (self['output'] - self['y']).abs()
+        return self[key]
+
+
 def inference_stable_net(net, x_tensor, y, matches, mask, use_black_loss=1.0, use_theta_only=0.0, before_ch=6, input_mask=True,
-                         mul=None, do_crop_rate=0.8, batch_size=None, regu_loss=0.0):
+                         mul=None, do_crop_rate=0.8, batch_size=None, regu_loss=0.0, fused=True):
     """One pass of reference s_net_bundle_nobm.py:266-381 -> the `ret` dict (same keys; 'theta', 'pts2', 'flow' added).
-    batch_size: the divisor of the batch-mean terms (GLOBAL batch under data parallelism)."""
+    batch_size: the divisor of the batch-mean terms (GLOBAL batch under data parallelism).  fused: everything after the head as
+    one autograd node (losses.train_pass); False composes the separate operators (same values)."""
     cur = 2 * before_ch if input_mask else before_ch                      # :282-285
     x = x_tensor[..., cur:cur + 1].contiguous()
     theta = net(x_tensor)
+    if fused:
+        total, parts, h_trans, black_pix, flow, _, pts2 = losses.train_pass(
+            theta, x, y, matches, mask, regu_loss=regu_loss, use_black_loss=use_black_loss, use_theta_only=use_theta_only, mul=mul,
+            grid=net.grid, do_crop_rate=do_crop_rate, batch_size=batch_size)
+        n, h, w, _ = h_trans.shape
+        ret = _Ret(parts)
+        ret.update(black_pix=black_pix.reshape(n, h, w, 1), mask=mask, matches=matches, x_tensor=x_tensor, use_theta_only=use_theta_only,
+                   y=y, output=h_trans, total_loss=total, theta=theta, pts2=pts2, flow=flow)
+        return ret
     pts1, pts2 = losses.get_4_pts(theta, grid=net.grid, do_crop_rate=do_crop_rate)
     img_l, h_trans, black_pix, flow = losses.transformer_img_loss(x, pts2, y, batch_size=batch_size)       # :332,:347-352
     feat_l, _ = losses.feature_loss(matches, mask, flow, batch_size=batch_size)                             # :335-343
     total, parts = losses.total_loss(theta, pts1, pts2, img_l, feat_l, regu_loss=regu_loss, use_black_loss=use_black_loss,
                                      use_theta_only=use_theta_only, mul=mul, do_crop_rate=do_crop_rate, batch_size=batch_size)
     n, h, w, _ = h_trans.shape
-    ret = dict(parts)
-    ret.update(error=(h_trans - y).abs(), black_pix=black_pix.reshape(n, h, w, 1), mask=mask, matches=matches, x_tensor=x_tensor,
+    ret = _Ret(parts)
+    ret.update(black_pix=black_pix.reshape(n, h, w, 1), mask=mask, matches=matches, x_tensor=x_tensor,
                use_theta_only=use_theta_only, y=y, output=h_trans, total_loss=total, theta=theta, pts2=pts2, flow=flow)
     return ret
 
 
-def train_losses(net, batch1, batch2, flow, gates, mul=None, batch_size=None):
+def train_losses(net, batch1, batch2, flow, gates, mul=None, batch_size=None, fused=True):
     """The training objective of train_bundle_nobm.py:107-141: two passes with shared weights and the temporal loss between
     them.  batch1/2 = dict(x, y, matches, mask); gates = losses.loss_gates(i).  -> (total_loss, ret1, ret2, temp_loss)"""
     m = dict(losses.V2_93_MULS)
     m.update(mul or {})
-    kw = dict(use_black_loss=float(gates['use_black']), use_theta_only=float(gates['theta_only']), mul=m, batch_size=batch_size)
+    kw = dict(use_black_loss=float(gates['use_black']), use_theta_only=float(gates['theta_only']), mul=m, batch_size=batch_size, fused=fused)
     ret1 = inference_stable_net(net, batch1['x'], batch1['y'], batch1['matches'], batch1['mask'], **kw)
     ret2 = inference_stable_net(net, batch2['x'], batch2['y'], batch2['matches'], batch2['mask'], **kw)
     t_loss = losses.temp_loss(ret1['output'], ret1['black_pix'], ret2['output'], ret2['black_pix'], flow,

@@ -105,15 +105,54 @@ MGW_API int mgw_mesh_warp_bwd_acc(const float* U, const float* theta, const floa
  * upstream_dev (here and in the other loss backwards): nullable DEVICE scalar multiplied onto `upstream` inside the kernel --
  * the autograd upstream gradient without a host read, so that a whole training step can be enqueued / graph-captured.
  * Backward: the upstream gradient of out is the loss's, d_out = upstream*2/batch * (out-y)(1-black)^2/(sums[n][1]+1e-8),
- * formed in registers inside the backward kernel (no d_out tensor is written or read); d_img nullable as before.
+ * formed in registers inside the backward kernel (no d_out tensor is written or read); d_img nullable as before; d_out_extra
+ * (nullable, [N,H,W,C]) = the gradient another consumer of `out` sends back (temp_loss), added to the loss's inside the kernel.
  * loss = sum_n sums[n][0]/(sums[n][1]+1e-8)/batch is N scalars of arithmetic left to the caller. */
 MGW_API int mgw_mesh_warp_img_loss_fwd(const float* U, const float* theta, const float* y, int N, int H, int W, int C, int gh,
                                int gw, float* Hs, float* out, float* black, float* img, float* sums, void* stream);
 MGW_API size_t mgw_mesh_warp_img_loss_bwd_workspace_bytes(int N, int H, int W, int C, int gh, int gw);
 MGW_API int mgw_mesh_warp_img_loss_bwd(const float* U, const float* theta, const float* Hs, const float* out, const float* y,
                                const float* black, const float* sums, float upstream, const float* upstream_dev, float batch,
-                               const float* d_img, int N, int H, int W, int C, int gh, int gw, float* dU, float* dtheta,
-                               void* workspace, void* stream);
+                               const float* d_img, const float* d_out_extra, int N, int H, int W, int C, int gh, int gw, float* dU,
+                               float* dtheta, void* workspace, void* stream);
+
+/* feature_loss backward taken straight to the homographies: dH_part [N*gh*gw, 8] = the dH terms (as mgw_warp_bwd forms them from a
+ * dense d_img) of d(loss)/d(flow map), which is non-zero at the <= M match pixels of a sample only -- no dense [N,H,W,2] gradient
+ * is written or read.  img = the forward's flow map, Hs its homographies, facc [N,2] = per-sample (sum of masked residuals, sum of
+ * mask) (only the count is read); upstream as mgw_feature_loss_bwd.  Feed dH_part to the solve backward as one more partial. */
+MGW_API int mgw_feature_loss_dh(const float* matches, const float* mask, const float* img, const float* Hs, const float* facc,
+                        float upstream, const float* upstream_dev, int N, int M, int H, int W, int gh, int gw, float* dH_part,
+                        void* stream);
+
+/* the O(N) scalar epilogue of img_loss / temp_loss (clamp = 0: out[0] = scale * sum_n sums[n][0] / (sums[n][1] + 1e-8)) and of
+ * feature_loss given per-sample (sum, count) pairs (clamp = 1: ... / max(sums[n][1], 1)) as one launch.  sums [N,2], out [1]. */
+MGW_API int mgw_loss_ratio_sum(const float* sums, int N, int clamp, float scale, float* out, void* stream);
+
+/* ---- one training pass: s_net_bundle_nobm.py:266-381 after the network head, as a handful of launches -------------------
+ * head [N, 2(gh+1)(gw+1)] (the network's output) -> get_4_pts (:29-71) -> transformer + img_loss (:332,:347-352) ->
+ * feature_loss / warp_pts (:215-230,:335-343) -> id / black_pos / distortion / consistency terms (:139-210,:246) -> total (:354-359).
+ * coef: HOST array of 11 floats = the multipliers of the vertex sums [4] (id, black_pos, distortion, consistency: configured
+ * multipliers, use_black_loss and element counts folded in), the multipliers of IMG = sum_n e2_n/(nb_n+1e-8)/batch, FEAT =
+ * sum_n acc_n/max(cnt_n,1)/batch and of the weight regulariser REGU (*regu_dev, nullable device scalar), the shares of the id term
+ * reported as theta_loss / grid_theta_loss, 1/batch (the GLOBAL batch under data parallelism), gate = 1 - use_theta_only:
+ * total = id + gate * (everything else), the parts are reported without the gate (:354-375).
+ * Forward outputs: pts1 [N,gh,gw,8], pts2 [N,gh+1,gw+1,2], Hs, out, black, img as mgw_mesh_warp_fwd (all required), acc [N,4]
+ * (img sums [N,2] then feature sums [N,2]), warpped [N,M,2] (nullable), vsums [4], result [9] = total, then the weighted parts
+ * theta, grid_theta, black, distortion, consistency, feature, img, regu (the reference's ret[...]).
+ * Backward: d_head [N, 2(gh+1)(gw+1)] = d(total * *g_total_dev)/d(head) (g_total_dev nullable = 1); d_out_extra (nullable) is a
+ * gradient reaching `out` from another consumer (temp_loss, train_bundle_nobm.py:115-125), added inside the warp backward; dU
+ * nullable.  The gradient of feature_loss goes straight to one dH partial per cell: no dense d(flow map) is written or read.
+ * The flow map `img` therefore must have no other differentiable consumer in this form. */
+MGW_API int mgw_train_pass_fwd(const float* head, const float* U, const float* y, const float* matches, const float* mask,
+                       const float* regu_dev, const float* coef, int N, int H, int W, int C, int gh, int gw, int M, float do_crop_rate,
+                       float* pts1, float* pts2, float* Hs, float* out, float* black, float* img, float* acc, float* warpped,
+                       float* vsums, float* result, void* stream);
+MGW_API size_t mgw_train_pass_bwd_workspace_bytes(int N, int H, int W, int C, int gh, int gw);
+MGW_API int mgw_train_pass_bwd(const float* head, const float* pts1, const float* pts2, const float* U, const float* y,
+                       const float* matches, const float* mask, const float* Hs, const float* out, const float* black,
+                       const float* img, const float* acc, const float* g_total_dev, const float* d_out_extra, const float* coef,
+                       int N, int H, int W, int C, int gh, int gw, int M, float do_crop_rate, float* dU, float* d_head,
+                       void* workspace, void* stream);
 
 /* ---- f1 (deploy side): warpRevBundle2(img, x_map, y_map), deploy_bundle.py:136-146 ---------------------------------
  * img [N,H,W,C] uint8 (the unstable frame at network size), xy [N,H,W,2] = the operator's x_map,y_map (the `img` output of
