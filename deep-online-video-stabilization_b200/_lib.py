@@ -36,7 +36,7 @@ SIGNATURES = {
     'mgw_mesh_warp_img_loss_bwd': (c_i, [c_f] * 7 + [c_fl, c_f, c_fl, c_f, c_f] + [c_i] * 6 + [c_f, c_f, c_f, c_st]),
     'mgw_feature_loss_dh': (c_i, [c_f] * 5 + [c_fl, c_f] + [c_i] * 6 + [c_f, c_st]),
     'mgw_loss_ratio_sum': (c_i, [c_f, c_i, c_i, c_fl, c_f, c_st]),
-    'mgw_train_pass_fwd': (c_i, [c_f] * 7 + [c_i] * 7 + [c_fl] + [c_f] * 10 + [c_st]),
+    'mgw_train_pass_fwd': (c_i, [c_f] * 7 + [c_i] * 7 + [c_fl] + [c_f] * 9 + [c_st]),
     'mgw_train_pass_bwd_workspace_bytes': (ctypes.c_size_t, [c_i] * 6),
     'mgw_train_pass_bwd': (c_i, [c_f] * 15 + [c_i] * 7 + [c_fl] + [c_f] * 3 + [c_st]),
     'mgw_remap_bundle_u8_workspace_bytes': (ctypes.c_size_t, [c_i, c_i, c_i]),

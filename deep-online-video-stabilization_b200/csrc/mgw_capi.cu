@@ -369,10 +369,9 @@ static mgw::PassCoef pass_coef(const float* c)
 
 int mgw_train_pass_fwd(const float* head, const float* U, const float* y, const float* matches, const float* mask, const float* regu_dev,
                        const float* coef, int N, int H, int W, int C, int gh, int gw, int M, float do_crop_rate, float* pts1, float* pts2,
-                       float* Hs, float* out, float* black, float* img, float* acc, float* warpped, float* vsums, float* result,
-                       void* stream)
+                       float* Hs, float* out, float* black, float* img, float* acc, float* warpped, float* result, void* stream)
 {
-    REQUIRE(head && U && y && matches && mask && coef && pts1 && pts2 && Hs && out && black && img && acc && vsums && result,
+    REQUIRE(head && U && y && matches && mask && coef && pts1 && pts2 && Hs && out && black && img && acc && result,
             "mgw_train_pass_fwd: null pointer");
     TRY(validate_mesh_shape("mgw_train_pass_fwd", N, H, W, C, gh, gw));
     REQUIRE(M > 0 && N <= 65535 && do_crop_rate > 0.0f, "mgw_train_pass_fwd: need M > 0, N <= 65535, do_crop_rate > 0");
@@ -382,7 +381,8 @@ int mgw_train_pass_fwd(const float* head, const float* U, const float* y, const 
     const PassCoef pc = pass_coef(coef);
     TRY(launch_vertices_fwd(head, N, gh, gw, do_crop_rate, pts2, pts1, st));                 // get_4_pts          :29-71
     TRY(launch_solve_h_fwd(pts2, N, gh, gw, Hs, st));                                        // get_Hs             st3:144-198
-    TRY(check_memset(cudaMemsetAsync(acc, 0, sizeof(float) * 4 * N, st), "memset acc"));     // img sums [N,2] | feature sums [N,2]
+    float* vsums = acc + 4 * (size_t)N;
+    TRY(check_memset(cudaMemsetAsync(acc, 0, sizeof(float) * (4 * (size_t)N + 4), st), "memset acc"));     // img [N,2] | feature [N,2] | vertex [4]
     int rc = MGW_OK;
     if (use_tma_fwd(s, U, out, black, img, &rc)) {                                           // transformer + img_loss  :332,:347-352
         TRY(launch_warp_fwd_tma(U, Hs, s, out, black, img, y, acc, st));
@@ -392,7 +392,7 @@ int mgw_train_pass_fwd(const float* head, const float* U, const float* y, const 
         TRY(launch_img_loss_fwd(out, y, black, N, H, W, C, acc, st));
     }
     TRY(launch_feature_acc_fwd(matches, mask, img, N, M, H, W, warpped, acc + 2 * (size_t)N, st));      // feature_loss  :335-343
-    TRY(launch_vertex_losses_fwd(head, pts1, pts2, N, gh, gw, do_crop_rate, vsums, nullptr, st));       // :139-210,:246
+    TRY(launch_vertex_losses_fwd(head, pts1, pts2, N, gh, gw, do_crop_rate, vsums, nullptr, st, true));  // :139-210,:246
     return launch_objective_fwd(acc, acc + 2 * (size_t)N, vsums, regu_dev, N, pc, result, st);           // :308-317,:354-359
 }
 

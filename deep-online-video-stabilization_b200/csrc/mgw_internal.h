@@ -133,7 +133,7 @@ int launch_fill_zero(void* p, size_t bytes, bool keep_in_l2, cudaStream_t st);
 
 // mgw_vertex_loss.cu : vertex regularisers (s_net_bundle_nobm.py:139-210,246-247)
 int launch_vertex_losses_fwd(const float* theta, const float* pts1, const float* pts2, int N, int gh, int gw, float do_crop_rate,
-                             float* sums, float* black_err, cudaStream_t st);
+                             float* sums, float* black_err, cudaStream_t st, bool sums_zeroed = false /* true: several blocks, reduce-adds */);
 int launch_vertex_losses_bwd(const float* theta, const float* pts1, const float* pts2, int N, int gh, int gw, float do_crop_rate,
                              const float* f, float* d_theta, float* d_pts1, float* d_pts2,
                              cudaStream_t st);

@@ -2,11 +2,11 @@
 //
 //   feature_acc_fwd : feature_loss / warp_pts (:215-230, :335-343) over a (match chunks x samples) grid -> per-sample
 //                     (sum of masked |residual|, sum of mask) accumulated into facc[N,2]
-//   feature_dh      : the backward of feature_loss taken straight to dH.  d(loss)/d(flow map) is non-zero at <= M pixels per sample,
-//                     and the flow map's only other consumer is nobody: instead of scattering it into a dense [N,H,W,2] tensor that
-//                     the warp backward then streams through (zero-fill + scatter + 8 B/px of reads), each (sample, cell) block
-//                     walks the sample's matches, keeps those whose pixel lies in its cell and reduces their dH terms
-//                     (the same terms the warp backward forms from d_img: SURVEY.md 8a-bwd) -> one extra partial per cell for K4
+//   feature_dh      : the backward of feature_loss taken straight to dH.  d(loss)/d(flow map) is non-zero at <= M pixels per sample
+//                     and the flow map has no other consumer: instead of scattering it into a dense [N,H,W,2] tensor that the warp
+//                     backward then streams through (zero-fill + scatter + 8 B/px of reads), each match adds its dH terms (the
+//                     same terms the warp backward forms from d_img: SURVEY.md 8a-bwd) to its cell -> one extra partial per cell
+//                     for K4
 //   objective_fwd   : the scalar epilogue (:308-317, :347-359): IMG, FEAT from the per-sample sums, the four vertex sums, the
 //                     configured multipliers -> total loss + the weighted parts of the reference's `ret`, one tiny launch
 #include "mgw_internal.h"
@@ -58,49 +58,41 @@ feature_acc_fwd_kernel(const float* __restrict__ matches, const float* __restric
     if (threadIdx.x == 0) { atomicAdd(facc + 2 * n, acc); atomicAdd(facc + 2 * n + 1, cnt); }
 }
 
-constexpr int kDhThreads = 128;
-
-// one block per (cell, sample); facc[n][1] = the forward's mask count of the sample
-__global__ void __launch_bounds__(kDhThreads)
+// one thread per match over a (match chunks x samples) grid; the eight dH terms of a match go to its cell's slot of extra_part
+// (zeroed by the launcher) by reduce-adds -- <= M * 8 of them per sample on gh*gw*8 addresses.  facc[n][1] = the forward's mask
+// count of the sample.  (A deterministic form -- one block per (cell, sample) walking all M matches -- is a chain of 24 dependent
+// L2 round trips: 28 us against 4.)
+__global__ void __launch_bounds__(kFeatThreads)
 feature_dh_kernel(const float* __restrict__ matches, const float* __restrict__ mask, const float* __restrict__ img,
                   const float* __restrict__ Hs, const float* __restrict__ facc, float upstream, const float* __restrict__ up_dev, int N,
                   int M, int H, int W, int gh, int gw, float* __restrict__ extra_part)
 {
-    __shared__ float sh[kDhThreads / 32];
-    const int cell = blockIdx.x, n = blockIdx.y, ci = cell / gw, cj = cell % gw;
-    const int cell_h = H / gh, cell_w = W / gw;
+    const int n = blockIdx.y, m = blockIdx.x * kFeatThreads + threadIdx.x;
+    if (m >= M) return;
+    const float mk = __ldg(mask + (size_t)n * M + m);
+    if (mk == 0.0f) return;
+    const float4 mt = __ldg(reinterpret_cast<const float4*>(matches) + (size_t)n * M + m);
+    const int px = match_px(mt.x, W), py = match_px(mt.y, H);
+    const int cell = cell_of(py, H / gh, gh) * gw + cell_of(px, W / gw, gw);
+    const float2 g = __ldg(reinterpret_cast<const float2*>(img) + ((size_t)n * H + py) * W + px);
     float Hc[9];
 #pragma unroll
     for (int k = 0; k < 9; ++k) Hc[k] = __ldg(Hs + ((size_t)n * gh * gw + cell) * 9 + k);
     if (up_dev) upstream *= __ldg(up_dev);
     const float kk = upstream / (fmaxf(__ldg(facc + 2 * n + 1), 1.0f) * (float)N);
-    const float stepx = lin_step(W), stepy = lin_step(H);
-    float dh[8];
-#pragma unroll
-    for (int k = 0; k < 8; ++k) dh[k] = 0.0f;
-    for (int m = threadIdx.x; m < M; m += kDhThreads) {
-        const float mk = __ldg(mask + (size_t)n * M + m);
-        const float4 mt = __ldg(reinterpret_cast<const float4*>(matches) + (size_t)n * M + m);
-        const int px = match_px(mt.x, W), py = match_px(mt.y, H);
-        if (mk == 0.0f || cell_of(py, cell_h, gh) != ci || cell_of(px, cell_w, gw) != cj) continue;
-        const float2 g = __ldg(reinterpret_cast<const float2*>(img) + ((size_t)n * H + py) * W + px);
-        const float dx = g.x - mt.z, dy = g.y - mt.w;                  // d|t| = sign(t), sign(0) = 0
-        const float gxn = kk * mk * ((dx > 0.0f) ? 1.0f : ((dx < 0.0f) ? -1.0f : 0.0f));
-        const float gyn = kk * mk * ((dy > 0.0f) ? 1.0f : ((dy < 0.0f) ? -1.0f : 0.0f));
-        const float xt = lin_at(px, stepx), yt = lin_at(py, stepy);
-        const Proj pr = project(Hc, xt, yt);
-        // dH terms of one pixel: xn = xs/zs, yn = ys/zs
-        const float rz = __frcp_rn(pr.zs);
-        const float dxs = gxn * rz, dys = gyn * rz, dzs = -(gxn * pr.xn + gyn * pr.yn) * rz;
-        dh[0] = fmaf(dxs, xt, dh[0]); dh[1] = fmaf(dxs, yt, dh[1]); dh[2] += dxs;
-        dh[3] = fmaf(dys, xt, dh[3]); dh[4] = fmaf(dys, yt, dh[4]); dh[5] += dys;
-        dh[6] = fmaf(dzs, xt, dh[6]); dh[7] = fmaf(dzs, yt, dh[7]);
-    }
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
-        const float v = block_sum_n(dh[k], sh);
-        if (threadIdx.x == 0) extra_part[((size_t)n * gh * gw + cell) * 8 + k] = v;
-    }
+    const float dx = g.x - mt.z, dy = g.y - mt.w;                  // d|t| = sign(t), sign(0) = 0
+    const float gxn = kk * mk * ((dx > 0.0f) ? 1.0f : ((dx < 0.0f) ? -1.0f : 0.0f));
+    const float gyn = kk * mk * ((dy > 0.0f) ? 1.0f : ((dy < 0.0f) ? -1.0f : 0.0f));
+    if (gxn == 0.0f && gyn == 0.0f) return;
+    const float xt = lin_at(px, lin_step(W)), yt = lin_at(py, lin_step(H));
+    const Proj pr = project(Hc, xt, yt);
+    // dH terms of one pixel: xn = xs/zs, yn = ys/zs
+    const float rz = __frcp_rn(pr.zs);
+    const float dxs = gxn * rz, dys = gyn * rz, dzs = -(gxn * pr.xn + gyn * pr.yn) * rz;
+    float* dst = extra_part + ((size_t)n * gh * gw + cell) * 8;
+    atomicAdd(dst + 0, dxs * xt); atomicAdd(dst + 1, dxs * yt); atomicAdd(dst + 2, dxs);
+    atomicAdd(dst + 3, dys * xt); atomicAdd(dst + 4, dys * yt); atomicAdd(dst + 5, dys);
+    atomicAdd(dst + 6, dzs * xt); atomicAdd(dst + 7, dzs * yt);
 }
 
 constexpr int kObjThreads = 128;
@@ -162,8 +154,10 @@ int launch_feature_acc_fwd(const float* matches, const float* mask, const float*
 int launch_feature_dh(const float* matches, const float* mask, const float* img, const float* Hs, const float* facc, float upstream,
                       const float* up_dev, int N, int M, int H, int W, int gh, int gw, float* extra_part, cudaStream_t st)
 {
-    feature_dh_kernel<<<dim3(gh * gw, N), kDhThreads, 0, st>>>(matches, mask, img, Hs, facc, upstream, up_dev, N, M, H, W, gh, gw,
-                                                               extra_part);
+    if (cudaMemsetAsync(extra_part, 0, sizeof(float) * (size_t)N * gh * gw * 8, st) != cudaSuccess)
+        return set_error(MGW_ERR_CUDA, "memset dH partial: %s", cudaGetErrorString(cudaGetLastError()));
+    feature_dh_kernel<<<dim3((M + kFeatThreads - 1) / kFeatThreads, N), kFeatThreads, 0, st>>>(matches, mask, img, Hs, facc, upstream, up_dev,
+                                                                                               N, M, H, W, gh, gw, extra_part);
     return check_launch("feature_dh");
 }
 

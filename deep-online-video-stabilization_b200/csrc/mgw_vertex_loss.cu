@@ -78,10 +78,12 @@ vertex_losses_fwd_kernel(const float* __restrict__ theta, const float* __restric
     __shared__ float sh[kThreads / 32];
     const int V = (gh + 1) * (gw + 1);
     float s_id = 0.0f, s_black = 0.0f, s_dist = 0.0f, s_cons = 0.0f;
+    // one block: fixed summation order, sums overwritten; several blocks (sums zeroed by the caller): one reduce-add per block and term
+    const int t0 = blockIdx.x * kThreads + threadIdx.x, nthr = gridDim.x * kThreads;
     if (theta)
-        for (int q = threadIdx.x; q < N * V * 2; q += kThreads) s_id += fabsf(__ldg(theta + q));
+        for (int q = t0; q < N * V * 2; q += nthr) s_id += fabsf(__ldg(theta + q));
     if (pts1)
-        for (int q = threadIdx.x; q < N * gh * gw; q += kThreads) {
+        for (int q = t0; q < N * gh * gw; q += nthr) {
             float x[4], y[4];
 #pragma unroll
             for (int k = 0; k < 4; ++k) { x[k] = __ldg(pts1 + (size_t)q * 8 + k); y[k] = __ldg(pts1 + (size_t)q * 8 + 4 + k); }
@@ -96,7 +98,7 @@ vertex_losses_fwd_kernel(const float* __restrict__ theta, const float* __restric
             s_dist += cell;
         }
     if (pts2)
-        for (int q = threadIdx.x; q < N * V * 2; q += kThreads) {
+        for (int q = t0; q < N * V * 2; q += nthr) {
             const int comp = q & 1, v = (q >> 1) % V, n = (q >> 1) / V, i = v / (gw + 1), j = v % (gw + 1);
             const float* P = pts2 + (size_t)n * V * 2 + comp;
             auto at = [&](int ii, int jj) { return __ldg(P + (size_t)(ii * (gw + 1) + jj) * 2); };
@@ -112,7 +114,10 @@ vertex_losses_fwd_kernel(const float* __restrict__ theta, const float* __restric
     s_black = block_sum256(s_black, sh);
     s_dist = block_sum256(s_dist, sh);
     s_cons = block_sum256(s_cons, sh);
-    if (threadIdx.x == 0) { sums[0] = s_id; sums[1] = s_black; sums[2] = s_dist; sums[3] = s_cons; }
+    if (threadIdx.x == 0) {
+        if (gridDim.x == 1) { sums[0] = s_id; sums[1] = s_black; sums[2] = s_dist; sums[3] = s_cons; }
+        else { atomicAdd(sums, s_id); atomicAdd(sums + 1, s_black); atomicAdd(sums + 2, s_dist); atomicAdd(sums + 3, s_cons); }
+    }
 }
 
 // f[k] (device) = d(total) / d(sums[k]); or (f == nullptr) coef[k] * (g_dev ? *g_dev : 1).  ACC: d_pts2 += instead of =
@@ -171,11 +176,13 @@ vertex_losses_bwd_kernel(const float* __restrict__ theta, const float* __restric
 }  // namespace
 
 int launch_vertex_losses_fwd(const float* theta, const float* pts1, const float* pts2, int N, int gh, int gw, float do_crop_rate,
-                             float* sums, float* black_err, cudaStream_t st)
+                             float* sums, float* black_err, cudaStream_t st, bool sums_zeroed)
 {
     // h = 2.0 / grid_h, w = 2.0 / grid_w; k = h / w (hw == 0) or w / h, in Python doubles then a float32 constant (:151-163)
     const double h = 2.0 / gh, w = 2.0 / gw;
-    vertex_losses_fwd_kernel<<<1, kThreads, 0, st>>>(theta, pts1, pts2, N, gh, gw, 1.0f / do_crop_rate, (float)(h / w), (float)(w / h), sums,
+    const int items = N * (gh + 1) * (gw + 1) * 2;
+    const int blocks = sums_zeroed ? std::max(1, std::min(32, items / kThreads)) : 1;
+    vertex_losses_fwd_kernel<<<blocks, kThreads, 0, st>>>(theta, pts1, pts2, N, gh, gw, 1.0f / do_crop_rate, (float)(h / w), (float)(w / h), sums,
                                                      black_err);
     return check_launch("vertex_losses_fwd");
 }

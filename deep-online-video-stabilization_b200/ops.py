@@ -262,7 +262,7 @@ def _coef_array(coef):
 
 def train_pass_fwd(head, U, y, matches, mask, coef, gh, gw, do_crop_rate=0.8, regu=None, want_warpped=True):
     """mgw_train_pass_fwd: head -> get_4_pts -> transformer + img_loss -> feature_loss -> vertex terms -> total, 7 launches.
-    -> dict(pts1, pts2, Hs, out, black, img, acc, warpped, vsums, result)."""
+    -> dict(pts1, pts2, Hs, out, black, img, acc, warpped, result)."""
     head, U, y, matches, mask = (_chk(t, nm) for t, nm in ((head, 'head'), (U, 'U'), (y, 'y'), (matches, 'matches'), (mask, 'mask')))
     n, h, w, c = U.shape
     if tuple(y.shape) != (n, h, w, c):
@@ -276,11 +276,11 @@ def train_pass_fwd(head, U, y, matches, mask, coef, gh, gw, do_crop_rate=0.8, re
     dev = U.device
     f = lambda *shape: torch.empty(shape, device=dev, dtype=torch.float32)      # noqa: E731
     r = dict(pts1=f(n, gh, gw, 8), pts2=f(n, gh + 1, gw + 1, 2), Hs=f(n, gh, gw, 9), out=f(n, h, w, c), black=f(n, h, w), img=f(n, h, w, 2),
-             acc=f(n, 4), warpped=f(n, m, 2) if want_warpped else None, vsums=f(4), result=f(9))
+             acc=f(4 * n + 4), warpped=f(n, m, 2) if want_warpped else None, result=f(9))
     with torch.cuda.device(dev):
         check(lib.mgw_train_pass_fwd(_p(head), _p(U), _p(y), _p(matches), _p(mask), _p(regu), _coef_array(coef), n, h, w, c, gh, gw, m,
                                      float(do_crop_rate), _p(r['pts1']), _p(r['pts2']), _p(r['Hs']), _p(r['out']), _p(r['black']),
-                                     _p(r['img']), _p(r['acc']), _p(r['warpped']), _p(r['vsums']), _p(r['result']), _st()),
+                                     _p(r['img']), _p(r['acc']), _p(r['warpped']), _p(r['result']), _st()),
               'mgw_train_pass_fwd')
     return r
 

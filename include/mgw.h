@@ -136,8 +136,8 @@ MGW_API int mgw_loss_ratio_sum(const float* sums, int N, int clamp, float scale,
  * sum_n acc_n/max(cnt_n,1)/batch and of the weight regulariser REGU (*regu_dev, nullable device scalar), the shares of the id term
  * reported as theta_loss / grid_theta_loss, 1/batch (the GLOBAL batch under data parallelism), gate = 1 - use_theta_only:
  * total = id + gate * (everything else), the parts are reported without the gate (:354-375).
- * Forward outputs: pts1 [N,gh,gw,8], pts2 [N,gh+1,gw+1,2], Hs, out, black, img as mgw_mesh_warp_fwd (all required), acc [N,4]
- * (img sums [N,2] then feature sums [N,2]), warpped [N,M,2] (nullable), vsums [4], result [9] = total, then the weighted parts
+ * Forward outputs: pts1 [N,gh,gw,8], pts2 [N,gh+1,gw+1,2], Hs, out, black, img as mgw_mesh_warp_fwd (all required), acc [4N+4]
+ * (img sums [N,2], feature sums [N,2], vertex sums [4]), warpped [N,M,2] (nullable), result [9] = total, then the weighted parts
  * theta, grid_theta, black, distortion, consistency, feature, img, regu (the reference's ret[...]).
  * Backward: d_head [N, 2(gh+1)(gw+1)] = d(total * *g_total_dev)/d(head) (g_total_dev nullable = 1); d_out_extra (nullable) is a
  * gradient reaching `out` from another consumer (temp_loss, train_bundle_nobm.py:115-125), added inside the warp backward; dU
@@ -146,7 +146,7 @@ MGW_API int mgw_loss_ratio_sum(const float* sums, int N, int clamp, float scale,
 MGW_API int mgw_train_pass_fwd(const float* head, const float* U, const float* y, const float* matches, const float* mask,
                        const float* regu_dev, const float* coef, int N, int H, int W, int C, int gh, int gw, int M, float do_crop_rate,
                        float* pts1, float* pts2, float* Hs, float* out, float* black, float* img, float* acc, float* warpped,
-                       float* vsums, float* result, void* stream);
+                       float* result, void* stream);
 MGW_API size_t mgw_train_pass_bwd_workspace_bytes(int N, int H, int W, int C, int gh, int gw);
 MGW_API int mgw_train_pass_bwd(const float* head, const float* pts1, const float* pts2, const float* U, const float* y,
                        const float* matches, const float* mask, const float* Hs, const float* out, const float* black,

@@ -329,10 +329,14 @@ def path_only():
     tot = 0
     rets = []
     for b in (b1, b2):
-        p1, p2 = mgw.get_4_pts(th, grid=(4, 4))
-        il, out, black, fl = mgw.transformer_img_loss(b['x'][..., 12:13].contiguous(), p2, b['y'], batch_size=256)
-        ftl, _ = mgw.feature_loss(b['matches'], b['mask'], fl, batch_size=256)
-        t, _ = mgw.total_loss(th, p1, p2, il, ftl, batch_size=256)
+        x = b['x'][..., 12:13].contiguous()
+        if FUSED_PASS:      # everything after the head as one autograd node (mgw_train_pass_fwd / _bwd)
+            t, _, out, black, _, _, _ = mgw.train_pass(th, x, b['y'], b['matches'], b['mask'], batch_size=256)
+        else:               # the separate operators composed by torch autograd
+            p1, p2 = mgw.get_4_pts(th, grid=(4, 4))
+            il, out, black, fl = mgw.transformer_img_loss(x, p2, b['y'], batch_size=256)
+            ftl, _ = mgw.feature_loss(b['matches'], b['mask'], fl, batch_size=256)
+            t, _ = mgw.total_loss(th, p1, p2, il, ftl, batch_size=256)
         tot = tot + t
         rets.append((out, black))
     tot = tot + 500.0 * mgw.temp_loss(rets[0][0], rets[0][1], rets[1][0], rets[1][1], flow, batch_size=256)
@@ -342,24 +346,32 @@ def path_only():
 
 with torch.no_grad():
     theta_leaf = net(b1['x'])
-t_path = dev_time(path_only, 10, flush_l2=False)
-# the same objective captured once in a CUDA graph (no host synchronisation anywhere in it: the loss backwards read their
-# upstream gradient on the device), replayed
-side = torch.cuda.Stream()
-side.wait_stream(torch.cuda.current_stream())
-with torch.cuda.stream(side):
-    for _ in range(3):
-        path_only()
-torch.cuda.current_stream().wait_stream(side)
-torch.cuda.synchronize()
-graph = torch.cuda.CUDAGraph()
-with torch.cuda.graph(graph):
+path = {}
+for FUSED_PASS in (False, True):
+    l0 = mgw.launch_count()
     path_only()
-t_path_graph = dev_time(graph.replay, 20, flush_l2=False)
+    nl = mgw.launch_count() - l0
+    t_path = dev_time(path_only, 10, flush_l2=False)
+    # the same objective captured once in a CUDA graph (no host synchronisation anywhere in it: the loss backwards read their
+    # upstream gradient on the device), replayed
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        for _ in range(3):
+            path_only()
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        path_only()
+    path['fused' if FUSED_PASS else 'composed'] = dict(us_eager=t_path, us_graph_replay=dev_time(graph.replay, 20, flush_l2=False),
+                                                      launches_of_this_library=nl)
+t_path, t_path_graph = path['fused']['us_eager'], path['fused']['us_graph_replay']
 res['config5_train_step_32_clips_per_gpu'] = {
     'us_step_backbone_plus_path_plus_adam': t_step, 'us_path_only_fwd_bwd_all_losses_eager': t_path, 'us_path_only_graph_replay': t_path_graph,
-    'path_share_pct_eager': 100 * t_path / t_step,
+    'path_share_pct_eager': 100 * t_path / t_step, 'path_only': path,
     'launches_of_this_library_per_step': ours,
     'note': 'two passes (shared weights) + temp_loss, every loss term of the reference objective, Adam; backbone = torch fp32 carrier; '
-            'the path = get_4_pts + fused warp/img_loss fwd+bwd + feature/temp/vertex losses on the 1-channel current frame'}
+            'the path = get_4_pts + fused warp/img_loss fwd+bwd + feature/temp/vertex losses on the 1-channel current frame; fused = one '
+            'autograd node per pass (mgw_train_pass_fwd/bwd), composed = the separate operators under torch autograd'}
 print(json.dumps(res, indent=1))
