@@ -101,6 +101,24 @@ def test_train_pass_equals_the_composed_operators(mgw, n, h, w, c, m, impl, kw, 
     assert relmax(a['g'], b['g']) <= 1.5e-3, relmax(a['g'], b['g'])
 
 
+@pytest.mark.parametrize('impl,n,h,w,c', [('auto', 3, 96, 128, 3), ('generic', 2, 48, 64, 1), ('auto', 2, 288, 512, 3)])
+def test_train_pass_gradient_of_the_frame(mgw, impl, n, h, w, c):
+    """x.requires_grad: the pass also returns d(total)/d(x) (the dU variant of the fused warp backward, zero-filled inside)"""
+    mgw.set_impl(impl)
+    raw = inputs(n, h, w, c, 100, 980)
+    t = {k: dev(v) for k, v in raw.items()}
+    flow = dev(smooth_flow(n, h, w))
+    gs = {}
+    for name, fn in (('composed', composed), ('fused', fused)):
+        head = t['head'].clone().requires_grad_(True)
+        tt = dict(t, x=t['x'].clone().requires_grad_(True))
+        total = fn(mgw, tt, head, {}, n, True, flow)[0]
+        gs[name] = [g.cpu().numpy() for g in torch.autograd.grad(total, [head, tt['x']])]
+    assert np.abs(gs['composed'][1]).max() > 0
+    assert relmax(gs['fused'][1], gs['composed'][1]) <= 2e-5, relmax(gs['fused'][1], gs['composed'][1])
+    assert relmax(gs['fused'][0], gs['composed'][0]) <= 1.5e-3
+
+
 def test_vertex_terms_of_the_pass_are_bit_equal_to_the_composed_path(mgw):
     """with the image-side multipliers at zero the pass is get_4_pts + vertex regularisers only: no atomics, no solve -> same bits"""
     mgw.set_impl('auto')
