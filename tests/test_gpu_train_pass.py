@@ -119,6 +119,47 @@ def test_train_pass_gradient_of_the_frame(mgw, impl, n, h, w, c):
     assert relmax(gs['fused'][0], gs['composed'][0]) <= 1.5e-3
 
 
+@pytest.mark.parametrize('seed', range(8))
+def test_train_pass_random_shapes_and_grids(mgw, seed):
+    """random batch / frame size / channel count / grid / match count / gates / multipliers: the fused node against the composed
+    operators (values, image-side tensors bit for bit, gradient of the head)"""
+    mgw.set_impl('auto')
+    rs = np.random.RandomState(4000 + seed)
+    n, c = int(rs.randint(1, 5)), int(rs.choice([1, 3, 4]))
+    gh, gw = int(rs.randint(1, 6)), int(rs.randint(1, 6))
+    h, w = gh * int(rs.randint(6, 40)) + int(rs.randint(0, 3)), gw * 4 * int(rs.randint(2, 12))
+    m = int(rs.randint(1, 400))
+    nv = 2 * (gh + 1) * (gw + 1)
+    raw = inputs(n, h, w, c, m, 4100 + seed)
+    raw['head'] = synth.randn((n, nv), 4200 + seed, float(rs.choice([0.02, 0.08, 0.2])))
+    t = {k: dev(v) for k, v in raw.items()}
+    flow = dev(smooth_flow(n, h, w))
+    kw = dict(use_black_loss=float(rs.randint(0, 2)), use_theta_only=0.0, regu_loss=float(rs.uniform(0, 1)),
+              mul=dict(grid_theta_mul=float(rs.uniform(0, 1)), feature_mul=float(rs.uniform(0.5, 2))))
+    batch = n * int(rs.randint(1, 9))
+    res = {}
+    for name in ('composed', 'fused'):
+        head = t['head'].clone().requires_grad_(True)
+        if name == 'composed':
+            p1, p2 = mgw.get_4_pts(head, grid=(gh, gw))
+            il, out, black, fl = mgw.transformer_img_loss(t['x'], p2, t['y'], batch_size=batch)
+            ftl, warpped = mgw.feature_loss(t['matches'], t['mask'], fl, batch_size=batch)
+            total, parts = mgw.total_loss(head, p1, p2, il, ftl, batch_size=batch, **kw)
+        else:
+            total, parts, out, black, fl, warpped, p2 = mgw.train_pass(head, t['x'], t['y'], t['matches'], t['mask'], grid=(gh, gw),
+                                                                       batch_size=batch, **kw)
+        total = total + 500.0 * mgw.temp_loss(out, black, t['out2'], t['black2'], flow, batch_size=batch)
+        (g,) = torch.autograd.grad(total, head)
+        res[name] = (float(total), {k: float(v) for k, v in parts.items()}, out.detach().cpu().numpy(), fl.detach().cpu().numpy(),
+                     g.cpu().numpy())
+    a, b = res['fused'], res['composed']
+    assert np.array_equal(a[2], b[2]) and np.array_equal(a[3], b[3])
+    assert abs(a[0] - b[0]) <= 5e-6 * abs(b[0]), (a[0], b[0])
+    for k, v in b[1].items():
+        assert abs(a[1][k] - v) <= 5e-6 * max(abs(v), 1e-12), (k, a[1][k], v)
+    assert np.isfinite(a[4]).all() and relmax(a[4], b[4]) <= 3e-3, relmax(a[4], b[4])
+
+
 def test_vertex_terms_of_the_pass_are_bit_equal_to_the_composed_path(mgw):
     """with the image-side multipliers at zero the pass is get_4_pts + vertex regularisers only: no atomics, no solve -> same bits"""
     mgw.set_impl('auto')
