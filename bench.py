@@ -221,6 +221,10 @@ def main():
                 # schedule (a CTA displaced by the NCCL kernel would finish late), the fill's 64-thread blocks leave the SMs
                 # nearly empty, so the GEMM and the NCCL kernel become resident at once
                 reducer.launch(slot=(i - 1) % nset, features=feats, dtheta=dth_slots[(i - 1) % nset])
+            if fill_mode == 'race':     # timing experiment only (WRONG dU): the fill next to the backward, no ordering between them
+                side.wait_stream(cur)
+                with torch.cuda.stream(side):
+                    ops.fill_zero(dU_buf, keep_in_l2=keep)
             if fill_mode == 'after_fwd':
                 ops.fill_zero(dU_buf, keep_in_l2=keep)
             if fill_mode == 'side':
@@ -230,6 +234,8 @@ def main():
             else:
                 dU, dtheta = ops.mesh_warp_bwd(s['U'], s['theta'], Hs, s['d_out'], s['d_img'], accumulate_into=dU_buf,
                                                dtheta_out=dth_slots[i % nset])
+            if fill_mode == 'race':
+                cur.wait_stream(side)
             if world > 1 and sync_reduce:
                 reducer.launch(slot=i % nset, features=feats, dtheta=dth_slots[i % nset])
             if world > 1:
