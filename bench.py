@@ -32,6 +32,19 @@ H, W, C, GH, GW = 288, 512, 3, 4, 4
 FWD_BYTES_PER_PX = 8 * C + 12      # read U 4C, write out 4C, black 4, x/y maps 8        
 BWD_BYTES_PER_PX = 12 * C + 8      # read d_out 4C, U 4C, write dU 4C, read d_img 8
 METRIC = 'warp_fwd_bwd_mpix_per_s'
+# where the zero-fill of dU sits in the step (see make_step): 'pipelined' = dU double-buffered, the fill of the buffer step i+1
+# accumulates into runs next to step i's backward (mgw_mesh_warp_bwd_acc); 'fused' = inside the plain backward call, behind the forward
+# 'pipelined_tail' = the same double buffering with the fill AFTER the backward, next to the join of the all-reduce (tuning aid).
+# The headline step keeps the fill inside the call ('fused') at every GPU count, so that the weak-scaling figures compare the same
+# schedule; the double-buffered form is reported next to it on one GPU (`dU_double_buffered`: 122.8 vs 126.9 us).  In a 32-frame
+# step that also carries the NCCL all-reduce and the head-gradient GEMM one more concurrent kernel costs more than it hides (2 GPUs:
+# 145.0 us next to the backward, 148.5 us after it, 137.0 us with the fill inside the call); config #5's 64+ frames per rank gain.
+FILL_MODE = os.environ.get('BENCH_FILL', '')
+PIPELINED = ('pipelined', 'pipelined_tail')
+
+
+def fill_mode_for(world, frames_per_rank):
+    return FILL_MODE or 'fused'
 
 
 def peaks():
@@ -186,11 +199,17 @@ def main():
     feats = torch.randn(n, 512, device=dev)
     reducer = mgw.parallel.MeshHeadGradReducer(512, 2 * (GH + 1) * (GW + 1), dev, nbuf=R)
 
-    def make_step(sets, feats, reducer, sync_reduce=False):
+    def make_step(sets, feats, reducer, sync_reduce=False, fill_mode=None):
         """the step over rotating input sets: K1, K2 (PDL), zero-fill of dU on a side branch, K3, K4 (PDL); with more than one
         rank the head gradient + all-reduce of the PREVIOUS step (overlapped form) or of THIS step (synchronous form)."""
         nset = len(sets)
-        dU_buf = torch.empty_like(sets[0]['U'])
+        fill_mode = fill_mode or fill_mode_for(world, sets[0]['U'].shape[0])
+        # 'pipelined' double-buffers dU: step i accumulates into buffer i % 2 (mgw_mesh_warp_bwd_acc) while the zero-fill of the
+        # buffer step i+1 will use runs next to its backward on a side branch -- one fill per step inside the timed region, every
+        # step's dU complete and correct (tests/test_gpu_configs.py::test_double_buffered_dU_pipeline)
+        dU_bufs = [torch.zeros_like(sets[0]['U']) for _ in range(2 if fill_mode in PIPELINED else 1)]
+        dU_buf = dU_bufs[0]
+        ngraph = nset * 2 if (fill_mode in PIPELINED and nset % 2) else nset
         dth_slots = [torch.zeros_like(sets[0]['theta']) for _ in range(nset)]
         side = torch.cuda.Stream(device=dev)
 
@@ -202,7 +221,6 @@ def main():
             # and backward on the main stream; with_k1 = on a side branch next to K1, joined before K2; side = on a side branch next
             # to the whole forward; serial = before K1; none = no fill (wrong dU, timing only); fused (default) = no fill here at
             # all: the plain backward entry point zero-fills dU itself (under the backward pipeline's own shadow when that runs)
-            fill_mode = os.environ.get('BENCH_FILL', 'fused')
             if fill_mode == 'serial':
                 ops.fill_zero(dU_buf, keep_in_l2=keep)
             if fill_mode in ('side', 'with_k1'):
@@ -225,19 +243,31 @@ def main():
                 side.wait_stream(cur)
                 with torch.cuda.stream(side):
                     ops.fill_zero(dU_buf, keep_in_l2=keep)
+            if fill_mode == 'pipelined':
+                side.wait_stream(cur)
+                with torch.cuda.stream(side):
+                    ops.fill_zero(dU_bufs[(i + 1) % 2], keep_in_l2=False)
             if fill_mode == 'after_fwd':
                 ops.fill_zero(dU_buf, keep_in_l2=keep)
             if fill_mode == 'side':
                 cur.wait_stream(side)
             if fill_mode == 'fused':
                 dU, dtheta = ops.mesh_warp_bwd(s['U'], s['theta'], Hs, s['d_out'], s['d_img'], dU_out=dU_buf, dtheta_out=dth_slots[i % nset])
+            elif fill_mode in PIPELINED:
+                dU, dtheta = ops.mesh_warp_bwd(s['U'], s['theta'], Hs, s['d_out'], s['d_img'], accumulate_into=dU_bufs[i % 2],
+                                               dtheta_out=dth_slots[i % nset])
             else:
                 dU, dtheta = ops.mesh_warp_bwd(s['U'], s['theta'], Hs, s['d_out'], s['d_img'], accumulate_into=dU_buf,
                                                dtheta_out=dth_slots[i % nset])
-            if fill_mode == 'race':
+            if fill_mode in ('race', 'pipelined'):
                 cur.wait_stream(side)
             if world > 1 and sync_reduce:
                 reducer.launch(slot=i % nset, features=feats, dtheta=dth_slots[i % nset])
+            if fill_mode == 'pipelined_tail':           # next to the all-reduce the step is about to wait for
+                side.wait_stream(cur)
+                with torch.cuda.stream(side):
+                    ops.fill_zero(dU_bufs[(i + 1) % 2], keep_in_l2=False)
+                cur.wait_stream(side)
             if world > 1:
                 reducer.wait()                          # join: fork and join both lie inside the step (CUDA-graph capturable)
             return dtheta
@@ -247,13 +277,13 @@ def main():
             # The step is launch-bound on the host once NCCL is in it (a dozen launches for ~100 us of GPU work): capture one
             # CUDA graph per rotating input set and replay.  Same kernels, same work; eager launches if capture is not possible.
             try:
-                for i in range(nset):
+                for i in range(ngraph):
                     step_eager(i)
                 if world > 1:
                     reducer.wait()
                 torch.cuda.synchronize()
                 graphs = []
-                for i in range(nset):
+                for i in range(ngraph):
                     gph = torch.cuda.CUDAGraph()
                     # thread_local: the NCCL watchdog thread polls CUDA events while we capture
                     with torch.cuda.graph(gph, capture_error_mode='thread_local'):
@@ -265,11 +295,15 @@ def main():
                 graphs = None
                 torch.cuda.synchronize()
 
-        def step(i):
+        state = {'k': 0}      # the steps follow each other whatever index the caller passes (the dU buffers alternate)
+
+        def step(_i):
+            k = state['k']
+            state['k'] = k + 1
             if graphs is not None:
-                graphs[i % nset].replay()
+                graphs[k % ngraph].replay()
             else:
-                step_eager(i)
+                step_eager(k)
         return step, step_eager, graphs, dU_buf
 
     def timed(fn, steps, warm, before_stop=None):
@@ -305,6 +339,11 @@ def main():
     if world > 1:
         reducer.wait()
     launches_per_step = mgw.launch_count() - l0          # kernels of OUR library per step (replayed as-is under the graph)
+    fill_mode = fill_mode_for(world, n)
+    if fill_mode in PIPELINED:
+        step_eager(1)                                    # an even number of steps: the dU buffers are back in phase
+        if world > 1:
+            reducer.wait()
     ms_total = timed(step, K, Wm)
     launches_timed = launches_per_step * K
     clocks = sampler.stop() if rank == 0 else None
@@ -319,6 +358,17 @@ def main():
         ms_s = timed(step, ks, 3)
         sustained = {'ms_per_step': ms_s / ks, 'steps': ks, 'seconds': ms_s * 1e-3, 'value': P * world * ks / (ms_s * 1e-3) / 1e6,
                      'unit': 'Mpix/s', 'clocks': sm2.stop() if rank == 0 else None}
+
+    # --- the same step with dU double-buffered: the zero-fill of the buffer step i+1 accumulates into runs next to step i's backward
+    # (mgw_mesh_warp_bwd_acc): what a training loop that owns two dU buffers gets.  One GPU only (see FILL_MODE above).
+    double_buffered = None
+    if not args.no_configs and fill_mode == 'fused' and world == 1:
+        step_db, _, _, _ = make_step(sets, feats, reducer, fill_mode='pipelined')
+        ms_db = timed(step_db, K, Wm) / K
+        double_buffered = {'ms_per_step': ms_db, 'value': P / (ms_db * 1e-3) / 1e6, 'unit': 'Mpix/s',
+                           'note': 'one zero-fill per step inside the timed region, of the buffer the NEXT step accumulates into, next to '
+                                   'this step\'s backward; every step\'s dU complete (tests: test_double_buffered_dU_pipeline)'}
+        del step_db
 
     # --- per-kernel timings (same rotation, CUDA events around the single C-ABI call)
     Hs_sets = [ops.solve_h_fwd(s['theta']) for s in sets]
@@ -456,6 +506,12 @@ def main():
         'config': {'workload': 'configs[1]: %d x %dx%dx%d fp32 frames per GPU, %dx%d mesh warp forward+backward (dU + dtheta)' % (n, H, W, C, GH, GW),
                    'l2': 'inputs rotate over %d sets of 151 MB (> 126 MB L2)' % R, 'kernel_impl': args.kernel_impl,
                    'launch': 'cuda graph replay' if graphs is not None else 'eager',
+                   'dU_zero_fill': {'pipelined': 'one fill per step inside the timed region; dU double-buffered: the fill of the buffer step i+1 '
+                                                 'accumulates into (mgw_mesh_warp_bwd_acc) runs next to the backward of step i',
+                                    'pipelined_tail': 'one fill per step inside the timed region; dU double-buffered: the fill of the buffer '
+                                                      'step i+1 accumulates into (mgw_mesh_warp_bwd_acc) runs after the backward of step i, '
+                                                      'next to the wait for the all-reduce',
+                                    'fused': 'inside the backward call (mgw_mesh_warp_bwd), between forward and backward'}.get(fill_mode, fill_mode),
                    'parallelism': ('dp%d (batch-sharded, 100 KB mesh-head grad all-reduce of step i-1 overlapped with step i; the '
                                    'synchronous form is in configs.config5)' % world) if world > 1 else 'single GPU',
                    'host_cores_pinned_per_rank': ncores},
@@ -466,6 +522,8 @@ def main():
                 'd2h_bytes_per_step': d2h, 'ms_per_step': ms_e2e, 'steps': Ke, 'h2d_gbs_per_rank': h2d / (ms_e2e * 1e-3) / 1e9},
         'gpu_launches': launches_timed, 'clocks': clocks,
     }
+    if double_buffered is not None:
+        line['dU_double_buffered'] = double_buffered
     if sustained is not None:
         line['sustained'] = sustained
     if e2e_u8 is not None:
@@ -589,7 +647,9 @@ def other_configs(mgw, ops, dev, rank, world, timed, make_step, keep):
     for name, sync in (('overlapped', False), ('synchronous', True)):
         if world == 1 and sync:
             continue
-        step5, _, _, _ = make_step(set5 * 2, feats5, red5, sync_reduce=sync)
+        mode5 = FILL_MODE or ('pipelined' if nb >= 64 else 'fused')
+        rec5['dU_zero_fill'] = mode5
+        step5, _, _, _ = make_step(set5 * 2, feats5, red5, sync_reduce=sync, fill_mode=mode5)
         k5 = 20
         ms5 = timed(step5, k5, 3)
         rec5['ms_per_step_' + name] = ms5 / k5

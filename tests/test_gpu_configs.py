@@ -391,3 +391,56 @@ def test_two_gpu_sharded_step_equals_single_gpu(mgw, tmp_path):
     r = subprocess.run([sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node', '2', '--master-addr', '127.0.0.1',
                         '--master-port', '29731', str(script)], capture_output=True, text=True, timeout=600, env=env)
     assert r.returncode == 0 and 'MULTI_GPU_OK' in r.stdout, r.stdout[-2000:] + r.stderr[-3000:]
+
+
+def test_double_buffered_dU_pipeline(mgw):
+    """the usage bench.py times: dU double-buffered, step i accumulates into buffer i % 2 (mgw_mesh_warp_bwd_acc) while the zero-fill
+    of the other buffer -- the one step i+1 accumulates into -- runs next to it on a side stream.  Every step's dU and dtheta equal
+    the plain call's (mgw_mesh_warp_bwd zero-fills inside), over several steps with different inputs, eager and as CUDA graphs."""
+    mgw.set_impl('auto')
+    n, h, w, c = 4, 96, 128, 3
+    sets = [dict(U=dev(synth.noise_image(n, h, w, c, 600 + k)), th=dev(synth.random_mesh(n, 4, 4, 0.05, 610 + k)),
+                 g=dev(synth.randn((n, h, w, c), 620 + k)), gi=dev(synth.randn((n, h, w, 2), 630 + k, 0.1))) for k in range(3)]
+    want = []
+    for s in sets:
+        _, _, _, Hs = mgw.ops.mesh_warp_fwd(s['U'], s['th'])
+        dU, dth = mgw.ops.mesh_warp_bwd(s['U'], s['th'], Hs, s['g'], s['gi'])
+        want.append((dU.clone(), dth.clone()))
+    bufs = [torch.zeros_like(sets[0]['U']) for _ in range(2)]
+    dths = [torch.empty_like(sets[0]['th']) for _ in range(3)]
+    side = torch.cuda.Stream()
+
+    def step(i):
+        s = sets[i % 3]
+        cur = torch.cuda.current_stream()
+        _, _, _, Hs = mgw.ops.mesh_warp_fwd(s['U'], s['th'])
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            mgw.ops.fill_zero(bufs[(i + 1) % 2])
+        mgw.ops.mesh_warp_bwd(s['U'], s['th'], Hs, s['g'], s['gi'], accumulate_into=bufs[i % 2], dtheta_out=dths[i % 3])
+        cur.wait_stream(side)
+
+    def check_step(i):
+        torch.cuda.synchronize()
+        dU, dth = want[i % 3]
+        # same kernels, same data: the reductions of a tile arrive in any order, so dU agrees to fp32 summation noise
+        assert relmax(bufs[i % 2].cpu().numpy(), dU.cpu().numpy()) <= 2e-6, i
+        assert torch.equal(dths[i % 3], dth), i
+
+    for i in range(6):
+        step(i)
+        check_step(i)
+    s_cap = torch.cuda.Stream()
+    s_cap.wait_stream(torch.cuda.current_stream())
+    graphs = []
+    with torch.cuda.stream(s_cap):
+        for i in range(6):
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=s_cap):
+                step(i)
+            graphs.append(g)
+    torch.cuda.current_stream().wait_stream(s_cap)
+    for rep in range(2):
+        for i in range(6):
+            graphs[i].replay()
+            check_step(i)
