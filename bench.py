@@ -9,8 +9,9 @@ BASELINE.json configs[1]: 32 x 288 x 512 x 3 fp32 per GPU, 4x4 mesh (weak scalin
 Rank 0 prints ONE JSON line.  Besides the contract's fields the line carries `sustained` (>= 1 s of graph replay of the same
 step with its own clock record), `configs` (the other BASELINE.json configurations: #1 single frame, #3 the warp stage inside
 a StabNet-shaped forward, #4 1080p stream latency with uint8 frames over PCIe, #5 the 256-clip data-parallel step with the
-all-reduce overlapped and synchronous) and `e2e_u8_fused` (a second end-to-end leg: uint8 frames over PCIe, loss fused onto the
-warp).  See DESIGN.md "Measurement" for how every field is obtained.
+all-reduce overlapped and synchronous), `e2e_u8_fused` (a second end-to-end leg: uint8 frames over PCIe, loss fused onto the
+warp) and, on one GPU, `dU_double_buffered` (the same step when the caller owns two dU buffers: the zero-fill of the next step's
+buffer runs next to this step's backward).  See DESIGN.md "Measurement" for how every field is obtained.
 """
 import argparse
 import json
