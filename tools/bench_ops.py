@@ -53,6 +53,8 @@ matches = torch.tensor(synth.uniform((n, M, 4), -1, 1, 5), device=dev)
 mask = (torch.rand(n, M, device=dev) < 0.3).float()
 timeit('feature_loss_fwd (3000 matches/sample)', lambda: ops.feature_loss_fwd(matches, mask, img), n * M * 28)
 timeit('feature_loss_bwd', lambda: ops.feature_loss_bwd(matches, mask, img, 1.0), n * M * 28 + P * 8)
+_Hs_feat = ops.solve_h_fwd(torch.tensor(synth.random_mesh(n, 4, 4, 0.05, 77), device=dev))
+timeit('feature_loss_dh (backward straight to dH partials; this wrapper also forms the mask counts with 4 torch kernels: the kernel itself is 11 us)', lambda: ops.feature_loss_dh(matches, mask, img, _Hs_feat, 1.0), n * M * 28)
 head = torch.tensor(synth.randn((n, 50), 6, 0.05), device=dev)
 timeit('vertices_fwd (get_4_pts)', lambda: ops.vertices_fwd(head, 4, 4), n * 50 * 12)
 pts1, pts2 = ops.vertices_fwd(head, 4, 4)
