@@ -444,3 +444,35 @@ def test_double_buffered_dU_pipeline(mgw):
         for i in range(6):
             graphs[i].replay()
             check_step(i)
+
+
+@pytest.mark.parametrize('n,gh,gw', [(3, 12, 12), (2, 16, 20), (5, 1, 1), (33, 3, 7)])
+def test_solve_kernels_on_large_and_odd_grids(mgw, n, gh, gw):
+    """K1 / K4 beyond the 4 x 4 mesh: more cells per sample than K4's block has threads (its per-cell loop runs more than once),
+    cell counts that are not multiples of K1's 16 cells per block, a single cell.  K1 bit-identical to the C oracle; K4 (from given
+    dHs, and from per-tile partials with a count that is not a multiple of four through the warp backward) against fp64 autograd
+    of the oracle's solve (spatial_transformer3.py:144-198)."""
+    theta = synth.random_mesh(n, gh, gw, 0.15 / max(gh, gw), 7000 + gh)
+    Hs = mgw.ops.solve_h_fwd(dev(theta))
+    assert bits_equal(Hs.cpu().numpy(), c_oracle.solve_h(theta)).all()
+    dHs = synth.randn((n, gh, gw, 9), 7100 + gw)
+    th64 = t64(theta, grad=True)
+    H64 = ref.solve_h(th64)
+    up = t64(dHs).clone()
+    up[..., 8] = 0
+    (H64 * up).sum().backward()
+    # K4 reads h6, h7 from Hs: with the fp64 solution (rounded to fp32) it reproduces the fp64 adjoint; with K1's own fp32 Hs the
+    # small cells of a fine mesh (an ill-conditioned 8x8 system) carry K1's error into dtheta, as the reference's fp32 graph does
+    got = mgw.ops.solve_h_bwd(dev(theta), dev(H64.detach().numpy()), dev(dHs)).cpu().numpy()
+    assert relmax(got, th64.grad.numpy()) < 2e-5, relmax(got, th64.grad.numpy())
+    got32 = mgw.ops.solve_h_bwd(dev(theta), Hs, dev(dHs)).cpu().numpy()
+    assert relmax(got32, th64.grad.numpy()) < (2e-5 if gh * gw <= 25 else 1e-2)
+    # through the warp backward: tile partials (TMA path when the cells are large enough, generic otherwise) -> K4
+    h, w = gh * 24, gw * 32
+    if n * h * w <= 4 * 288 * 512:
+        U = dev(synth.smooth_image(n, h, w, 1, 7200))
+        g = dev(synth.randn((n, h, w, 1), 7300))
+        _, dHs2 = mgw.ops.warp_bwd(U, Hs, g, want_dU=False)
+        _, dth = mgw.ops.mesh_warp_bwd(U, dev(theta), Hs, g, want_dU=False)
+        want = mgw.ops.solve_h_bwd(dev(theta), Hs, dHs2)
+        assert relmax(dth.cpu().numpy(), want.cpu().numpy()) < 1e-5
