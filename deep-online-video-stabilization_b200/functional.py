@@ -75,11 +75,13 @@ class TrainPass(torch.autograd.Function):
     through `total` and h_trans (another consumer of the warped frame, i.e. temp_loss, adds its gradient inside the warp
     backward); flow / pts2 / the parts are returned for display only."""
 
+    _FWD_KEYS = ('pts1', 'pts2', 'Hs', 'out', 'black', 'img', 'acc')
+
     @staticmethod
     def forward(ctx, head, U, y, matches, mask, regu, coef, gh, gw, do_crop_rate):
         f = ops.train_pass_fwd(head, U, y, matches, mask, coef, gh, gw, do_crop_rate, regu=regu)
-        ctx.save_for_backward(head, U, y, matches, mask)
-        ctx.fwd = {k: f[k] for k in ('pts1', 'pts2', 'Hs', 'out', 'black', 'img', 'acc')}
+        # (outputs go through save_for_backward as well: kept on ctx directly they would form a reference cycle with the graph)
+        ctx.save_for_backward(head, U, y, matches, mask, *[f[k] for k in TrainPass._FWD_KEYS])
         ctx.cfg = (coef, gh, gw, do_crop_rate)
         total, parts = f['result'][0], f['result'][1:]
         ctx.mark_non_differentiable(parts, f['black'], f['img'], f['warpped'], f['pts2'])
@@ -88,11 +90,14 @@ class TrainPass(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, g_total, _g_parts, g_out, *_unused):
-        head, U, y, matches, mask = ctx.saved_tensors
+        head, U, y, matches, mask = ctx.saved_tensors[:5]
+        fwd = dict(zip(TrainPass._FWD_KEYS, ctx.saved_tensors[5:]))
         coef, gh, gw, rate = ctx.cfg
+        if g_total is None and g_out is None:
+            return (torch.zeros_like(head), torch.zeros_like(U) if ctx.needs_input_grad[1] else None) + (None,) * 8
         if g_total is None:
             coef = (0.0,) * 9 + (coef[9], 0.0)      # only the gradient through h_trans is alive
-        d_head, dU = ops.train_pass_bwd(head, U, y, matches, mask, ctx.fwd, coef, gh, gw, rate, g_total=g_total,
+        d_head, dU = ops.train_pass_bwd(head, U, y, matches, mask, fwd, coef, gh, gw, rate, g_total=g_total,
                                         d_out_extra=None if g_out is None else g_out.contiguous(), want_dU=ctx.needs_input_grad[1])
         regu_grad = None
         if ctx.needs_input_grad[5]:
