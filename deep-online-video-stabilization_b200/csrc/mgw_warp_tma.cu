@@ -20,6 +20,23 @@
 // depend on the box heuristic.  Arithmetic is mgw_device.cuh's, bit-identical to the generic kernels and the C oracle.
 #include "mgw_tile.cuh"
 
+#ifdef MGW_PROBE
+__device__ unsigned long long g_probe[16];
+extern "C" __attribute__((visibility("default"))) int mgw_debug_probe(unsigned long long* out, int reset)
+{
+    cudaDeviceSynchronize();
+    cudaMemcpyFromSymbol(out, g_probe, sizeof(g_probe));
+    if (reset) { unsigned long long z[16] = {}; cudaMemcpyToSymbol(g_probe, z, sizeof(z)); }
+    return 0;
+}
+#define PROBE(i) do { if (threadIdx.x == MGW_PROBE_TID) { const long long t_ = clock64(); atomicAdd(&g_probe[i], (unsigned long long)(t_ - tprev)); tprev = t_; } } while (0)
+#else
+#define PROBE(i) do {} while (0)
+#endif
+#ifndef MGW_PROBE_TID
+#define MGW_PROBE_TID 32
+#endif
+
 namespace mgw {
 
 constexpr int kMaxWarps = 16;
@@ -318,6 +335,15 @@ struct LossBwd {
     const float* kscale_dev;    // nullable device factor on kscale
 };
 
+#ifndef MGW_BWD_STAGE_IMG
+#define MGW_BWD_STAGE_IMG 1
+#endif
+#ifndef MGW_BWD_STAGE
+#define MGW_BWD_STAGE 1
+#endif
+#ifndef MGW_BWD_DRAIN_RED
+#define MGW_BWD_DRAIN_RED 1
+#endif
 #ifndef MGW_BWD_MINB
 #define MGW_BWD_MINB (NT == 256 ? (K <= 3 ? 4 : 3) : 2)
 #endif
@@ -329,7 +355,7 @@ struct LossBwd {
 template <int C, int TW, int K, int NT, bool LOSS, bool DU>
 __global__ void __launch_bounds__(NT, DU ? MGW_BWD_MINB : MGW_BWD_NODU_MINB)
 warp_bwd_tma_kernel(const __grid_constant__ CUtensorMap mapU, const __grid_constant__ CUtensorMap mapDU,
-                    const float* __restrict__ U, const float* __restrict__ Hs, const float* __restrict__ d_out,
+                    const __grid_constant__ CUtensorMap mapG, const __grid_constant__ CUtensorMap mapGI, const float* __restrict__ U, const float* __restrict__ Hs, const float* __restrict__ d_out,
                     const float* __restrict__ d_img, const __grid_constant__ TileCfg cfg, float* __restrict__ dU,
                     float* __restrict__ parts, const LossBwd loss)
 {
@@ -341,13 +367,32 @@ warp_bwd_tma_kernel(const __grid_constant__ CUtensorMap mapU, const __grid_const
     TileInfo* ti = reinterpret_cast<TileInfo*>(bar + 2);
     int* s_acc = reinterpret_cast<int*>(s_red + 256);                  // fixed-point dU box (only when dU != nullptr)
 
+    // STAGE: the tile's d_out / d_img arrive by TMA too, into the (not yet zeroed) accumulator box, and every thread picks its
+    // pixels up from shared memory (12-byte lane stride: conflict free).  As 24 LDGs per thread with a 12-byte lane stride
+    // (three lines per request) they queued in the LSU for ~3500 cycles next to the other CTAs' shared-memory traffic and
+    // the CTA spent more than half of its life before its first pixel.
+    constexpr bool STAGE = MGW_BWD_STAGE && DU && !LOSS && (G::kBoxF >= G::TH * TW * (C + 2));
+    constexpr int kStageOut = G::TH * TW * C;         // floats of the staged d_out tile; the d_img tile follows it
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+#ifdef MGW_PROBE
+    long long tprev = clock64();
+    if (tid == MGW_PROBE_TID) atomicAdd(&g_probe[15], 1ull);
+#endif
     if (tid == 0) {
         tma::mbar_init(bar, 1);
+        if (STAGE) tma::mbar_init(bar + 1, 1);
         tma::fence_barrier_init();
     }
     griddep_launch_dependents();                      // K4 (launched programmatically) may run its factorisation under this kernel
+    PROBE(11);     // barrier init
     const Tile tl = this_tile(cfg);
+    PROBE(12);     // tile decode
+    if (STAGE && tid == 0) {
+        float* sg = reinterpret_cast<float*>(s_acc);
+        tma::mbar_expect_tx(bar + 1, (uint32_t)((kStageOut + ((MGW_BWD_STAGE_IMG && d_img) ? G::TH * TW * 2 : 0)) * sizeof(float)));
+        tma::load_3d(sg, &mapG, bar + 1, tl.c0 * C, tl.r0, tl.n);
+        if (MGW_BWD_STAGE_IMG && d_img) tma::load_3d(sg + kStageOut, &mapGI, bar + 1, tl.c0 * 2, tl.r0, tl.n);
+    }
     float Hc[9];
 #pragma unroll
     for (int k = 0; k < 9; ++k) Hc[k] = __ldg(Hs + (size_t)tl.cell * 9 + k);
@@ -355,9 +400,49 @@ warp_bwd_tma_kernel(const __grid_constant__ CUtensorMap mapU, const __grid_const
     const int tx = tid % TW, g = tid / TW;
     const int col = tl.c0 + tx;
 
+    // warp 0 issues the TMA load of the source box FIRST, ahead of everybody's gradient loads (24 LDGs per thread that queue in
+    // the LSU for ~3500 cycles next to the other CTAs' shared-memory traffic: issued behind them, the box arrived ~4000 cycles
+    // after the first barrier).  Thread 0 initialised the barrier itself; everybody else meets it after the __syncthreads below.
+    if (tid < 32) {
+        int bx0, by0, interior, area_ok, complete;
+        source_box<C, TW, K, NT>(cfg, tl, Hc, stepx, stepy, bx0, by0, interior, area_ok, &complete);
+        if (tid == 0) {
+            ti->bx0 = bx0; ti->by0 = by0; ti->interior = complete; ti->area_ok = area_ok;      // backward: "interior" = complete
+            tma::mbar_expect_tx(bar, (uint32_t)(G::kBoxF * sizeof(float)));
+            tma::load_3d(s_src, &mapU, bar, bx0 * C, by0, tl.n);
+        }
+    }
     // this thread's K pixels of d_out / d_img: 12 / 8 contiguous bytes per lane, coalesced, all loads in flight at once
+    PROBE(13);     // Hs loads issued, lin_step
     float gout[K][C], gimg[K][2];
-    {
+    if (STAGE) {
+#if !MGW_BWD_STAGE_IMG
+        {   // d_img: 8 contiguous bytes per lane (two lines per request), wanted only at the end of a pixel: plain loads
+            const float2* pi = reinterpret_cast<const float2*>(d_img) + ((size_t)tl.n * cfg.H + tl.r0 + g * K) * cfg.W + col;
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+                const float2 di = d_img ? __ldg(pi + (size_t)k * cfg.W) : make_float2(0.0f, 0.0f);
+                gimg[k][0] = di.x; gimg[k][1] = di.y;
+            }
+        }
+#endif
+        __syncthreads();                              // the barriers thread 0 initialised are visible to everybody
+        tma::mbar_wait(bar + 1, 0);
+        const float* sg = reinterpret_cast<const float*>(s_acc) + (g * K * TW + tx) * C;
+        const float2* si = reinterpret_cast<const float2*>(reinterpret_cast<const float*>(s_acc) + kStageOut) + g * K * TW + tx;
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+#pragma unroll
+            for (int ch = 0; ch < C; ++ch) gout[k][ch] = sg[k * TW * C + ch];
+            if (!MGW_BWD_STAGE_IMG) continue;
+            if (d_img) {
+                const float2 di = si[k * TW];
+                gimg[k][0] = di.x; gimg[k][1] = di.y;
+            } else {
+                gimg[k][0] = 0.0f; gimg[k][1] = 0.0f;
+            }
+        }
+    } else {
         size_t p = ((size_t)tl.n * cfg.H + tl.r0 + g * K) * cfg.W + col;
         const float kn = LOSS ? (loss.kscale_dev ? loss.kscale * __ldg(loss.kscale_dev) : loss.kscale) / (__ldg(loss.sums + 2 * tl.n + 1) + 1e-8f) : 0.0f;
 #pragma unroll
@@ -382,23 +467,7 @@ warp_bwd_tma_kernel(const __grid_constant__ CUtensorMap mapU, const __grid_const
             }
         }
     }
-    // warp 0 issues the TMA load of the source box first (thread 0 initialised the barrier itself; everybody else meets it
-    // after the __syncthreads below), then everyone zeroes the accumulator under the load's latency
-    if (tid < 32) {
-        int bx0, by0, interior, area_ok, complete;
-        source_box<C, TW, K, NT>(cfg, tl, Hc, stepx, stepy, bx0, by0, interior, area_ok, &complete);
-        if (tid == 0) {
-            ti->bx0 = bx0; ti->by0 = by0; ti->interior = complete; ti->area_ok = area_ok;      // backward: "interior" = complete
-            tma::mbar_expect_tx(bar, (uint32_t)(G::kBoxF * sizeof(float)));
-            tma::load_3d(s_src, &mapU, bar, bx0 * C, by0, tl.n);
-        }
-    }
-    if (DU) {
-        int4* a4 = reinterpret_cast<int4*>(s_acc);
-#pragma unroll
-        for (int i = 0; i < (G::kBoxF / 4 + NT - 1) / NT; ++i)
-            if (i * NT + tid < G::kBoxF / 4) a4[i * NT + tid] = make_int4(0, 0, 0, 0);
-    }
+    PROBE(0);      // gradients in registers (STAGE) / their loads issued
     // ---- per-tile fixed-point scale from max|d_out| (Inf/NaN anywhere in the tile disables the fixed-point path)
     if (DU) {
         // max over |d_out| as unsigned bit patterns: Inf/NaN (>= 0x7f800000) win the max, one REDUX per warp
@@ -410,7 +479,16 @@ warp_bwd_tma_kernel(const __grid_constant__ CUtensorMap mapU, const __grid_const
         m = __reduce_max_sync(0xffffffffu, m);
         if (lane == 0) ti->wmax[warp] = __int_as_float((int)m);
     }
+    if (DU) {
+        if (STAGE) __syncthreads();                   // everybody has taken its gradients out of the box
+        int4* a4 = reinterpret_cast<int4*>(s_acc);
+#pragma unroll
+        for (int i = 0; i < (G::kBoxF / 4 + NT - 1) / NT; ++i)
+            if (i * NT + tid < G::kBoxF / 4) a4[i * NT + tid] = make_int4(0, 0, 0, 0);
+    }
+    PROBE(1);      // source box / zero / max (includes the wait for the gradient loads)
     __syncthreads();                                  // wmax, box and the zeroed accumulator are visible
+    PROBE(2);      // barrier 1
     const int bx0 = ti->bx0, by0 = ti->by0;
     int fixed = 0;
     float scale = 0.0f, inv_scale = 0.0f;
@@ -440,7 +518,9 @@ warp_bwd_tma_kernel(const __grid_constant__ CUtensorMap mapU, const __grid_const
     for (int k = 0; k < 8; ++k) dh[k] = 0.0f;
     const float halfW = 0.5f * (float)cfg.W, halfH = 0.5f * (float)cfg.H;
 
+    PROBE(3);
     tma::mbar_wait(bar, 0);
+    PROBE(4);      // wait for the TMA box
     if (ti->interior && (fixed || !DU)) {
         // ---- fast path: every UNCLIPPED tap lies inside the box; shared-memory offsets are compile-time constants.
         // A pixel with a clipped tap (its sample point is outside the image) contributes nothing but its d_img term: clipping
@@ -537,6 +617,7 @@ warp_bwd_tma_kernel(const __grid_constant__ CUtensorMap mapU, const __grid_const
             }
         }
     }
+    PROBE(5);      // pixel loop
     // dH: halving butterfly (9 shuffles for the 8 sums instead of 40) -> shared -> one partial per tile.
     // After the three halving steps lane l holds term (l>>2)&7 summed over the lanes that share l's low two bits ... the
     // last two steps finish the sum, so lanes 0,4,..,28 hold terms 0..7.
@@ -562,7 +643,9 @@ warp_bwd_tma_kernel(const __grid_constant__ CUtensorMap mapU, const __grid_const
         // lane l now holds term  4*bit4(l) + 2*bit3(l) + bit2(l)
         if ((lane & 3) == 0) s_red[warp * 8 + ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1)] = v1;
     }
+    PROBE(6);      // dH shuffles
     __syncthreads();                                  // also orders every shared atomic before the conversion below
+    PROBE(7);      // barrier 2
     if (tid < 8) {
         float v = 0.0f;
 #pragma unroll
@@ -570,6 +653,28 @@ warp_bwd_tma_kernel(const __grid_constant__ CUtensorMap mapU, const __grid_const
         parts[((size_t)tl.cell * (cfg.parts_y * cfg.parts_x) + tl.part) * 8 + tid] = v;
     }
     if (fixed) {
+#if MGW_BWD_DRAIN_RED
+        // fixed point -> fp32 straight from the accumulator into dU by 16-byte reductions (red.global.add.v4.f32, fire and
+        // forget through the LSU): no conversion back into shared memory, no proxy fence, no third barrier, and nothing of this
+        // CTA waits in the SM's TMA unit in front of the next CTA's box load
+        const int4* a4 = reinterpret_cast<const int4*>(s_acc);
+        constexpr int kQ = G::kRowF / 4;                                   // 16-byte groups per box row
+        const int rows = min(G::SBH, cfg.H - by0);                           // the part of the box inside the image
+        const int nq = min(G::kRowF, (cfg.W - bx0) * C) / 4;                 // ((W - bx0) * C is a multiple of 4 floats)
+        float* base = dU + (((size_t)tl.n * cfg.H + by0) * cfg.W + bx0) * C;
+        const int pitch = cfg.W * C;
+#pragma unroll
+        for (int i = 0; i < (G::kBoxF / 4 + NT - 1) / NT; ++i) {
+            const int j = i * NT + tid;
+            const int row = j / kQ, q = j % kQ;
+            if (row < rows && q < nq) {
+                const int4 v = a4[j];
+                tma::red_add_v4(base + row * pitch + q * 4, float_of_fixed(v.x) * inv_scale, float_of_fixed(v.y) * inv_scale,
+                                float_of_fixed(v.z) * inv_scale, float_of_fixed(v.w) * inv_scale);
+            }
+        }
+        PROBE(8);
+#else
         // fixed point -> fp32 in place, then ONE TMA reduce-add of the whole box into dU
         int4* a4 = reinterpret_cast<int4*>(s_acc);
 #pragma unroll
@@ -581,13 +686,17 @@ warp_bwd_tma_kernel(const __grid_constant__ CUtensorMap mapU, const __grid_const
                                                                   float_of_fixed(v.z) * inv_scale, float_of_fixed(v.w) * inv_scale);
             }
         }
+        PROBE(8);      // convert
         tma::fence_proxy_async();
         __syncthreads();
+        PROBE(9);      // barrier 3
         if (tid == 0) {
             tma::reduce_add_3d(&mapDU, s_acc, bx0 * C, by0, tl.n);
             tma::commit_group();
             tma::wait_group_read0();
         }
+        PROBE(10);     // TMA reduce issued and read (thread 0 only)
+#endif
     }
 }
 
@@ -680,24 +789,29 @@ static int launch_bwd_v(const float* U, const float* Hs, const float* d_out, con
     CUtensorMap mU, mDU;
     TRY_RC(make_map(&mU, U, c.W * C, c.H, c.N, G::kRowF, G::SBH));
     if (dU) TRY_RC(make_map(&mDU, dU, c.W * C, c.H, c.N, G::kRowF, G::SBH)); else mDU = mU;
+    CUtensorMap mG = mU, mGI = mU;                  // staged d_out / d_img tiles (plain backward with dU only)
+    if (dU && !loss) {
+        TRY_RC(make_map(&mG, d_out, c.W * C, c.H, c.N, TW * C, G::TH));
+        if (d_img) TRY_RC(make_map(&mGI, d_img, c.W * 2, c.H, c.N, TW * 2, G::TH));
+    }
     const size_t smem = (size_t)(G::kBoxF + 256 + (dU ? G::kBoxF : 0)) * 4 + 64;
     const dim3 grid(p.ntx, p.nty, c.N);
     if (loss && dU) {
         static bool attr[64] = {};
         TRY_RC(allow_smem(warp_bwd_tma_kernel<C, TW, K, NT, true, true>, attr, "warp_bwd_tma(loss)"));
-        warp_bwd_tma_kernel<C, TW, K, NT, true, true><<<grid, NT, smem, st>>>(mU, mDU, U, Hs, d_out, d_img, c, dU, parts, *loss);
+        warp_bwd_tma_kernel<C, TW, K, NT, true, true><<<grid, NT, smem, st>>>(mU, mDU, mG, mGI, U, Hs, d_out, d_img, c, dU, parts, *loss);
     } else if (loss) {
         static bool attr[64] = {};
         TRY_RC(allow_smem(warp_bwd_tma_kernel<C, TW, K, NT, true, false>, attr, "warp_bwd_tma(loss, no dU)"));
-        warp_bwd_tma_kernel<C, TW, K, NT, true, false><<<grid, NT, smem, st>>>(mU, mDU, U, Hs, d_out, d_img, c, nullptr, parts, *loss);
+        warp_bwd_tma_kernel<C, TW, K, NT, true, false><<<grid, NT, smem, st>>>(mU, mDU, mG, mGI, U, Hs, d_out, d_img, c, nullptr, parts, *loss);
     } else if (dU) {
         static bool attr[64] = {};
         TRY_RC(allow_smem(warp_bwd_tma_kernel<C, TW, K, NT, false, true>, attr, "warp_bwd_tma"));
-        warp_bwd_tma_kernel<C, TW, K, NT, false, true><<<grid, NT, smem, st>>>(mU, mDU, U, Hs, d_out, d_img, c, dU, parts, LossBwd{});
+        warp_bwd_tma_kernel<C, TW, K, NT, false, true><<<grid, NT, smem, st>>>(mU, mDU, mG, mGI, U, Hs, d_out, d_img, c, dU, parts, LossBwd{});
     } else {
         static bool attr[64] = {};
         TRY_RC(allow_smem(warp_bwd_tma_kernel<C, TW, K, NT, false, false>, attr, "warp_bwd_tma(no dU)"));
-        warp_bwd_tma_kernel<C, TW, K, NT, false, false><<<grid, NT, smem, st>>>(mU, mDU, U, Hs, d_out, d_img, c, nullptr, parts, LossBwd{});
+        warp_bwd_tma_kernel<C, TW, K, NT, false, false><<<grid, NT, smem, st>>>(mU, mDU, mG, mGI, U, Hs, d_out, d_img, c, nullptr, parts, LossBwd{});
     }
     return check_launch("warp_bwd_tma");
 }
