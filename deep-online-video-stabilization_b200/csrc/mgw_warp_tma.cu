@@ -335,6 +335,9 @@ struct LossBwd {
     const float* kscale_dev;    // nullable device factor on kscale
 };
 
+#ifndef MGW_BWD_SKIP_ZERO
+#define MGW_BWD_SKIP_ZERO 1
+#endif
 #ifndef MGW_BWD_STAGE_IMG
 #define MGW_BWD_STAGE_IMG 1
 #endif
@@ -669,6 +672,9 @@ warp_bwd_tma_kernel(const __grid_constant__ CUtensorMap mapU, const __grid_const
             const int row = j / kQ, q = j % kQ;
             if (row < rows && q < nq) {
                 const int4 v = a4[j];
+#if MGW_BWD_SKIP_ZERO
+                if ((v.x | v.y | v.z | v.w) != 0)      // most of the box outside the tile's own footprint received nothing: no traffic for +0
+#endif
                 tma::red_add_v4(base + row * pitch + q * 4, float_of_fixed(v.x) * inv_scale, float_of_fixed(v.y) * inv_scale,
                                 float_of_fixed(v.z) * inv_scale, float_of_fixed(v.w) * inv_scale);
             }
@@ -794,7 +800,8 @@ static int launch_bwd_v(const float* U, const float* Hs, const float* d_out, con
         TRY_RC(make_map(&mG, d_out, c.W * C, c.H, c.N, TW * C, G::TH));
         if (d_img) TRY_RC(make_map(&mGI, d_img, c.W * 2, c.H, c.N, TW * 2, G::TH));
     }
-    const size_t smem = (size_t)(G::kBoxF + 256 + (dU ? G::kBoxF : 0)) * 4 + 64;
+    size_t smem = (size_t)(G::kBoxF + 256 + (dU ? G::kBoxF : 0)) * 4 + 64;
+    if (const char* e = getenv("MGW_BWD_PAD_SMEM")) smem += (size_t)atoi(e);      // tuning aid: fewer CTAs per SM (occupancy experiments)
     const dim3 grid(p.ntx, p.nty, c.N);
     if (loss && dU) {
         static bool attr[64] = {};
