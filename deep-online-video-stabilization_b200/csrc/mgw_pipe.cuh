@@ -218,6 +218,7 @@ static bool plan(const WarpShape& s, int TW, int TH, PipePlan* out)
     p.TW = TW; p.TH = TH;
     TileCfg& c = p.cfg.t;
     c.N = s.N; c.H = s.H; c.W = s.W; c.gh = s.gh; c.gw = s.gw;
+    tile_steps(&c);
     p.cfg.nty = fill_axis(&c.rows, s.gh, cell_h, s.H, TH, &c.parts_y);
     p.cfg.ntx = fill_axis(&c.cols, s.gw, cell_w, s.W, TW, &c.parts_x);
     if (p.cfg.nty < 0 || p.cfg.ntx < 0 || c.parts_y > 255 || c.parts_x > 255) return false;

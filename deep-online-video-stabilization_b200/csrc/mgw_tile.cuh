@@ -26,10 +26,18 @@ struct AxisTab {
 struct TileCfg {
     int N, H, W, gh, gw;
     int parts_y, parts_x;           // max tiles per cell (backward partial layout)
+    float stepx, stepy;             // tf.linspace step 2/(W-1), 2/(H-1): the host's IEEE single division == __fdiv_rn (set by tile_steps())
     AxisTab rows, cols;             // grid = (cols, rows, N): blockIdx is the tile, no index arithmetic on the device
 };
 
 // ------------------------------------------------------------------------------------------------ host side
+// lin_step() of mgw_device.cuh on the host: one correctly rounded fp32 division, bit-identical to the device's __fdiv_rn
+static inline void tile_steps(TileCfg* c)
+{
+    volatile float two = 2.0f, w1 = (float)(c->W - 1), h1 = (float)(c->H - 1);      // volatile: no constant folding at another precision
+    c->stepx = two / w1; c->stepy = two / h1;
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);

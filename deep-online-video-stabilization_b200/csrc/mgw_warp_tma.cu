@@ -187,7 +187,7 @@ warp_fwd_tma_kernel(const __grid_constant__ CUtensorMap mapU, const __grid_const
     float Hc[9];
 #pragma unroll
     for (int k = 0; k < 9; ++k) Hc[k] = __ldg(Hs + (size_t)tl.cell * 9 + k);
-    const float stepx = lin_step(cfg.W), stepy = lin_step(cfg.H);
+    const float stepx = cfg.stepx, stepy = cfg.stepy;
     __syncthreads();                                  // barrier initialised; nobody has waited on anything long yet
     if (tid < 32 && out) {
         int bx0, by0, interior, area_ok;
@@ -399,7 +399,7 @@ warp_bwd_tma_kernel(const __grid_constant__ CUtensorMap mapU, const __grid_const
     float Hc[9];
 #pragma unroll
     for (int k = 0; k < 9; ++k) Hc[k] = __ldg(Hs + (size_t)tl.cell * 9 + k);
-    const float stepx = lin_step(cfg.W), stepy = lin_step(cfg.H);
+    const float stepx = cfg.stepx, stepy = cfg.stepy;
     const int tx = tid % TW, g = tid / TW;
     const int col = tl.c0 + tx;
 
@@ -747,6 +747,7 @@ static bool plan(const WarpShape& s, Plan* out)
     p.TW = kVariants[best][0]; p.K = kVariants[best][1]; p.NT = kVariants[best][2]; p.TH = (p.NT / p.TW) * p.K;
     TileCfg& c = p.cfg;
     c.N = s.N; c.H = s.H; c.W = s.W; c.gh = s.gh; c.gw = s.gw;
+    tile_steps(&c);
     p.nty = fill_axis(&c.rows, s.gh, cell_h, s.H, p.TH, &c.parts_y);
     p.ntx = fill_axis(&c.cols, s.gw, cell_w, s.W, p.TW, &c.parts_x);
     if (p.nty < 0 || p.ntx < 0 || c.parts_y > 255 || c.parts_x > 255) return false;
