@@ -512,7 +512,8 @@ def main():
                                     'pipelined_tail': 'one fill per step inside the timed region; dU double-buffered: the fill of the buffer '
                                                       'step i+1 accumulates into (mgw_mesh_warp_bwd_acc) runs after the backward of step i, '
                                                       'next to the wait for the all-reduce',
-                                    'fused': 'inside the backward call (mgw_mesh_warp_bwd), between forward and backward'}.get(fill_mode, fill_mode),
+                                    'fused': 'inside the backward call (mgw_mesh_warp_bwd), between forward and backward; the backward kernel is launched '
+                                             'programmatically behind it and waits for it (griddepcontrol.wait) before its first access to dU'}.get(fill_mode, fill_mode),
                    'parallelism': ('dp%d (batch-sharded, 100 KB mesh-head grad all-reduce of step i-1 overlapped with step i; the '
                                    'synchronous form is in configs.config5)' % world) if world > 1 else 'single GPU',
                    'host_cores_pinned_per_rank': ncores},

@@ -184,11 +184,12 @@ static int warp_bwd_core(const float* U, const float* Hs, const float* d_out, co
     // (a fused img_loss with a second gradient on `output` is served by the tile kernels)
     const bool pipe_ok = mode != 1 && mode != 2 && (prefer_pipe || mode == 3) && dU && workspace && pipe_bwd_supported(s) && aligned(U, 16) && aligned(dU, 16) &&
                          (!d_img || aligned(d_img, 8)) && !(fl && d_out);
+    bool own_fill = false;          // the tile backward then runs NEXT TO the fill up to its first access to dU (programmatic launch)
     if (dU && zero_dU) {
         // the library's own fill (evict_last: the lines are still in L2 when the reductions arrive) where its 16-byte granularity
         // fits, the driver's memset otherwise (odd sizes only occur on the generic path)
         const size_t bytes = sizeof(float) * (size_t)s.N * s.H * s.W * s.C;
-        if (bytes % 16 == 0 && aligned(dU, 16)) TRY(launch_fill_zero(dU, bytes, true, st));
+        if (bytes % 16 == 0 && aligned(dU, 16)) { TRY(launch_fill_zero(dU, bytes, true, st)); own_fill = true; }
         else TRY(check_memset(cudaMemsetAsync(dU, 0, bytes, st), "memset dU"));
     }
     if (pipe_ok) {
@@ -202,7 +203,7 @@ static int warp_bwd_core(const float* U, const float* Hs, const float* d_out, co
         return set_error(MGW_ERR_UNSUPPORTED, "TMA path required (MGW_IMPL=tma|pipe) but shape/alignment/workspace does not allow it");
     if (tma_ok) {
         int np = 0;
-        TRY(launch_warp_bwd_tma(U, Hs, d_out, d_img, s, dU, (float*)workspace, &np, fl, st));
+        TRY(launch_warp_bwd_tma(U, Hs, d_out, d_img, s, dU, (float*)workspace, &np, fl, st, own_fill));
         *parts = (const float*)workspace; *nparts = np; *part_stride = 8;
         return MGW_OK;
     }

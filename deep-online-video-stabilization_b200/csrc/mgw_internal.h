@@ -99,7 +99,8 @@ bool tma_bwd_supported(const WarpShape& s);
 size_t tma_bwd_workspace_bytes(const WarpShape& s);
 // fl nullable: when given, d_out is ignored and the upstream gradient is the fused img_loss's
 int launch_warp_bwd_tma(const float* U, const float* Hs, const float* d_out, const float* d_img, const WarpShape& s,
-                        float* dU, float* dHs_part, int* nparts, const FusedImgLoss* fl, cudaStream_t st);
+                        float* dU, float* dHs_part, int* nparts, const FusedImgLoss* fl, cudaStream_t st,
+                        bool behind_own_fill = false);      // true: the kernel right before us in `st` is the library's zero-fill of dU
 
 // mgw_warp_pipe.cu : forward as a persistent warp-specialised pipeline over TMA-staged tiles (serves the full call:
 // out + black + img)

@@ -18,6 +18,23 @@
 // is outside, so results never depend on the box heuristic.  Arithmetic is mgw_device.cuh's: bit-identical to the generic kernels and the C oracle on the forward.
 #include "mgw_pipe.cuh"
 
+#ifdef MGW_PROBE
+__device__ unsigned long long g_probe_f[16];
+extern "C" __attribute__((visibility("default"))) int mgw_debug_probe_fwd(unsigned long long* out, int reset)
+{
+    cudaDeviceSynchronize();
+    cudaMemcpyFromSymbol(out, g_probe_f, sizeof(g_probe_f));
+    if (reset) { unsigned long long z[16] = {}; cudaMemcpyToSymbol(g_probe_f, z, sizeof(z)); }
+    return 0;
+}
+#define FPROBE(i) do { if (threadIdx.x == MGW_PROBE_TID) { const long long t_ = clock64(); atomicAdd(&g_probe_f[i], (unsigned long long)(t_ - tprev)); tprev = t_; } } while (0)
+#else
+#define FPROBE(i) do {} while (0)
+#endif
+#ifndef MGW_PROBE_TID
+#define MGW_PROBE_TID 0
+#endif
+
 namespace mgw {
 
 using namespace pipe;
@@ -137,9 +154,16 @@ warp_fwd_pipe_kernel(const __grid_constant__ CUtensorMap mapU, const __grid_cons
     // ---------------------------------------------------------------- consumers
     const int tx = tid % TW, g = tid / TW;
     const unsigned char* sbase = smem_raw;
+#ifdef MGW_PROBE
+    long long tprev = clock64();
+#endif
     for (int it = 0, t = blockIdx.x; t < cfg.total; ++it, t += gridDim.x) {
         const int s = it % S;
         if (it % kRoundTiles == 0) tma::mbar_wait(recbar + ((it / kRoundTiles) & 1), (it / (2 * kRoundTiles)) & 1);
+        FPROBE(0);     // wait for the records
+#ifdef MGW_PROBE
+        if (tid == MGW_PROBE_TID) atomicAdd(&g_probe_f[15], 1ull);
+#endif
         const PInfo* in = info + (it % kInfoRing);
         const int n = in->n, r0 = in->r0, c0 = in->c0, complete = in->complete, bx0 = in->bx0, by0 = in->by0;
         const int offbase = -(by0 * G::kRowF + bx0 * C) + s * G::kBoxF;
@@ -172,12 +196,14 @@ warp_fwd_pipe_kernel(const __grid_constant__ CUtensorMap mapU, const __grid_cons
                     xn[k] = q.xn; yn[k] = q.yn;
                 }
             }
+            FPROBE(1);     // phase 1 (record read + projective map)
             // phase 2: x_map,y_map and black_pix: 8 / 4 contiguous bytes per lane, plain coalesced stores
 #pragma unroll
             for (int k = 0; k < K; ++k) {
                 pimg[k * W] = make_float2(xn[k], yn[k]);
                 pblk[k * W] = black_of(xn[k], yn[k]);
             }
+            FPROBE(2);     // phase 2 (map / mask stores)
             // phase 3: taps
             PixTaps tp[K];
             bool clip[K], anyclip = false;
@@ -188,8 +214,10 @@ warp_fwd_pipe_kernel(const __grid_constant__ CUtensorMap mapU, const __grid_cons
                 for (int k = 0; k < K; ++k)
                     if (clip[k]) pix_taps_clipped<C, G::kRowF>(xn[k], yn[k], H, W, offbase, tp[k]);
             }
+            FPROBE(3);     // phase 3 (taps)
             // phase 4: bilinear gather from the staged box (the only phase that needs it)
             tma::mbar_wait(full + s, (it / S) & 1);
+            FPROBE(4);     // wait for the box
 #pragma unroll
             for (int k = 0; k < K; ++k) {
                 const unsigned char* pa = sbase + tp[k].off;
@@ -214,15 +242,19 @@ warp_fwd_pipe_kernel(const __grid_constant__ CUtensorMap mapU, const __grid_cons
                 pixel_general_fwd<G, C>(Un, src, bx0, by0, H, W, q.xn, q.yn, so + k * TW * C);
             }
         }
+        FPROBE(5);     // phase 4 (gather) / general path
         __syncwarp();
         if (lane == 0) tma::mbar_arrive(empty + s);               // the source box may be refilled
         tma::fence_proxy_async();                                 // my part of the output tile -> visible to the TMA store
         if (tid == 0) tma::wait_group_read0();                    // the previous tile's store has left ITS buffer (the next one's)
+        FPROBE(6);     // release, proxy fence, wait for the previous tile's store
         tma::named_bar_sync<1, NC>();
+        FPROBE(7);     // consumer barrier
         if (tid == 0) {
             tma::store_3d(&mapOut, s_out + (it & 1) * G::kOutF, c0 * C, r0, n);
             tma::commit_group();
         }
+        FPROBE(8);     // store issue
     }
     if (tid == 0) tma::wait_group_read0();
 }

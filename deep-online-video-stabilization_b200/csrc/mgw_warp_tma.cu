@@ -571,6 +571,7 @@ warp_bwd_tma_kernel(const __grid_constant__ CUtensorMap mapU, const __grid_const
             }
         }
     } else {
+        if (DU) griddep_wait();                       // this path adds to dU from inside the loop: the zero-fill before us must be complete
         const float* Un = U + (size_t)tl.n * cfg.H * cfg.W * C;
         float* dUn = DU ? dU + (size_t)tl.n * cfg.H * cfg.W * C : nullptr;
 #pragma unroll
@@ -656,6 +657,9 @@ warp_bwd_tma_kernel(const __grid_constant__ CUtensorMap mapU, const __grid_const
         parts[((size_t)tl.cell * (cfg.parts_y * cfg.parts_x) + tl.part) * 8 + tid] = v;
     }
     if (fixed) {
+        // Launched programmatically behind the zero-fill of dU (mgw_capi.cu), this kernel has run up to here NEXT TO it: nothing
+        // above reads or writes dU.  From here on the fill must be complete and visible (a no-op under a plain launch).
+        griddep_wait();
 #if MGW_BWD_DRAIN_RED
         // fixed point -> fp32 straight from the accumulator into dU by 16-byte reductions (red.global.add.v4.f32, fire and
         // forget through the LSU): no conversion back into shared memory, no proxy fence, no third barrier, and nothing of this
@@ -789,7 +793,7 @@ static int launch_fwd_v(const float* U, const float* Hs, const Plan& p, float* o
 
 template <int C, int TW, int K, int NT>
 static int launch_bwd_v(const float* U, const float* Hs, const float* d_out, const float* d_img, const Plan& p, float* dU,
-                        float* parts, const LossBwd* loss, cudaStream_t st)
+                        float* parts, const LossBwd* loss, cudaStream_t st, bool behind_own_fill)
 {
     using G = Geo<C, TW, K, NT>;
     const TileCfg& c = p.cfg;
@@ -815,7 +819,9 @@ static int launch_bwd_v(const float* U, const float* Hs, const float* d_out, con
     } else if (dU) {
         static bool attr[64] = {};
         TRY_RC(allow_smem(warp_bwd_tma_kernel<C, TW, K, NT, false, true>, attr, "warp_bwd_tma"));
-        warp_bwd_tma_kernel<C, TW, K, NT, false, true><<<grid, NT, smem, st>>>(mU, mDU, mG, mGI, U, Hs, d_out, d_img, c, dU, parts, LossBwd{});
+        const cudaError_t e = launch_ex(warp_bwd_tma_kernel<C, TW, K, NT, false, true>, grid, dim3(NT), smem, st, behind_own_fill && pdl_enabled(),
+                                        mU, mDU, mG, mGI, U, Hs, d_out, d_img, c, dU, parts, LossBwd{});
+        if (e != cudaSuccess) { count_launches(1); return set_error(MGW_ERR_CUDA, "warp_bwd_tma: %s", cudaGetErrorString(e)); }
     } else {
         static bool attr[64] = {};
         TRY_RC(allow_smem(warp_bwd_tma_kernel<C, TW, K, NT, false, false>, attr, "warp_bwd_tma(no dU)"));
@@ -841,15 +847,15 @@ static int launch_fwd_c(const Plan& p, const float* U, const float* Hs, float* o
 
 template <int C>
 static int launch_bwd_c(const Plan& p, const float* U, const float* Hs, const float* d_out, const float* d_img, float* dU,
-                        float* parts, const LossBwd* loss, cudaStream_t st)
+                        float* parts, const LossBwd* loss, cudaStream_t st, bool behind_own_fill)
 {
-    if (p.NT == 256 && p.TW == 32 && p.K == 3) return launch_bwd_v<C, 32, 3, 256>(U, Hs, d_out, d_img, p, dU, parts, loss, st);
-    if (p.NT == 256 && p.TW == 32 && p.K == 2) return launch_bwd_v<C, 32, 2, 256>(U, Hs, d_out, d_img, p, dU, parts, loss, st);
-    if (p.NT == 256 && p.TW == 32 && p.K == 1) return launch_bwd_v<C, 32, 1, 256>(U, Hs, d_out, d_img, p, dU, parts, loss, st);
+    if (p.NT == 256 && p.TW == 32 && p.K == 3) return launch_bwd_v<C, 32, 3, 256>(U, Hs, d_out, d_img, p, dU, parts, loss, st, behind_own_fill);
+    if (p.NT == 256 && p.TW == 32 && p.K == 2) return launch_bwd_v<C, 32, 2, 256>(U, Hs, d_out, d_img, p, dU, parts, loss, st, behind_own_fill);
+    if (p.NT == 256 && p.TW == 32 && p.K == 1) return launch_bwd_v<C, 32, 1, 256>(U, Hs, d_out, d_img, p, dU, parts, loss, st, behind_own_fill);
     if constexpr (C != 4) {
-        if (p.NT == 256 && p.TW == 64 && p.K == 6) return launch_bwd_v<C, 64, 6, 256>(U, Hs, d_out, d_img, p, dU, parts, loss, st);
-        if (p.NT == 512 && p.TW == 64 && p.K == 3) return launch_bwd_v<C, 64, 3, 512>(U, Hs, d_out, d_img, p, dU, parts, loss, st);
-        if (p.NT == 256 && p.TW == 64 && p.K == 3) return launch_bwd_v<C, 64, 3, 256>(U, Hs, d_out, d_img, p, dU, parts, loss, st);
+        if (p.NT == 256 && p.TW == 64 && p.K == 6) return launch_bwd_v<C, 64, 6, 256>(U, Hs, d_out, d_img, p, dU, parts, loss, st, behind_own_fill);
+        if (p.NT == 512 && p.TW == 64 && p.K == 3) return launch_bwd_v<C, 64, 3, 512>(U, Hs, d_out, d_img, p, dU, parts, loss, st, behind_own_fill);
+        if (p.NT == 256 && p.TW == 64 && p.K == 3) return launch_bwd_v<C, 64, 3, 256>(U, Hs, d_out, d_img, p, dU, parts, loss, st, behind_own_fill);
     }
     return set_error(MGW_ERR_UNSUPPORTED, "warp_bwd_tma: no tile variant");
 }
@@ -865,7 +871,7 @@ int launch_warp_fwd_tma(const float* U, const float* Hs, const WarpShape& s, flo
 }
 
 int launch_warp_bwd_tma(const float* U, const float* Hs, const float* d_out, const float* d_img, const WarpShape& s, float* dU,
-                        float* parts, int* nparts, const FusedImgLoss* fl, cudaStream_t st)
+                        float* parts, int* nparts, const FusedImgLoss* fl, cudaStream_t st, bool behind_own_fill)
 {
     LossBwd lb{};
     const LossBwd* loss = nullptr;
@@ -881,9 +887,10 @@ int launch_warp_bwd_tma(const float* U, const float* Hs, const float* d_out, con
                                    (p.ntx == s.gw * ((cell_w + p.TW - 1) / p.TW));
     if (!all_slots_written && cudaMemsetAsync(parts, 0, tma_bwd_workspace_bytes(s), st) != cudaSuccess)
         return set_error(MGW_ERR_CUDA, "memset parts: %s", cudaGetErrorString(cudaGetLastError()));
-    if (s.C == 1) return launch_bwd_c<1>(p, U, Hs, d_out, d_img, dU, parts, loss, st);
-    if (s.C == 3) return launch_bwd_c<3>(p, U, Hs, d_out, d_img, dU, parts, loss, st);
-    return launch_bwd_c<4>(p, U, Hs, d_out, d_img, dU, parts, loss, st);
+    if (!all_slots_written) behind_own_fill = false;          // the memset sits between the fill and us
+    if (s.C == 1) return launch_bwd_c<1>(p, U, Hs, d_out, d_img, dU, parts, loss, st, behind_own_fill);
+    if (s.C == 3) return launch_bwd_c<3>(p, U, Hs, d_out, d_img, dU, parts, loss, st, behind_own_fill);
+    return launch_bwd_c<4>(p, U, Hs, d_out, d_img, dU, parts, loss, st, behind_own_fill);
 }
 
 }  // namespace mgw
