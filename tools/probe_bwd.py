@@ -15,8 +15,8 @@ out, black, img, Hs = ops.mesh_warp_fwd(U, th)
 dU_buf = torch.empty_like(U)
 flush = torch.empty(64 * 1024 * 1024, device=dev)
 buf = (ctypes.c_ulonglong * 16)()
-names = ['setup + gradient loads issued', 'source box / zero / max (waits for the gradient loads)', 'barrier 1', 'scale', 'wait for the TMA box',
-         'pixel loop', 'dH shuffles', 'barrier 2', 'convert', 'barrier 3', 'TMA reduce issue + read wait']
+names = ['gradients staged by TMA: CTA barrier + wait + copy to registers', 'max|d_out|, barrier, zero the accumulator', 'barrier 1', 'scale',
+         'wait for the TMA box of U', 'pixel loop', 'dH shuffles', 'barrier 2', 'drain: fixed point -> fp32 -> red.global.add.v4.f32', '(unused)', '(unused)']
 for rep in range(3):
     flush.zero_()
     lib.mgw_debug_probe(buf, 1)
@@ -25,5 +25,5 @@ for rep in range(3):
     ctas = buf[15]
     tot = sum(buf[i] for i in range(14))
     print('rep %d: %d CTAs, mean lifetime %.0f cycles' % (rep, ctas, tot / max(ctas, 1)))
-    for i, nm in [(11, 'barrier init'), (12, 'tile decode'), (13, 'Hs loads issued')] + list(enumerate(names)):
+    for i, nm in [(11, 'barrier init, gradient TMA requests (thread 0)'), (12, 'tile decode'), (13, 'Hs loads; warp 0: source box + TMA box request')] + list(enumerate(names)):
         print('  %-58s %7.0f cycles  %5.1f %%' % (nm, buf[i] / max(ctas, 1), 100.0 * buf[i] / max(tot, 1)))
