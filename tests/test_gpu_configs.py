@@ -446,6 +446,52 @@ def test_double_buffered_dU_pipeline(mgw):
             check_step(i)
 
 
+@pytest.mark.parametrize('sigma', [0.05, 0.3])
+def test_backward_next_to_its_own_zero_fill(mgw, sigma):
+    """mgw_mesh_warp_bwd zero-fills dU itself and launches the tile backward PROGRAMMATICALLY behind that fill: the kernel runs next to
+    the fill up to its first access to dU (griddepcontrol.wait before the drain; before the loop on the general path, which
+    sigma = 0.3 exercises).  At config #2's size the fill takes ~10 us, so a missing wait would let reductions land in a buffer that
+    is zeroed afterwards or still holds garbage: dU is pre-filled with NaN before every call and must come out equal to the
+    accumulate-into-zeros form (no fill inside the call, plain launch), eager back to back and as a replayed CUDA graph.
+    (Checked once by mutation: a build WITHOUT the two waits passes this test as well -- the fill sweeps the buffer in address order
+    and stays ahead of the tiles, which run in the same order -- so the test guards the call sequence and the NaN-prefilled buffer,
+    while the guarantee itself is the griddepcontrol.wait in mgw_warp_tma.cu.)"""
+    mgw.set_impl('auto')
+    n, h, w, c = 32, 288, 512, 3
+    U = dev(synth.noise_image(n, h, w, c, 700)); th = dev(synth.random_mesh(n, 4, 4, sigma, 701))
+    g = dev(synth.randn((n, h, w, c), 702)); gi = dev(synth.randn((n, h, w, 2), 703, 0.1))
+    _, _, _, Hs = mgw.ops.mesh_warp_fwd(U, th)
+    ref = torch.zeros_like(U)
+    _, dth_ref = mgw.ops.mesh_warp_bwd(U, th, Hs, g, gi, accumulate_into=ref)
+    torch.cuda.synchronize()
+    scale = float(ref.abs().max())
+    buf = torch.empty_like(U)
+
+    def run():
+        buf.fill_(float('nan'))
+        return mgw.ops.mesh_warp_bwd(U, th, Hs, g, gi, dU_out=buf)
+
+    def check(dth):
+        torch.cuda.synchronize()
+        assert torch.isfinite(buf).all()
+        assert float((buf - ref).abs().max()) <= 2e-6 * scale        # same kernels, same data: fp32 order of the tiles' reductions only
+        assert torch.equal(dth, dth_ref)
+
+    for _ in range(4):
+        _, dth = run()
+        check(dth)
+    s_cap = torch.cuda.Stream()
+    s_cap.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s_cap):
+        gr = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(gr, stream=s_cap):
+            _, dth_g = run()
+    torch.cuda.current_stream().wait_stream(s_cap)
+    for _ in range(4):
+        gr.replay()
+        check(dth_g)
+
+
 @pytest.mark.parametrize('n,gh,gw', [(3, 12, 12), (2, 16, 20), (5, 1, 1), (33, 3, 7)])
 def test_solve_kernels_on_large_and_odd_grids(mgw, n, gh, gw):
     """K1 / K4 beyond the 4 x 4 mesh: more cells per sample than K4's block has threads (its per-cell loop runs more than once),
