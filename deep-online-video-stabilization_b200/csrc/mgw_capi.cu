@@ -177,9 +177,10 @@ static int warp_bwd_core(const float* U, const float* Hs, const float* d_out, co
     const bool tma_ok = mode != 1 && workspace && tma_bwd_supported(s) && aligned(U, 16) && (!dU || aligned(dU, 16)) &&
                         (!d_img || aligned(d_img, 8));
     // the persistent pipeline serves the calls that want dU (modes auto / pipe); dH-only calls and mode 2 take the tile kernels
-    // auto takes the one-tile-per-CTA backward: on one GPU the two families are equally fast (73 us at config #2), but the tile
-    // kernel's 3072 short CTAs share the SMs gracefully with a concurrent NCCL kernel, while a CTA of the persistent pipeline
-    // that starts late finishes late (2 GPUs: 141 vs 146 us per step).  MGW_IMPL=pipe or MGW_BWD=pipe selects the pipeline.
+    // auto takes the one-tile-per-CTA backward: 61-63 us at config #2 against the pipeline's 77 (they were equally fast until the
+    // tile kernel got its gradients by TMA and its drain by vector reductions), and its 3072 short CTAs share the SMs gracefully
+    // with a concurrent NCCL kernel, while a CTA of the persistent pipeline that starts late finishes late.
+    // MGW_IMPL=pipe or MGW_BWD=pipe selects the pipeline.
     static const bool prefer_pipe = [] { const char* v = getenv("MGW_BWD"); return v && v[0] == 'p'; }();
     // (a fused img_loss with a second gradient on `output` is served by the tile kernels)
     const bool pipe_ok = mode != 1 && mode != 2 && (prefer_pipe || mode == 3) && dU && workspace && pipe_bwd_supported(s) && aligned(U, 16) && aligned(dU, 16) &&
