@@ -7,13 +7,18 @@
 //             SASS UTMALDG) of the source bounding box while all threads compute the per-pixel projective map; the
 //             bilinear gather reads shared memory; out / x_map,y_map / black_pix are staged in shared memory and
 //             leave by TMA stores (UTMASTG).
-//   backward: the same source box of U plus the d_out / d_img tiles arrive by TMA.  dU is pre-accumulated in a
-//             shared-memory box in FIXED POINT with native integer shared atomics (ATOMS.ADD, ~1 cycle per warp
-//             instruction measured on B200, against ~4-6 cycles and a serialising ~300-cycle round trip for the CAS
-//             loop behind atomicAdd(float*)); the scale is a power of two chosen per tile from max|d_out| so the
-//             quantum is 2^-22 of that maximum (fp32-grade) with 9 bits of headroom for coincident taps.  The box is
-//             converted back to fp32 and leaves by ONE TMA reduce-add (cp.reduce.async.bulk.tensor, UTMAREDG: L2
-//             atomics at line granularity).  The 8 dH terms are reduced warp-shuffle -> shared -> one deterministic
+//   backward: the same source box of U by TMA, requested before anything else; in the plain variant (dU wanted, no fused loss)
+//             the tile's d_out / d_img arrive by TMA too, into the accumulator box before it is zeroed (as 24 strided LDGs
+//             per thread they queued in the LSU for thousands of cycles).  dU is pre-accumulated in a shared-memory box in
+//             FIXED POINT with native integer shared atomics (ATOMS.ADD, ~1 cycle per warp instruction measured on B200,
+//             against ~4-6 cycles and a serialising ~300-cycle round trip for the CAS loop behind atomicAdd(float*)); the
+//             scale is a power of two chosen per tile from max|d_out|, kBits = 31 - ceil(log2(TH*TW)) <= 22 bits per term,
+//             so the int32 sums provably cannot overflow.  The box leaves as fp32 by 16-byte reductions
+//             (red.global.add.v4.f32, REDG; all-zero groups skipped) straight from the fixed-point words -- no conversion
+//             back into shared memory, no third barrier, no TMA read wait before the CTA exits (MGW_BWD_DRAIN_RED=0 brings
+//             the round-1 drain back: ONE TMA reduce-add of the converted box, cp.reduce.async.bulk.tensor / UTMAREDG).
+//             Launched programmatically behind the library's zero-fill of dU, the kernel runs next to it up to its first
+//             access to dU (griddepcontrol.wait).  The 8 dH terms are reduced warp-shuffle -> shared -> one deterministic
 //             partial per tile (no global atomics).
 // Every tap is checked against the staged box; taps outside it (folded cells, extreme magnification, far
 // out-of-range pixels) and weights outside [-1,1] fall back to global loads / global fp32 atomics, so results never
