@@ -383,7 +383,11 @@ int launch_fill_zero(void* p, size_t bytes, bool keep_in_l2, cudaStream_t st)
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    const size_t want = (n16 + 63) / 64, cap = (size_t)sms * 16;
+    // 24 blocks of 64 threads per SM: measured next to the tile backward that now starts under the fill (step at config #2 with
+    // 4 / 8 / 16 / 24 / 32 blocks per SM: 131.7 / 118.1 / 109.6 / 108.3 / 108.7 us)
+    size_t per_sm = 24;
+    if (const char* e = getenv("MGW_FILL_BLOCKS_PER_SM")) { const int v = atoi(e); if (v > 0) per_sm = (size_t)v; }      // tuning aid
+    const size_t want = (n16 + 63) / 64, cap = (size_t)sms * per_sm;
     const unsigned grid = (unsigned)(want < cap ? want : cap);
     const cudaError_t e = keep_in_l2 ? launch_ex(fill_zero_kernel<true>, dim3(grid), dim3(64), 0, st, pdl_enabled(), reinterpret_cast<uint4*>(p), n16)
                                      : launch_ex(fill_zero_kernel<false>, dim3(grid), dim3(64), 0, st, pdl_enabled(), reinterpret_cast<uint4*>(p), n16);
